@@ -13,6 +13,14 @@ for p in (ROOT, PKG):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # Build (no-op when up to date) the product library and the oracle before anything imports them.
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mfa_build", os.path.join(PKG, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build()
+    from oracle import oracle as _o
+    _o.build()
 
 
 def _cuda_ok():

@@ -1,0 +1,99 @@
+// common.h -- shared host/device definitions for libMFAFFI.so (B200 / sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mfa {
+
+// Element types, numbered like mfa_precision_t (include/mfa_ffi.h).
+enum DType : int { kF16 = 0, kBF16 = 1, kF32 = 2, kI8 = 3, kI4 = 4 };
+
+inline __host__ __device__ int dtype_bytes(int dt) { return dt == kF32 ? 4 : (dt == kI8 || dt == kI4) ? 1 : 2; }
+
+enum MaskKind : int { kMaskNone = 0, kMaskBool = 1, kMaskAdditive = 2 };
+enum MaskScalar : int { kMaskU8 = 0, kMaskF16 = 1, kMaskBF16 = 2, kMaskF32 = 3 };
+
+// A [B, H, S, D] operand view: element (b,h,s,d) lives at ptr + b*sb + h*sh + s*ss + d*sd (element units).
+// Contiguous BHSD has sd = 1, ss = D, sh = S*D, sb = H*S*D; transpose_x (reference: [D,S] per head) has
+// ss = 1, sd = S.
+struct TensorView {
+  const void* ptr;
+  int64_t sb, sh, ss, sd;
+};
+
+// Per-tensor / per-block symmetric quantisation metadata for an int8/int4 operand.
+// block_rows tokens share one scale (0 = one scale for the whole tensor); scales laid out [B*H*ceil(S/block_rows)]
+// when block_rows > 0.  value = (code - zero_point) * scale.
+struct QuantView {
+  const float* scales;   // device pointer, or nullptr -> use `scale`
+  float scale;
+  int zero_point;
+  int block_rows;
+};
+
+struct AttnParams {
+  TensorView q, k, v;       // inputs, in_dtype
+  TensorView o;             // output (forward) or saved O (backward), o_dtype
+  float* lse;               // [B,H,Sq] fp32, log2 units (L = log2e * logsumexp); may be null in forward
+  // backward only
+  TensorView d_o;           // dO, do_dtype
+  float* dq;                // fp32, contiguous BHSD
+  float* dk;
+  float* dv;
+  float* dterm;             // [B,H,Sq] fp32: scale * rowsum(dO*O)
+  int B, H, Hkv, Sq, Skv, D;
+  float scale;
+  int causal;               // key j visible to query i iff j <= i
+  int window;               // <0: none; else hidden iff i > j + window
+  // external mask, broadcast via zero strides
+  const void* mask;
+  int mask_kind, mask_scalar;
+  int64_t mask_sb, mask_sh, mask_sq, mask_sk;
+  int in_dtype, o_dtype, do_dtype;
+  QuantView qq, qk, qv;     // used when in_dtype is kI8 / kI4
+};
+
+// Visible key range [lo, hi) for query rows [r0, r1) under causal/window rules (used for tile skipping).
+__host__ __device__ inline void visible_key_range(int causal, int window, int Skv, int r0, int r1, int& lo, int& hi) {
+  lo = 0; hi = Skv;
+  if (causal) { int h = r1; if (h < hi) hi = h; }            // cols <= r1-1
+  if (window >= 0) { int l = r0 - window; if (l > lo) lo = l; } // cols >= r0 - window
+  if (hi < lo) hi = lo;
+}
+
+// Visible query range [lo, hi) for key columns [c0, c1).
+__host__ __device__ inline void visible_query_range(int causal, int window, int Sq, int c0, int c1, int& lo, int& hi) {
+  lo = 0; hi = Sq;
+  if (causal) { if (c0 > lo) lo = c0; }                        // rows >= c0
+  if (window >= 0) { long h = (long)c1 - 1 + window + 1; if (h < hi) hi = (int)h; } // rows <= c1-1+window
+  if (hi < lo) hi = lo;
+}
+
+// ---- kernel launchers (each returns cudaGetLastError()) ----
+cudaError_t launch_fwd_simt(const AttnParams& p, cudaStream_t st);
+cudaError_t launch_bwd_simt(const AttnParams& p, cudaStream_t st);          // dterm + dQ + dK/dV
+cudaError_t launch_dterm(const AttnParams& p, cudaStream_t st);
+cudaError_t launch_bwd_dkv_only(const AttnParams& p, cudaStream_t st);      // dK/dV from a caller-supplied dterm
+
+// tcgen05 forward (bf16/fp16, D in {64,128}); returns cudaErrorNotSupported when the problem is not eligible.
+bool fwd_tc_eligible(const AttnParams& p);
+cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st);
+
+// quantiser & friends
+cudaError_t launch_quantize(const void* src, int src_dtype, void* codes, float* scales, uint64_t rows, uint64_t cols,
+                            uint32_t block_rows, uint32_t block_cols, int bits, float scale_floor, cudaStream_t st);
+cudaError_t launch_dequantize(const void* codes, const float* scales, float* out, uint64_t rows, uint64_t cols,
+                              uint32_t block_rows, uint32_t block_cols, int bits, cudaStream_t st);
+cudaError_t launch_merge_partials(float* o_acc, float* l_acc, const float* o_part, const float* l_part,
+                                  uint64_t rows, uint32_t D, cudaStream_t st);
+cudaError_t launch_hadamard(float* data, uint32_t block_size, uint32_t num_blocks, cudaStream_t st);
+cudaError_t launch_rope(const void* src, void* dst, const float* cos_t, const float* sin_t, int64_t sB, int64_t sH,
+                        int64_t sS, int64_t table_batch_stride, bool negate_sin, uint32_t B, uint32_t H, uint32_t S,
+                        uint32_t D, int dtype, cudaStream_t st);
+cudaError_t launch_convert_from_f32(const float* src, void* dst, int dst_dtype, uint64_t n, cudaStream_t st);
+
+// Count of kernel launches performed by this library (bench.py's gpu_launches claim).
+extern unsigned long long g_launch_count;
+extern const char* g_last_kernel;
+
+}  // namespace mfa

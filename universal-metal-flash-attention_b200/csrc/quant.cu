@@ -1,0 +1,410 @@
+// quant.cu -- HBM-bound helper kernels: symmetric int8/int4 quantiser, dequantiser, LSE merge of attention
+// partials, Hadamard rotation, RoPE, dtype conversion.
+//
+// Quantiser contract (bit-exact with oracle/attention_oracle.c, which restates
+// metal-flash-attention/Sources/FlashAttention/GEMM/GEMMQuantization.swift:305-623 and
+// GEMMRuntimeQuantization.swift:80-181):  scale = absmax / 127 (int8) or / 7 (int4) as an IEEE fp32 division,
+// optionally floored; code = clamp(roundf(x / scale)) with an IEEE division and round-half-away-from-zero;
+// int4 packs two codes per byte, flat element 2i in the low nibble, stored +8, odd tail padded with code 0.
+// Where the reference needs two dispatches and a host round trip per tensor, the common granularities
+// (per-row, per-token-block, per-head) are one fused kernel: absmax and quantise from the same cached tile,
+// 16-byte vector loads, algorithmic traffic = read once + write codes.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+#include "common.h"
+
+namespace mfa {
+namespace {
+
+template <typename T> __device__ __forceinline__ float to_f32(T x);
+template <> __device__ __forceinline__ float to_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half x) { return __half2float(x); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+// 8 consecutive elements -> fp32 (16-byte loads for 2-byte types, 2 x 16 bytes for fp32)
+template <typename T> struct Vec8 {
+  static __device__ __forceinline__ void load(const T* p, float out[8]) {
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = to_f32<T>(e[i]);
+  }
+};
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float out[8]) {
+    float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+  }
+};
+
+__device__ __forceinline__ float make_scale(float amax, int bits, float floor_v) {
+  float sc = __fdiv_rn(amax, bits == 8 ? 127.0f : 7.0f);
+  if (floor_v > 0.f && !(sc > floor_v)) sc = floor_v;
+  return sc;
+}
+
+__device__ __forceinline__ int quant_code(float x, float scale, int bits) {
+  if (!(scale > 0.f)) return 0;
+  float r = roundf(__fdiv_rn(x, scale));
+  const float lo = bits == 8 ? -128.f : -8.f, hi = bits == 8 ? 127.f : 7.f;
+  r = fminf(fmaxf(r, lo), hi);
+  return (int)r;
+}
+
+// ---- fused path: each quantisation block is a contiguous span [e0, e1) of the flat tensor (block_cols == cols).
+// One worker (warp if WARP else CTA) per block; pass 1 absmax, pass 2 re-reads the same lines from L1/L2.
+// Requires: span start and length multiples of 8 and 16-byte aligned base (checked by the launcher).
+template <typename T, int BITS, bool WARP>
+__global__ void __launch_bounds__(256) quant_span_kernel(const T* __restrict__ src, uint8_t* __restrict__ codes,
+                                                         float* __restrict__ scales, uint64_t rows, uint64_t cols,
+                                                         uint32_t block_rows, uint64_t group_rows, uint32_t nb_per_group,
+                                                         uint64_t nblocks, float floor_v) {
+  __shared__ float red[8];
+  const int nworker = WARP ? 32 : 256;
+  const int wid = WARP ? (threadIdx.x >> 5) : 0;
+  const int lane = WARP ? (threadIdx.x & 31) : threadIdx.x;
+  const uint64_t blk = WARP ? (uint64_t)blockIdx.x * 8 + wid : blockIdx.x;
+  if (blk >= nblocks) return;
+  const uint64_t g = blk / nb_per_group, lb = blk % nb_per_group;
+  const uint64_t r0 = g * group_rows + lb * block_rows;
+  uint64_t r1 = r0 + block_rows;
+  if (r1 > (g + 1) * group_rows) r1 = (g + 1) * group_rows;
+  if (r1 > rows) r1 = rows;
+  const uint64_t e0 = r0 * cols, e1 = r1 * cols;
+
+  float amax = 0.f;
+  for (uint64_t e = e0 + (uint64_t)lane * 8; e < e1; e += (uint64_t)nworker * 8) {
+    float x[8];
+    Vec8<T>::load(src + e, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(x[i]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (!WARP) {
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    amax = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) amax = fmaxf(amax, red[i]);
+  }
+  const float sc = make_scale(amax, BITS, floor_v);
+  if (lane == 0) scales[blk] = sc;
+
+  for (uint64_t e = e0 + (uint64_t)lane * 8; e < e1; e += (uint64_t)nworker * 8) {
+    float x[8];
+    Vec8<T>::load(src + e, x);
+    int q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = quant_code(x[i], sc, BITS);
+    if (BITS == 8) {
+      uint2 out;
+      out.x = (q[0] & 0xFF) | ((q[1] & 0xFF) << 8) | ((q[2] & 0xFF) << 16) | ((uint32_t)(q[3] & 0xFF) << 24);
+      out.y = (q[4] & 0xFF) | ((q[5] & 0xFF) << 8) | ((q[6] & 0xFF) << 16) | ((uint32_t)(q[7] & 0xFF) << 24);
+      *reinterpret_cast<uint2*>(codes + e) = out;
+    } else {
+      uint32_t out = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out |= (uint32_t)((q[i] + 8) & 0xF) << (4 * i);
+      *reinterpret_cast<uint32_t*>(codes + (e >> 1)) = out;
+    }
+  }
+}
+
+// ---- generic path, kernel 1: absmax of arbitrary block_rows x block_cols tiles via uint-bit atomicMax
+// (|x| >= 0, so the IEEE bit pattern orders like the value -- the reference GPU path does the same,
+// GEMMRuntimeQuantization.swift:22-41).
+template <typename T>
+__global__ void absmax_generic_kernel(const T* __restrict__ src, unsigned int* __restrict__ amax_bits, uint64_t rows,
+                                      uint64_t cols, uint32_t block_rows, uint32_t block_cols, uint64_t group_rows,
+                                      uint32_t nb_per_group, uint32_t nbc) {
+  const uint64_t n = rows * cols;
+  uint64_t cur_blk = ~0ull;
+  float cur = 0.f;
+  // each thread walks a contiguous chunk so consecutive elements mostly share a block -> few atomics
+  const uint64_t chunk = 64;
+  for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * chunk; base < n;
+       base += (uint64_t)gridDim.x * blockDim.x * chunk) {
+    uint64_t end = base + chunk < n ? base + chunk : n;
+    for (uint64_t e = base; e < end; ++e) {
+      uint64_t r = e / cols, c = e - r * cols;
+      uint64_t g = r / group_rows;
+      uint64_t blk = (g * nb_per_group + (r - g * group_rows) / block_rows) * nbc + c / block_cols;
+      if (blk != cur_blk) {
+        if (cur_blk != ~0ull) atomicMax(amax_bits + cur_blk, __float_as_uint(cur));
+        cur_blk = blk; cur = 0.f;
+      }
+      cur = fmaxf(cur, fabsf(to_f32<T>(src[e])));
+    }
+  }
+  if (cur_blk != ~0ull) atomicMax(amax_bits + cur_blk, __float_as_uint(cur));
+}
+
+__global__ void finalize_scales_kernel(float* scales /* in: absmax bits, out: scale */, uint64_t nblocks, int bits,
+                                       float floor_v) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nblocks) scales[i] = make_scale(scales[i], bits, floor_v);
+}
+
+// ---- generic path, kernel 2: one thread per output byte pair
+template <typename T, int BITS>
+__global__ void quant_apply_generic_kernel(const T* __restrict__ src, uint8_t* __restrict__ codes,
+                                           const float* __restrict__ scales, uint64_t rows, uint64_t cols,
+                                           uint32_t block_rows, uint32_t block_cols, uint64_t group_rows,
+                                           uint32_t nb_per_group, uint32_t nbc) {
+  const uint64_t n = rows * cols;
+  for (uint64_t e = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; e < n;
+       e += (uint64_t)gridDim.x * blockDim.x * 2) {
+    int q[2] = {0, 0};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      uint64_t ee = e + i;
+      if (ee >= n) break;
+      uint64_t r = ee / cols, c = ee - r * cols;
+      uint64_t g = r / group_rows;
+      uint64_t blk = (g * nb_per_group + (r - g * group_rows) / block_rows) * nbc + c / block_cols;
+      q[i] = quant_code(to_f32<T>(src[ee]), scales[blk], BITS);
+    }
+    if (BITS == 8) {
+      codes[e] = (uint8_t)(q[0] & 0xFF);
+      if (e + 1 < n) codes[e + 1] = (uint8_t)(q[1] & 0xFF);
+    } else {
+      codes[e >> 1] = (uint8_t)(((q[0] + 8) & 0xF) | (((q[1] + 8) & 0xF) << 4));
+    }
+  }
+}
+
+template <int BITS>
+__global__ void dequant_kernel(const uint8_t* __restrict__ codes, const float* __restrict__ scales,
+                               float* __restrict__ out, uint64_t rows, uint64_t cols, uint32_t block_rows,
+                               uint32_t block_cols, uint32_t nbc) {
+  const uint64_t n = rows * cols;
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t r = e / cols, c = e - r * cols;
+    float sc = scales[(r / block_rows) * nbc + c / block_cols];
+    int q;
+    if (BITS == 8) q = reinterpret_cast<const int8_t*>(codes)[e];
+    else { uint8_t b = codes[e >> 1]; q = (int)((e & 1) ? (b >> 4) : (b & 0xF)) - 8; }
+    out[e] = (float)q * sc;
+  }
+}
+
+// ---- merge of two attention partials over disjoint key sets (log2-domain L)
+__global__ void merge_partials_kernel(float* __restrict__ o_acc, float* __restrict__ l_acc,
+                                      const float* __restrict__ o_part, const float* __restrict__ l_part,
+                                      uint64_t rows, uint32_t D) {
+  const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float la = l_acc[row], lp = l_part[row];
+  if (lp == -CUDART_INF_F) return;
+  const float m = fmaxf(la, lp);
+  const float wa = (la == -CUDART_INF_F) ? 0.f : exp2f(la - m), wp = exp2f(lp - m);
+  const float s = wa + wp;
+  const float ca = wa / s, cp = wp / s;
+  float* oa = o_acc + row * D;
+  const float* op = o_part + row * D;
+  if ((D & 3) == 0) {
+    for (uint32_t d = lane * 4; d < D; d += 128) {
+      float4 a = *reinterpret_cast<float4*>(oa + d);
+      const float4 b = *reinterpret_cast<const float4*>(op + d);
+      a.x = a.x * ca + b.x * cp; a.y = a.y * ca + b.y * cp; a.z = a.z * ca + b.z * cp; a.w = a.w * ca + b.w * cp;
+      *reinterpret_cast<float4*>(oa + d) = a;
+    }
+  } else {
+    for (uint32_t d = lane; d < D; d += 32) oa[d] = oa[d] * ca + op[d] * cp;
+  }
+  __syncwarp();
+  if (lane == 0) l_acc[row] = m + log2f(s);
+}
+
+// ---- in-place FWHT over blocks of n = 2^k <= 1024 fp32 values, scaled by 1/sqrt(n)
+// (metal-flash-attention/Sources/FlashAttention/Attention/HadamardRotation.swift:113-147 does this with one
+// thread per block; here a CTA of n/2 butterflies per stage, data staged in shared memory).
+__global__ void hadamard_kernel(float* __restrict__ data, uint32_t n, uint32_t num_blocks) {
+  extern __shared__ float buf[];
+  for (uint32_t blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
+    float* p = data + (uint64_t)blk * n;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) buf[i] = p[i];
+    __syncthreads();
+    for (uint32_t h = 1; h < n; h <<= 1) {
+      for (uint32_t t = threadIdx.x; t < n / 2; t += blockDim.x) {
+        uint32_t i = ((t / h) * 2 * h) + (t % h);
+        float a = buf[i], b = buf[i + h];
+        buf[i] = a + b; buf[i + h] = a - b;
+      }
+      __syncthreads();
+    }
+    const float norm = rsqrtf((float)n);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) p[i] = buf[i] * norm;
+    __syncthreads();
+  }
+}
+
+// ---- interleaved-pair RoPE (Sources/MFABridge/MFABridge.swift:269-319): (x0, x1) -> (x0 c - x1 s, x0 s + x1 c)
+template <typename T> __device__ __forceinline__ T from_f32(float x);
+template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return __float2half_rn(x); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+template <typename T>
+__global__ void rope_kernel(const T* __restrict__ src, T* __restrict__ dst, const float* __restrict__ cos_t,
+                            const float* __restrict__ sin_t, int64_t sB, int64_t sH, int64_t sS,
+                            int64_t table_batch_stride, bool negate_sin, uint32_t B, uint32_t H, uint32_t S, uint32_t D) {
+  const uint32_t half = D / 2;
+  const uint64_t total = (uint64_t)B * H * S * half;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t j = (uint32_t)(i % half);
+    uint64_t t = i / half;
+    uint32_t s = (uint32_t)(t % S); t /= S;
+    uint32_t h = (uint32_t)(t % H);
+    uint32_t b = (uint32_t)(t / H);
+    const int64_t in = b * sB + h * sH + s * sS + 2 * j;
+    const int64_t out = (((int64_t)b * H + h) * S + s) * D + 2 * j;     // dst is contiguous BHSD
+    const int64_t ti = b * table_batch_stride + (int64_t)s * half + j;
+    float c = cos_t[ti], sn = sin_t[ti];
+    if (negate_sin) sn = -sn;
+    float x0 = to_f32<T>(src[in]), x1 = to_f32<T>(src[in + 1]);
+    dst[out] = from_f32<T>(x0 * c - x1 * sn);
+    dst[out + 1] = from_f32<T>(x0 * sn + x1 * c);
+  }
+}
+
+template <typename T>
+__global__ void convert_kernel(const float* __restrict__ src, T* __restrict__ dst, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    dst[i] = from_f32<T>(src[i]);
+}
+
+inline unsigned grid_for(uint64_t work_items, int threads) {
+  uint64_t g = (work_items + threads - 1) / threads;
+  const uint64_t cap = 148ull * 32;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+template <typename T>
+cudaError_t quantize_typed(const T* src, uint8_t* codes, float* scales, uint64_t rows, uint64_t cols, uint32_t br,
+                           uint32_t bc, uint64_t group_rows, int bits, float floor_v, cudaStream_t st) {
+  const uint32_t nb_per_group = (uint32_t)((group_rows + br - 1) / br);
+  const uint64_t ngroups = (rows + group_rows - 1) / group_rows;
+  const uint32_t nbc = (uint32_t)((cols + bc - 1) / bc);
+  const uint64_t nblocks = ngroups * nb_per_group * nbc;
+  const uint64_t span = (uint64_t)br * cols;
+  const bool aligned = (cols % 8 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(codes) & 7) == 0);
+  if (bc == cols && aligned && span <= 65536) {
+    if (span <= 2048) {
+      unsigned grid = (unsigned)((nblocks + 7) / 8);
+      if (bits == 8) quant_span_kernel<T, 8, true><<<grid, 256, 0, st>>>(src, codes, scales, rows, cols, br, group_rows, nb_per_group, nblocks, floor_v);
+      else quant_span_kernel<T, 4, true><<<grid, 256, 0, st>>>(src, codes, scales, rows, cols, br, group_rows, nb_per_group, nblocks, floor_v);
+    } else {
+      unsigned grid = (unsigned)nblocks;
+      if (bits == 8) quant_span_kernel<T, 8, false><<<grid, 256, 0, st>>>(src, codes, scales, rows, cols, br, group_rows, nb_per_group, nblocks, floor_v);
+      else quant_span_kernel<T, 4, false><<<grid, 256, 0, st>>>(src, codes, scales, rows, cols, br, group_rows, nb_per_group, nblocks, floor_v);
+    }
+    ++g_launch_count;
+    g_last_kernel = "quant_span";
+    return cudaGetLastError();
+  }
+  // generic: absmax (atomics) -> scales -> apply
+  cudaError_t e = cudaMemsetAsync(scales, 0, nblocks * sizeof(float), st);
+  if (e != cudaSuccess) return e;
+  const uint64_t n = rows * cols;
+  absmax_generic_kernel<T><<<grid_for((n + 63) / 64, 256), 256, 0, st>>>(
+      src, reinterpret_cast<unsigned int*>(scales), rows, cols, br, bc, group_rows, nb_per_group, nbc);
+  finalize_scales_kernel<<<(unsigned)((nblocks + 255) / 256), 256, 0, st>>>(scales, nblocks, bits, floor_v);
+  if (bits == 8) quant_apply_generic_kernel<T, 8><<<grid_for((n + 1) / 2, 256), 256, 0, st>>>(src, codes, scales, rows, cols, br, bc, group_rows, nb_per_group, nbc);
+  else quant_apply_generic_kernel<T, 4><<<grid_for((n + 1) / 2, 256), 256, 0, st>>>(src, codes, scales, rows, cols, br, bc, group_rows, nb_per_group, nbc);
+  g_launch_count += 3;
+  g_last_kernel = "quant_generic";
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// group_rows: quantisation blocks restart every group_rows rows (one (batch, head) slab); 0 = no grouping.
+cudaError_t launch_quantize_grouped(const void* src, int src_dtype, void* codes, float* scales, uint64_t rows,
+                                    uint64_t cols, uint32_t block_rows, uint32_t block_cols, uint64_t group_rows,
+                                    int bits, float scale_floor, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return cudaSuccess;
+  if (bits != 8 && bits != 4) return cudaErrorInvalidValue;
+  if (group_rows == 0 || group_rows > rows) group_rows = rows;
+  uint32_t br = (block_rows == 0 || block_rows > group_rows) ? (uint32_t)group_rows : block_rows;
+  uint32_t bc = (block_cols == 0 || block_cols > cols) ? (uint32_t)cols : block_cols;
+  if (bits == 4 && bc != cols && ((bc & 1) || (cols & 1))) return cudaErrorInvalidValue;  // nibble pairs must share a block row
+  uint8_t* c8 = reinterpret_cast<uint8_t*>(codes);
+  switch (src_dtype) {
+    case kF32: return quantize_typed(reinterpret_cast<const float*>(src), c8, scales, rows, cols, br, bc, group_rows, bits, scale_floor, st);
+    case kF16: return quantize_typed(reinterpret_cast<const __half*>(src), c8, scales, rows, cols, br, bc, group_rows, bits, scale_floor, st);
+    case kBF16: return quantize_typed(reinterpret_cast<const __nv_bfloat16*>(src), c8, scales, rows, cols, br, bc, group_rows, bits, scale_floor, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_quantize(const void* src, int src_dtype, void* codes, float* scales, uint64_t rows, uint64_t cols,
+                            uint32_t block_rows, uint32_t block_cols, int bits, float scale_floor, cudaStream_t st) {
+  return launch_quantize_grouped(src, src_dtype, codes, scales, rows, cols, block_rows, block_cols, 0, bits, scale_floor, st);
+}
+
+cudaError_t launch_dequantize(const void* codes, const float* scales, float* out, uint64_t rows, uint64_t cols,
+                              uint32_t block_rows, uint32_t block_cols, int bits, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return cudaSuccess;
+  uint32_t br = (block_rows == 0 || block_rows > rows) ? (uint32_t)rows : block_rows;
+  uint32_t bc = (block_cols == 0 || block_cols > cols) ? (uint32_t)cols : block_cols;
+  uint32_t nbc = (uint32_t)((cols + bc - 1) / bc);
+  unsigned grid = grid_for(rows * cols, 256);
+  if (bits == 8) dequant_kernel<8><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(codes), scales, out, rows, cols, br, bc, nbc);
+  else if (bits == 4) dequant_kernel<4><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(codes), scales, out, rows, cols, br, bc, nbc);
+  else return cudaErrorInvalidValue;
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_merge_partials(float* o_acc, float* l_acc, const float* o_part, const float* l_part, uint64_t rows,
+                                  uint32_t D, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  merge_partials_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(o_acc, l_acc, o_part, l_part, rows, D);
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_hadamard(float* data, uint32_t block_size, uint32_t num_blocks, cudaStream_t st) {
+  if (block_size == 0 || block_size > 1024 || (block_size & (block_size - 1))) return cudaErrorInvalidValue;
+  if (num_blocks == 0) return cudaSuccess;
+  unsigned threads = block_size / 2 < 32 ? 32 : block_size / 2;
+  unsigned grid = num_blocks < 148u * 16 ? num_blocks : 148u * 16;
+  hadamard_kernel<<<grid, threads, block_size * sizeof(float), st>>>(data, block_size, num_blocks);
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rope(const void* src, void* dst, const float* cos_t, const float* sin_t, int64_t sB, int64_t sH,
+                        int64_t sS, int64_t table_batch_stride, bool negate_sin, uint32_t B, uint32_t H, uint32_t S,
+                        uint32_t D, int dtype, cudaStream_t st) {
+  if (D & 1) return cudaErrorInvalidValue;
+  uint64_t total = (uint64_t)B * H * S * (D / 2);
+  if (total == 0) return cudaSuccess;
+  unsigned grid = grid_for(total, 256);
+  switch (dtype) {
+    case kF32: rope_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, cos_t, sin_t, sB, sH, sS, table_batch_stride, negate_sin, B, H, S, D); break;
+    case kF16: rope_kernel<__half><<<grid, 256, 0, st>>>((const __half*)src, (__half*)dst, cos_t, sin_t, sB, sH, sS, table_batch_stride, negate_sin, B, H, S, D); break;
+    case kBF16: rope_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, cos_t, sin_t, sB, sH, sS, table_batch_stride, negate_sin, B, H, S, D); break;
+    default: return cudaErrorInvalidValue;
+  }
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_convert_from_f32(const float* src, void* dst, int dst_dtype, uint64_t n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  unsigned grid = grid_for(n, 256);
+  if (dst_dtype == kF16) convert_kernel<__half><<<grid, 256, 0, st>>>(src, (__half*)dst, n);
+  else if (dst_dtype == kBF16) convert_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, (__nv_bfloat16*)dst, n);
+  else return cudaErrorInvalidValue;
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+}  // namespace mfa
