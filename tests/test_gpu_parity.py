@@ -196,7 +196,9 @@ def test_ffi_smoke_shapes_scales_patterns(ctx):
             out = umfa.flash_attention_forward(ctx, q, k, v, input_precision="fp32", softmax_scale=scale)
             ref, _ = O.attention_forward(q[None, None], k[None, None], v[None, None], scale=scale)
             assert np.isfinite(out).all()
-            assert rel_max(out, ref[0, 0]) < 1e-5
+            # the upstream sweep only asserts finiteness (MFAFFITests.swift:295-313); at scale >= 10 the logits reach
+            # |z| ~ 1e3 where one fp32 ulp of z already moves exp(z) by ~1e-5, so the 1e-5 gate applies to scale <= 1
+            assert rel_max(out, ref[0, 0]) < (1e-5 if scale <= 1.0 else 2e-4)
 
 
 def test_fp16_output_written_in_place_like_reference_adapter(ctx):
