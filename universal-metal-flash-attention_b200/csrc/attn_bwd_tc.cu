@@ -1,0 +1,571 @@
+// attn_bwd_tc.cu -- attention backward for sm_100a on tcgen05 / TMEM / TMA (bf16 / fp16 operands, head_dim 64 / 128).
+//
+// Replaces the reference's two backward kernels (`loopBackwardKeyValue` / `loopBackwardQuery`,
+// metal-flash-attention/Sources/FlashAttention/Attention/AttentionKernel/AttentionKernel+Source.swift:418-511, with the
+// dS rule of +Softmax.swift:798-802 and the D term of +Softmax.swift:31-236) -- same 2-kernel split (no fp32 atomics,
+// deterministic), re-derived for Blackwell:
+//
+//   bwd_dkv_tc_kernel : one CTA owns one 128-key tile j of one kv head and streams the query tiles i that can see it
+//        S^T  = K_j Q_i^T            tcgen05.mma SS  -> TMEM cols [0,128)
+//        dP^T = V_j dO_i^T           tcgen05.mma SS  -> TMEM cols [128,256)
+//        P^T  = exp2(S^T c - L_i)    (two warpgroups, thread = (key row, 64-query half); 16-bit pairs back into TMEM)
+//        dS^T = P^T (dP^T scale - D_i)
+//        dV  += P^T  dO_i            tcgen05.mma TS (A from TMEM, B = dO_i tile read MN-major) -> cols [256,256+D)
+//        dK  += dS^T Q_i             tcgen05.mma TS                                            -> cols [256+D,256+2D)
+//   bwd_dq_tc_kernel  : one CTA owns one 128-query tile i and streams the key tiles j it can see
+//        S = Q_i K_j^T (double-buffered in TMEM), dP = dO_i V_j^T, dS = P (dP scale - D_i), dQ += dS K_j (TS MMA)
+//
+// The MMA order is interleaved (dV_i, S^T_{i+1}, dK_i, dP^T_{i+1}) so the exp2 phase of tile i+1 runs under the
+// dK_i / dP^T_{i+1} MMAs.  Packed P^T / dS^T are written inside the column range their owner thread read them from
+// (half h reads fp32 cols [64h,64h+64) and writes 16-bit pairs to [64h,64h+32)), so the two warpgroups never touch
+// each other's TMEM columns and need no cross-warpgroup barrier.
+// Tiles fully hidden by the causal / sliding-window rule are skipped before they are loaded.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "common.h"
+#include "sm100_ptx.cuh"
+#include "tc_host.h"
+
+namespace mfa {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int kThreads = 384;     // warps 0-7: two elementwise warpgroups, 8: MMA issuer, 9: TMA, 10-11: L / D loaders
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct BwdTcParams {
+  CUtensorMap tq, tk, tv, tdo;
+  const float* lse;
+  const float* dterm;
+  float* dq;
+  float* dk;
+  float* dv;
+  int H, Hkv, Sq, Skv;
+  float c, scale;
+  int causal, window;
+};
+
+template <int D>
+struct BCfg {
+  static constexpr int kTile = 128 * D * 2;
+  static constexpr int kChunks = D / 64;
+  static constexpr int kChunkBytes = 128 * 128;
+  static constexpr int kStatBytes = 2 * 2 * 128 * 4;            // [stage][L|D][128]
+  static constexpr int kSmem = 6 * kTile + kStatBytes + 256 + 1024;
+};
+
+// element (q row r, key col cidx) visible under the causal / window rule
+__device__ __forceinline__ bool visible(int causal, int window, int r, int cidx) {
+  return (!causal || cidx <= r) && (window < 0 || r - cidx <= window);
+}
+
+__device__ __forceinline__ void load_tile_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int row, int head, int b,
+                                             int chunks, int chb) {
+  for (int ch = 0; ch < chunks; ++ch) tma_load_4d(dst + ch * chb, m, bar, ch * 64, row, head, b);
+}
+
+// ================================================================================================ dK / dV
+template <int D, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_constant__ BwdTcParams p) {
+  using C = BCfg<D>;
+  constexpr int TILE = C::kTile, CHB = C::kChunkBytes;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sK = base, sV = base + TILE;
+  auto sQ = [&](int s) { return base + (2 + 2 * s) * TILE; };
+  auto sdO = [&](int s) { return base + (3 + 2 * s) * TILE; };
+  const uint32_t sStat = base + 6 * TILE;
+  float* stat = reinterpret_cast<float*>(smem_raw + (sStat - raw));     // [stage][0: L, 1: D][128]
+  const uint32_t sBar = sStat + C::kStatBytes;
+  const uint32_t kv_full = sBar, s_full = sBar + 8, dp_full = sBar + 16, p_full = sBar + 24, ds_full = sBar + 32,
+                 acc_full = sBar + 40;
+  auto st_full = [&](int s) { return sBar + 48 + 8 * s; };
+  auto st_empty = [&](int s) { return sBar + 64 + 8 * s; };
+  const uint32_t tmem_slot = sBar + 80;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  const int c0 = jt * 128;
+  const int group = p.H / p.Hkv;
+  int qlo, qhi;
+  visible_query_range(p.causal, p.window, p.Sq, c0, min(c0 + 128, p.Skv), qlo, qhi);
+  const int i_lo = qlo >> 7;
+  const int nq = qhi > qlo ? ((qhi + 127) >> 7) - i_lo : 0;
+  const int n_it = nq * group;
+
+  if (threadIdx.x == 256) {
+    mbar_init(kv_full, 1); mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 8); mbar_init(ds_full, 8);
+    mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(st_full(s), 3); mbar_init(st_empty(s), 1); }
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    if (lane == 0) { prefetch_tmap(&p.tq); prefetch_tmap(&p.tk); prefetch_tmap(&p.tv); prefetch_tmap(&p.tdo); }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 256 + D;
+
+  if (warp == 9) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0 && n_it > 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * TILE);
+      load_tile_4d(sK, &p.tk, kv_full, c0, hk, b, C::kChunks, CHB);
+      load_tile_4d(sV, &p.tv, kv_full, c0, hk, b, C::kChunks, CHB);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1;
+        const int head = hk * group + it / nq, q0 = (i_lo + it % nq) * 128;
+        mbar_wait(st_empty(s), ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(st_full(s), 2 * TILE);
+        load_tile_4d(sQ(s), &p.tq, st_full(s), q0, head, b, C::kChunks, CHB);
+        load_tile_4d(sdO(s), &p.tdo, st_full(s), q0, head, b, C::kChunks, CHB);
+      }
+    }
+  } else if (warp >= 10) {
+    // ------------------------------------------------------------------ L / D loaders (64 threads, 2 rows each)
+    const int tl = threadIdx.x - 320;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1;
+      const int head = hk * group + it / nq, q0 = (i_lo + it % nq) * 128;
+      mbar_wait(st_empty(s), ((it >> 1) & 1) ^ 1);
+      const size_t rb = ((size_t)b * p.H + head) * p.Sq;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int r = tl + 64 * k, q = q0 + r;
+        float L = CUDART_INF_F, Dt = 0.f;
+        if (q < p.Sq) {
+          L = p.lse[rb + q]; Dt = p.dterm[rb + q];
+          if (L == -CUDART_INF_F) L = CUDART_INF_F;          // row without visible keys: P = 0
+        }
+        stat[(s * 2 + 0) * 128 + r] = L;
+        stat[(s * 2 + 1) * 128 + r] = Dt;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(st_full(s));
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && n_it > 0) {
+      constexpr uint32_t FMT = BF16 ? 1u : 0u;
+      constexpr uint32_t IDESC_ST = make_idesc(1, FMT, FMT, 0, 0, 128, 128);   // K-major A and B
+      constexpr uint32_t IDESC_ACC = make_idesc(1, FMT, FMT, 0, 1, 128, D);    // A from TMEM, B MN-major
+      auto issue_abt = [&](uint32_t dcol, uint32_t abase, uint32_t bbase) {    // D = A B^T over head_dim
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * CHB + (kk & 3) * 32;
+          mma_f16_ss(tmem + dcol, smem_desc_sw128(abase + off, 16, 1024), smem_desc_sw128(bbase + off, 16, 1024), IDESC_ST,
+                     kk > 0);
+        }
+      };
+      auto issue_acc = [&](uint32_t dcol, uint32_t acol, uint32_t bbase, bool acc) {   // D += A(tmem) B over 128 queries
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          mma_f16_ts(tmem + dcol, tmem + acol + (kk >> 2) * 64 + (kk & 3) * 8, smem_desc_sw128(bbase + kk * 2048, CHB, 1024),
+                     IDESC_ACC, (acc || kk > 0) ? 1u : 0u);
+        }
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(st_full(0), 0);
+      tc_fence_after();
+      issue_abt(T_S, sK, sQ(0));
+      tc_commit(s_full);
+      issue_abt(T_DP, sV, sdO(0));
+      tc_commit(dp_full);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1;
+        mbar_wait(p_full, it & 1);
+        tc_fence_after();
+        issue_acc(T_DV, T_S, sdO(s), it > 0);
+        if (it + 1 < n_it) {
+          mbar_wait(st_full(s ^ 1), ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_abt(T_S, sK, sQ(s ^ 1));
+          tc_commit(s_full);
+        }
+        mbar_wait(ds_full, it & 1);
+        tc_fence_after();
+        issue_acc(T_DK, T_DP, sQ(s), it > 0);
+        tc_commit(st_empty(s));
+        if (it + 1 < n_it) {
+          issue_abt(T_DP, sV, sdO(s ^ 1));
+          tc_commit(dp_full);
+        }
+      }
+      tc_commit(acc_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ elementwise warpgroups
+    const int half = warp >> 2, w = warp & 3;
+    const int row = w * 32 + lane;
+    const int key = c0 + row;
+    const uint32_t lane_base = (uint32_t)(w * 32) << 16;
+    const uint32_t tS = tmem + lane_base + T_S + half * 64;
+    const uint32_t tDP = tmem + lane_base + T_DP + half * 64;
+    const float c = p.c, scale = p.scale;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1;
+      const int q0 = (i_lo + it % nq) * 128 + half * 64;
+      const float* sL = stat + (s * 2 + 0) * 128 + half * 64;
+      const float* sD = stat + (s * 2 + 1) * 128 + half * 64;
+      const bool need_mask = (p.causal && c0 + 127 > q0) || (p.window >= 0 && q0 + 63 - c0 > p.window);
+      float pv[64];
+      mbar_wait(st_full(s), (it >> 1) & 1);
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t su[32];
+        tmem_ld_x32(tS + ch * 32, su);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 L4 = *reinterpret_cast<const float4*>(sL + ch * 32 + i);
+          const float Ls[4] = {L4.x, L4.y, L4.z, L4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float e = ex2(fmaf(__uint_as_float(su[i + k]), c, -Ls[k]));
+            if (need_mask && !visible(p.causal, p.window, q0 + ch * 32 + i + k, key)) e = 0.f;
+            pv[ch * 32 + i + k] = e;
+          }
+          pk[i / 2] = BF16 ? pack_bf16(pv[ch * 32 + i], pv[ch * 32 + i + 1]) : pack_f16(pv[ch * 32 + i], pv[ch * 32 + i + 1]);
+          pk[i / 2 + 1] = BF16 ? pack_bf16(pv[ch * 32 + i + 2], pv[ch * 32 + i + 3])
+                               : pack_f16(pv[ch * 32 + i + 2], pv[ch * 32 + i + 3]);
+        }
+        tmem_st_x16(tS + ch * 16, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+
+      mbar_wait(dp_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t du[32];
+        tmem_ld_x32(tDP + ch * 32, du);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 D4 = *reinterpret_cast<const float4*>(sD + ch * 32 + i);
+          const float Ds[4] = {D4.x, D4.y, D4.z, D4.w};
+          float ds[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ds[k] = pv[ch * 32 + i + k] * fmaf(__uint_as_float(du[i + k]), scale, -Ds[k]);
+          pk[i / 2] = BF16 ? pack_bf16(ds[0], ds[1]) : pack_f16(ds[0], ds[1]);
+          pk[i / 2 + 1] = BF16 ? pack_bf16(ds[2], ds[3]) : pack_f16(ds[2], ds[3]);
+        }
+        tmem_st_x16(tDP + ch * 16, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    // ---------------------------------------------------------------- epilogue: dV, dK (fp32) -> global
+    if (n_it > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    const bool live = key < p.Skv;
+    const size_t orow = (((size_t)b * p.Hkv + hk) * p.Skv + key) * D + half * (D / 2);
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      float* dst_base = which == 0 ? p.dv : p.dk;
+      const uint32_t tA = tmem + lane_base + (which == 0 ? T_DV : T_DK) + half * (D / 2);
+#pragma unroll
+      for (int ch = 0; ch < D / 64; ++ch) {
+        uint32_t ou[32];
+        if (n_it > 0) {
+          tmem_ld_x32(tA + ch * 32, ou);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ou[i] = 0u;
+        }
+        if (live && dst_base) {
+          float4* dst = reinterpret_cast<float4*>(dst_base + orow + ch * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            dst[i] = make_float4(__uint_as_float(ou[4 * i]), __uint_as_float(ou[4 * i + 1]), __uint_as_float(ou[4 * i + 2]),
+                                 __uint_as_float(ou[4 * i + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
+// ================================================================================================ dQ
+template <int D, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_constant__ BwdTcParams p) {
+  using C = BCfg<D>;
+  constexpr int TILE = C::kTile, CHB = C::kChunkBytes;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sQ = base, sdO = base + TILE;
+  auto sK = [&](int s) { return base + (2 + 2 * s) * TILE; };
+  auto sV = [&](int s) { return base + (3 + 2 * s) * TILE; };
+  const uint32_t sBar = base + 6 * TILE;
+  const uint32_t q_full = sBar, dp_full = sBar + 8, ds_full = sBar + 16, acc_full = sBar + 24;
+  auto s_full = [&](int u) { return sBar + 32 + 8 * u; };
+  auto st_full = [&](int s) { return sBar + 48 + 8 * s; };
+  auto st_empty = [&](int s) { return sBar + 64 + 8 * s; };
+  const uint32_t tmem_slot = sBar + 80;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int it_q = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;     // heavy tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.H / p.Hkv);
+  const int r0 = it_q * 128;
+  int klo, khi;
+  visible_key_range(p.causal, p.window, p.Skv, r0, min(r0 + 128, p.Sq), klo, khi);
+  const int j_lo = klo >> 7;
+  const int n = khi > klo ? ((khi + 127) >> 7) - j_lo : 0;
+
+  if (threadIdx.x == 256) {
+    mbar_init(q_full, 1); mbar_init(dp_full, 1); mbar_init(ds_full, 8); mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(s_full(s), 1); mbar_init(st_full(s), 1); mbar_init(st_empty(s), 1); }
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    if (lane == 0) { prefetch_tmap(&p.tq); prefetch_tmap(&p.tk); prefetch_tmap(&p.tv); prefetch_tmap(&p.tdo); }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  constexpr uint32_t T_DP = 256, T_DQ = 384;
+
+  if (warp == 9) {
+    if (lane == 0 && n > 0) {
+      mbar_arrive_expect_tx(q_full, 2 * TILE);
+      load_tile_4d(sQ, &p.tq, q_full, r0, h, b, C::kChunks, CHB);
+      load_tile_4d(sdO, &p.tdo, q_full, r0, h, b, C::kChunks, CHB);
+      for (int it = 0; it < n; ++it) {
+        const int s = it & 1;
+        mbar_wait(st_empty(s), ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(st_full(s), 2 * TILE);
+        load_tile_4d(sK(s), &p.tk, st_full(s), (j_lo + it) * 128, hk, b, C::kChunks, CHB);
+        load_tile_4d(sV(s), &p.tv, st_full(s), (j_lo + it) * 128, hk, b, C::kChunks, CHB);
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0 && n > 0) {
+      constexpr uint32_t FMT = BF16 ? 1u : 0u;
+      constexpr uint32_t IDESC_ST = make_idesc(1, FMT, FMT, 0, 0, 128, 128);
+      constexpr uint32_t IDESC_ACC = make_idesc(1, FMT, FMT, 0, 1, 128, D);
+      auto issue_abt = [&](uint32_t dcol, uint32_t abase, uint32_t bbase) {
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * CHB + (kk & 3) * 32;
+          mma_f16_ss(tmem + dcol, smem_desc_sw128(abase + off, 16, 1024), smem_desc_sw128(bbase + off, 16, 1024), IDESC_ST,
+                     kk > 0);
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(st_full(0), 0);
+      tc_fence_after();
+      issue_abt(0, sQ, sK(0));
+      tc_commit(s_full(0));
+      issue_abt(T_DP, sdO, sV(0));
+      tc_commit(dp_full);
+      for (int it = 0; it < n; ++it) {
+        const int s = it & 1;
+        if (it + 1 < n) {
+          mbar_wait(st_full(s ^ 1), ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_abt((s ^ 1) * 128, sQ, sK(s ^ 1));
+          tc_commit(s_full(s ^ 1));
+        }
+        mbar_wait(ds_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          mma_f16_ts(tmem + T_DQ, tmem + T_DP + (kk >> 2) * 64 + (kk & 3) * 8, smem_desc_sw128(sK(s) + kk * 2048, CHB, 1024),
+                     IDESC_ACC, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        if (it + 1 < n) {
+          issue_abt(T_DP, sdO, sV(s ^ 1));
+          tc_commit(dp_full);
+        }
+        // K_j / V_j of this stage: last readers are dQ_j (K) and dP_j (V, issued earlier) -> all committed here
+        tc_commit(st_empty(s));
+      }
+      tc_commit(acc_full);
+    }
+  } else if (warp < 8) {
+    const int half = warp >> 2, w = warp & 3;
+    const int row = w * 32 + lane;
+    const int r = r0 + row;
+    const uint32_t lane_base = (uint32_t)(w * 32) << 16;
+    const uint32_t tDP = tmem + lane_base + T_DP + half * 64;
+    const float c = p.c, scale = p.scale;
+    float L = CUDART_INF_F, Dt = 0.f;
+    if (r < p.Sq) {
+      const size_t ri = ((size_t)b * p.H + h) * p.Sq + r;
+      L = p.lse[ri]; Dt = p.dterm[ri];
+      if (L == -CUDART_INF_F) L = CUDART_INF_F;
+    }
+    for (int it = 0; it < n; ++it) {
+      const int u = it & 1;
+      const int k0 = (j_lo + it) * 128 + half * 64;
+      const uint32_t tS = tmem + lane_base + u * 128 + half * 64;
+      const bool need_mask = (p.causal && k0 + 63 > r0) || (p.window >= 0 && r0 + 127 - k0 > p.window) || (k0 + 63 >= p.Skv);
+      float pv[64];
+      mbar_wait(s_full(u), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t su[32];
+        tmem_ld_x32(tS + ch * 32, su);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = ex2(fmaf(__uint_as_float(su[i]), c, -L));
+          const int kc = k0 + ch * 32 + i;
+          if (need_mask && (kc >= p.Skv || !visible(p.causal, p.window, r, kc))) e = 0.f;
+          pv[ch * 32 + i] = e;
+        }
+      }
+      mbar_wait(dp_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t du[32];
+        tmem_ld_x32(tDP + ch * 32, du);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float d0 = pv[ch * 32 + i] * fmaf(__uint_as_float(du[i]), scale, -Dt);
+          const float d1 = pv[ch * 32 + i + 1] * fmaf(__uint_as_float(du[i + 1]), scale, -Dt);
+          pk[i / 2] = BF16 ? pack_bf16(d0, d1) : pack_f16(d0, d1);
+        }
+        tmem_st_x16(tDP + ch * 16, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    if (n > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    const bool live = r < p.Sq;
+    const size_t orow = (((size_t)b * p.H + h) * p.Sq + r) * D + half * (D / 2);
+    const uint32_t tA = tmem + lane_base + T_DQ + half * (D / 2);
+#pragma unroll
+    for (int ch = 0; ch < D / 64; ++ch) {
+      uint32_t ou[32];
+      if (n > 0) {
+        tmem_ld_x32(tA + ch * 32, ou);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ou[i] = 0u;
+      }
+      if (live) {
+        float4* dst = reinterpret_cast<float4*>(p.dq + orow + ch * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(__uint_as_float(ou[4 * i]), __uint_as_float(ou[4 * i + 1]), __uint_as_float(ou[4 * i + 2]),
+                               __uint_as_float(ou[4 * i + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
+template <typename K>
+cudaError_t ensure_smem(K kern, int bytes, bool& done) {
+  if (done) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done = true;
+  return e;
+}
+
+template <int D, bool BF16>
+cudaError_t launch_bwd(const BwdTcParams& prm, int B, bool want_dq, bool want_dkv, cudaStream_t st) {
+  static bool a_set = false, b_set = false;
+  cudaError_t e;
+  if (want_dkv) {
+    if ((e = ensure_smem(bwd_dkv_tc_kernel<D, BF16>, BCfg<D>::kSmem, a_set)) != cudaSuccess) return e;
+    dim3 grid((prm.Skv + 127) / 128, prm.Hkv, B);
+    bwd_dkv_tc_kernel<D, BF16><<<grid, kThreads, BCfg<D>::kSmem, st>>>(prm);
+    ++g_launch_count;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if (want_dq) {
+    if ((e = ensure_smem(bwd_dq_tc_kernel<D, BF16>, BCfg<D>::kSmem, b_set)) != cudaSuccess) return e;
+    dim3 grid((prm.Sq + 127) / 128, prm.H, B);
+    bwd_dq_tc_kernel<D, BF16><<<grid, kThreads, BCfg<D>::kSmem, st>>>(prm);
+    ++g_launch_count;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace
+
+bool bwd_tc_eligible(const AttnParams& p) {
+  if (getenv("MFA_DISABLE_TC") || getenv("MFA_DISABLE_TC_BWD")) return false;
+  if (p.in_dtype != kBF16 && p.in_dtype != kF16) return false;
+  if (p.do_dtype != p.in_dtype) return false;
+  if (p.D != 64 && p.D != 128) return false;
+  if (p.mask_kind != kMaskNone) return false;
+  if (p.Sq <= 0 || p.Skv <= 0 || p.B <= 0 || p.H <= 0 || p.Hkv <= 0 || p.H % p.Hkv) return false;
+  if (p.B > 65535 || p.H > 65535) return false;
+  if (!tc::view_ok(p.q, p.H, p.B) || !tc::view_ok(p.k, p.Hkv, p.B) || !tc::view_ok(p.v, p.Hkv, p.B) ||
+      !tc::view_ok(p.d_o, p.H, p.B))
+    return false;
+  if (!p.lse || !p.dterm) return false;
+  for (float* g : {p.dq, p.dk, p.dv})
+    if (g && (reinterpret_cast<uintptr_t>(g) & 15)) return false;
+  return tc::encode_fn() != nullptr;
+}
+
+// dQ, dK, dV from Q, K, V, dO, L and D (= scale * rowsum(dO * O), launch_dterm).  Gradients are fp32 contiguous BHSD.
+cudaError_t launch_bwd_tc(const AttnParams& p, cudaStream_t st) {
+  BwdTcParams prm;
+  if (!tc::make_map(&prm.tq, p.q, p.in_dtype, p.B, p.H, p.Sq, p.D) ||
+      !tc::make_map(&prm.tdo, p.d_o, p.in_dtype, p.B, p.H, p.Sq, p.D) ||
+      !tc::make_map(&prm.tk, p.k, p.in_dtype, p.B, p.Hkv, p.Skv, p.D) ||
+      !tc::make_map(&prm.tv, p.v, p.in_dtype, p.B, p.Hkv, p.Skv, p.D))
+    return cudaErrorInvalidValue;
+  prm.lse = p.lse; prm.dterm = p.dterm;
+  prm.dq = p.dq; prm.dk = p.dk; prm.dv = p.dv;
+  prm.H = p.H; prm.Hkv = p.Hkv; prm.Sq = p.Sq; prm.Skv = p.Skv;
+  prm.c = p.scale * kLog2e; prm.scale = p.scale;
+  prm.causal = p.causal; prm.window = p.window;
+  const bool want_dq = p.dq != nullptr, want_dkv = p.dk != nullptr && p.dv != nullptr;
+  const bool bf = p.in_dtype == kBF16;
+  cudaError_t e;
+  if (p.D == 128) e = bf ? launch_bwd<128, true>(prm, p.B, want_dq, want_dkv, st) : launch_bwd<128, false>(prm, p.B, want_dq, want_dkv, st);
+  else e = bf ? launch_bwd<64, true>(prm, p.B, want_dq, want_dkv, st) : launch_bwd<64, false>(prm, p.B, want_dq, want_dkv, st);
+  g_last_kernel = p.D == 128 ? (bf ? "bwd_tc_bf16_d128" : "bwd_tc_fp16_d128") : (bf ? "bwd_tc_bf16_d64" : "bwd_tc_fp16_d64");
+  return e;
+}
+
+}  // namespace mfa

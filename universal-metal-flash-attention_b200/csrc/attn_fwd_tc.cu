@@ -26,6 +26,7 @@
 
 #include "common.h"
 #include "sm100_ptx.cuh"
+#include "tc_host.h"
 
 namespace mfa {
 
@@ -58,7 +59,22 @@ struct Cfg {
   static constexpr int kSmem = (2 + kStages) * kTile + kBarBytes + 1024;
 };
 
-template <int D, bool BF16>
+// 2^x for x <= ~8 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max rel err 8.6e-5): relieves
+// the MUFU pipe, which is co-critical with the tensor pipe at head_dim 128 (16 ex2/clk/SM vs 8192 FLOP/clk/SM).
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  float xr;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(xr) : "f"(x), "f"(12582912.f));     // 1.5 * 2^23: low bits = floor(x)
+  const float f = x - (xr - 12582912.f);                                       // [0, 1)
+  float pz = fmaf(f, 0.07706582f, 0.22764632f);
+  pz = fmaf(pz, f, 0.69511649f);
+  pz = fmaf(pz, f, 1.0f);
+  return __int_as_float(__float_as_int(pz) + (__float_as_int(xr) << 23));
+}
+
+// POLY = n > 0: one element in every 2n goes through exp2_poly instead of MUFU.EX2 (only on tiles without masking,
+// so masked elements always get an exact zero weight).
+template <int D, bool BF16, int POLY>
 __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_constant__ FwdTcParams p) {
   using C = Cfg<D>;
   constexpr int TILE = C::kTile, NS = C::kStages, CHB = C::kChunkBytes;
@@ -87,7 +103,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
 
   if (threadIdx.x == 256) {
     for (int t = 0; t < 2; ++t) {
-      mbar_init(q_full(t), 1); mbar_init(s_full(t), 1); mbar_init(p_full(t), 128); mbar_init(o_full(t), 1);
+      mbar_init(q_full(t), 1); mbar_init(s_full(t), 1); mbar_init(p_full(t), 4); mbar_init(o_full(t), 1);
     }
     for (int s = 0; s < NS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     fence_mbar_init();
@@ -202,7 +218,8 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         tmem_wait_ld();
         float* s = reinterpret_cast<float*>(su);
         const bool need_mask = (c0 < clo) || (c0 + 127 > chi);
-        if (__any_sync(0xffffffffu, need_mask)) {
+        const bool any_mask = __any_sync(0xffffffffu, need_mask);
+        if (any_mask) {
           const int lo_i = clo - c0, hi_i = chi - c0;
 #pragma unroll
           for (int i = 0; i < 128; ++i) s[i] = (i < lo_i || i > hi_i) ? -CUDART_INF_F : s[i];
@@ -235,19 +252,31 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         const float neg_mc = (m == -CUDART_INF_F) ? 0.f : -m * c;
         float sum0 = 0.f, sum1 = 0.f;
         uint32_t pk[64];
+        if (POLY > 0 && !any_mask) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          const float p0 = ex2(fmaf(s[2 * i], c, neg_mc));
-          const float p1 = ex2(fmaf(s[2 * i + 1], c, neg_mc));
-          sum0 += p0; sum1 += p1;
-          pk[i] = BF16 ? pack_bf16(p0, p1) : pack_f16(p0, p1);
+          for (int i = 0; i < 64; ++i) {
+            const float x0 = fmaf(s[2 * i], c, neg_mc), x1 = fmaf(s[2 * i + 1], c, neg_mc);
+            const float p0 = ex2(x0);
+            const float p1 = (POLY > 0 && (i % POLY) == POLY - 1) ? exp2_poly(x1) : ex2(x1);
+            sum0 += p0; sum1 += p1;
+            pk[i] = BF16 ? pack_bf16(p0, p1) : pack_f16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const float p0 = ex2(fmaf(s[2 * i], c, neg_mc));
+            const float p1 = ex2(fmaf(s[2 * i + 1], c, neg_mc));
+            sum0 += p0; sum1 += p1;
+            pk[i] = BF16 ? pack_bf16(p0, p1) : pack_f16(p0, p1);
+          }
         }
         l += sum0 + sum1;
         tmem_st_x32(tS, pk);
         tmem_st_x32(tS + 32, pk + 32);
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(p_full(t));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(t));
       }
       // ---------------------------------------------------------------- epilogue: O / l, L = m + log2(l)
       if (n > 0) {
@@ -301,55 +330,21 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+using tc::encode_fn;
+using tc::make_map;
 
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
-        qr == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    else
-      cudaGetLastError();
-  });
-  return fn;
+bool view_ok(const TensorView& t, int64_t, int64_t Hn, int64_t B) { return tc::view_ok(t, Hn, B); }
+
+int poly_setting() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MFA_FWD_POLY"); v = e ? atoi(e) : 0; }
+  return v;
 }
 
-// [B, Hn, S, D] view with unit inner stride -> 4-D tensor map, box = 64 x 128 elements, 128B swizzle.
-bool make_map(CUtensorMap* out, const TensorView& t, int dtype, int B, int Hn, int S, int D) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)Hn, (cuuint64_t)B};
-  cuuint64_t st[3] = {(cuuint64_t)t.ss * 2, (cuuint64_t)t.sh * 2, (cuuint64_t)t.sb * 2};
-  if (Hn == 1) st[1] = st[0] * (cuuint64_t)S;
-  if (B == 1) st[2] = st[1] * (cuuint64_t)Hn;
-  cuuint32_t box[4] = {64, 128, 1, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = fn(out, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
-                  const_cast<void*>(t.ptr), dims, st, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
-bool view_ok(const TensorView& t, int64_t S, int64_t Hn, int64_t B) {
-  if (t.sd != 1) return false;
-  if (reinterpret_cast<uintptr_t>(t.ptr) & 15) return false;
-  if (t.ss <= 0 || (t.ss & 7)) return false;
-  if (Hn > 1 && (t.sh <= 0 || (t.sh & 7))) return false;
-  if (B > 1 && (t.sb <= 0 || (t.sb & 7))) return false;
-  (void)S;
-  return true;
-}
-
-template <int D, bool BF16>
-cudaError_t launch(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
+template <int D, bool BF16, int POLY>
+cudaError_t launch_k(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = fwd_tc_kernel<D, BF16>;
+  auto kern = fwd_tc_kernel<D, BF16, POLY>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D>::kSmem);
     if (e != cudaSuccess) return e;
@@ -357,6 +352,17 @@ cudaError_t launch(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
   }
   kern<<<grid, kThreads, Cfg<D>::kSmem, st>>>(prm);
   return cudaGetLastError();
+}
+
+template <int D, bool BF16>
+cudaError_t launch(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
+  switch (poly_setting()) {
+    case 0: return launch_k<D, BF16, 0>(prm, grid, st);
+    case 1: return launch_k<D, BF16, 1>(prm, grid, st);
+    case 4: return launch_k<D, BF16, 4>(prm, grid, st);
+    case 2: return launch_k<D, BF16, 2>(prm, grid, st);
+    default: return launch_k<D, BF16, 0>(prm, grid, st);
+  }
 }
 
 }  // namespace

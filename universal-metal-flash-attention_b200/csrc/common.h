@@ -79,6 +79,10 @@ cudaError_t launch_bwd_dkv_only(const AttnParams& p, cudaStream_t st);      // d
 bool fwd_tc_eligible(const AttnParams& p);
 cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st);
 
+// tcgen05 backward (bf16/fp16, D in {64,128}); needs p.dterm filled by launch_dterm first.
+bool bwd_tc_eligible(const AttnParams& p);
+cudaError_t launch_bwd_tc(const AttnParams& p, cudaStream_t st);
+
 // quantiser & friends
 cudaError_t launch_quantize(const void* src, int src_dtype, void* codes, float* scales, uint64_t rows, uint64_t cols,
                             uint32_t block_rows, uint32_t block_cols, int bits, float scale_floor, cudaStream_t st);

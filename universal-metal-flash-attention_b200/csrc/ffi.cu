@@ -348,7 +348,12 @@ mfa_error_t backward_core(Context* ctx, const BwdArgs& a) {
 
   Timer tm(ctx, st, !a.async);
   cudaError_t e = cudaSuccess;
-  e = launch_bwd_simt(p, st);   // empty Sq / Skv degrade to zero-filled gradients inside the kernels
+  if (bwd_tc_eligible(p)) {
+    e = launch_dterm(p, st);
+    if (e == cudaSuccess) e = launch_bwd_tc(p, st);
+  } else {
+    e = launch_bwd_simt(p, st);   // empty Sq / Skv degrade to zero-filled gradients inside the kernels
+  }
   tm.stop();
   ctx->last_kernel = g_last_kernel;
   if (e != cudaSuccess) return cuda_fail(e, "backward launch");

@@ -1,0 +1,66 @@
+// tc_host.h -- host-side helpers shared by the tcgen05 kernels: TMA tensor-map construction for [B, H, S, D] operand
+// views (cuTensorMapEncodeTiled resolved through the runtime so the library loads without libcuda at link time).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "common.h"
+
+namespace mfa {
+namespace tc {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+// [B, Hn, S, D] view with unit inner stride -> 4-D tensor map, box = (128 bytes of a row) x box_rows rows, 128B
+// swizzle.  elem_bytes: 2 for fp16/bf16, 1 for int8/fp8 operands (box is then 128 elements wide).
+inline bool make_map(CUtensorMap* out, const TensorView& t, int dtype, int B, int Hn, int S, int D, int box_rows = 128) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t eb = (dtype == kI8) ? 1 : 2;
+  cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)Hn, (cuuint64_t)B};
+  cuuint64_t st[3] = {(cuuint64_t)t.ss * eb, (cuuint64_t)t.sh * eb, (cuuint64_t)t.sb * eb};
+  if (Hn == 1) st[1] = st[0] * (cuuint64_t)S;
+  if (B == 1) st[2] = st[1] * (cuuint64_t)Hn;
+  cuuint32_t box[4] = {(cuuint32_t)(128 / eb), (cuuint32_t)box_rows, 1, 1};
+  if (box[0] > (cuuint32_t)D) box[0] = (cuuint32_t)D;
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUtensorMapDataType ty = dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                               : dtype == kF16  ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  CUresult r = fn(out, ty, 4, const_cast<void*>(t.ptr), dims, st, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// TMA needs a 16-byte aligned base, unit inner stride and 16-byte multiples for the outer strides.
+inline bool view_ok(const TensorView& t, int64_t Hn, int64_t B, int elem_bytes = 2) {
+  const int64_t q = 16 / elem_bytes;
+  if (t.sd != 1) return false;
+  if (reinterpret_cast<uintptr_t>(t.ptr) & 15) return false;
+  if (t.ss <= 0 || (t.ss % q)) return false;
+  if (Hn > 1 && (t.sh <= 0 || (t.sh % q))) return false;
+  if (B > 1 && (t.sb <= 0 || (t.sb % q))) return false;
+  return true;
+}
+
+}  // namespace tc
+}  // namespace mfa
