@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="flux", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="fwd", choices=["fwd", "fwdbwd"],
+                    help="fwd: forward only (the headline FLUX metric); fwdbwd: forward + backward per step (config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -190,7 +192,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     B, H, Sq, Skv, D = w["B"], w["H"], w["Sq"], w["Skv"], w["D"]
     scale = 1.0 / float(np.sqrt(D))
-    flops = fwd_flops(w)
+    flops = fwd_flops(w) * (3.5 if args.mode == "fwdbwd" else 1.0)      # fwd 4, bwd 10 FLOP per pair per d
     prec = {"bf16": 1, "fp16": 0}[w["dtype"]]
     tdt = {"bf16": torch.bfloat16, "fp16": torch.float16}[w["dtype"]]
 
@@ -206,18 +208,32 @@ def main():
         k = torch.randn(B, H, Skv, D, device=dev, dtype=torch.float32, generator=g).to(tdt)
         v = torch.randn(B, H, Skv, D, device=dev, dtype=torch.float32, generator=g).to(tdt)
         o = torch.empty(B, H, Sq, D, device=dev, dtype=torch.float32)
-        bufs = [umfa.MFABuffer(ctx, device_ptr=t.data_ptr(), size=t.numel() * t.element_size()) for t in (q, k, v, o)]
-        sets.append(((q, k, v, o), bufs))
+        ts = [q, k, v, o]
+        if args.mode == "fwdbwd":
+            ts.append(torch.empty(B, H, Sq, device=dev, dtype=torch.float32))                                   # L
+            ts.append(torch.randn(B, H, Sq, D, device=dev, dtype=torch.float32, generator=g).to(tdt))           # dO
+            ts += [torch.empty(B, H, S, D, device=dev, dtype=torch.float32) for S in (Sq, Skv, Skv)]           # dQ dK dV
+            ts.append(torch.empty(B, H, Sq, device=dev, dtype=torch.float32))                                   # D
+        bufs = [umfa.MFABuffer(ctx, device_ptr=t.data_ptr(), size=t.numel() * t.element_size()) for t in ts]
+        sets.append((ts, bufs))
     stream = torch.cuda.current_stream(dev)
     stream_ptr = ctypes.c_void_p(stream.cuda_stream)
 
     def enqueue(i):
         _, b = sets[i % nsets]
-        rc = lib.mfa_attention_forward_ex(ctx.handle, b[0].handle, b[1].handle, b[2].handle, b[3].handle, None,
+        lse = b[4].handle if args.mode == "fwdbwd" else None
+        rc = lib.mfa_attention_forward_ex(ctx.handle, b[0].handle, b[1].handle, b[2].handle, b[3].handle, lse,
                                           B, Sq, Skv, H, D, scale, w["causal"], w["window"], prec, 2,
                                           None, 0, None, None, 0, 0, 0, stream_ptr)
         if rc != 0:
             raise RuntimeError(f"mfa_attention_forward_ex failed: {rc}")
+        if args.mode == "fwdbwd":
+            rc = lib.mfa_attention_backward_ex(ctx.handle, b[5].handle, b[0].handle, b[1].handle, b[2].handle, b[3].handle,
+                                               b[4].handle, b[6].handle, b[7].handle, b[8].handle, b[9].handle,
+                                               B, Sq, Skv, H, D, scale, w["causal"], w["window"], prec,
+                                               None, 0, None, None, 0, 0, 0, stream_ptr)
+            if rc != 0:
+                raise RuntimeError(f"mfa_attention_backward_ex failed: {rc}")
 
     def barrier():
         if world > 1:
@@ -258,7 +274,7 @@ def main():
 
     # --- end-to-end arm through the blocking reference entry point with host buffers
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.mode == "fwd":
         hq, hk, hv = (torch.randn(B, H, S, D, dtype=torch.float32).to(tdt).pin_memory() for S in (Sq, Skv, Skv))
         ho = torch.empty(B, H, Sq, D, dtype=torch.float32).pin_memory()
         hb = []
@@ -296,14 +312,15 @@ def main():
         peak, peak_src = load_peaks()
         med = float(np.median(per_launch_ms))
         achieved = flops / (med * 1e-3) / 1e12
-        line = {"metric": "attention forward TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world,
+        mname = "attention forward TFLOP/s" if args.mode == "fwd" else "attention forward+backward TFLOP/s"
+        line = {"metric": mname, "value": value, "unit": "TFLOP/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"],
                 "data": "synthetic",
                 "config": {"workload": w["label"], "per_gpu": {k: w[k] for k in ("B", "H", "Sq", "Skv", "D", "causal", "window")},
                            "parallelism": f"batchxhead sharding over {world} GPU(s), no collective",
                            "cache": f"inputs rotate over {nsets} buffer sets ({nsets * (in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2)",
-                           "kernel": kernel_name, "output": "fp32 O (reference contract)"},
+                           "kernel": kernel_name, "mode": args.mode, "output": "fp32 O (reference contract)"},
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                              "flops_per_launch": flops, "launch_ms_median": med,

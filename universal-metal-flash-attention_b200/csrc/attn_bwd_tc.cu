@@ -58,10 +58,6 @@ struct BCfg {
   static constexpr int kSmem = 6 * kTile + kStatBytes + 256 + 1024;
 };
 
-// element (q row r, key col cidx) visible under the causal / window rule
-__device__ __forceinline__ bool visible(int causal, int window, int r, int cidx) {
-  return (!causal || cidx <= r) && (window < 0 || r - cidx <= window);
-}
 
 __device__ __forceinline__ void load_tile_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int row, int head, int b,
                                              int chunks, int chb) {
@@ -212,12 +208,16 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
     const uint32_t tS = tmem + lane_base + T_S + half * 64;
     const uint32_t tDP = tmem + lane_base + T_DP + half * 64;
     const float c = p.c, scale = p.scale;
+    const int qlo_r = p.causal ? key : 0;
+    const int qhi_r = p.window >= 0 ? min(key + p.window, 1 << 30) : (1 << 30);
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1;
       const int q0 = (i_lo + it % nq) * 128 + half * 64;
       const float* sL = stat + (s * 2 + 0) * 128 + half * 64;
       const float* sD = stat + (s * 2 + 1) * 128 + half * 64;
-      const bool need_mask = (p.causal && c0 + 127 > q0) || (p.window >= 0 && q0 + 63 - c0 > p.window);
+      // queries visible to this key: [qlo_r, qhi_r]; rows past Sq carry L = +inf (P = 0)
+      const bool any_mask = __any_sync(0xffffffffu, q0 < qlo_r || q0 + 63 > qhi_r);
+      const int lo_i = qlo_r - q0, hi_i = qhi_r - q0;
       float pv[64];
       mbar_wait(st_full(s), (it >> 1) & 1);
       mbar_wait(s_full, it & 1);
@@ -227,21 +227,22 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
         uint32_t su[32];
         tmem_ld_x32(tS + ch * 32, su);
         tmem_wait_ld();
-        uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 L4 = *reinterpret_cast<const float4*>(sL + ch * 32 + i);
-          const float Ls[4] = {L4.x, L4.y, L4.z, L4.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float e = ex2(fmaf(__uint_as_float(su[i + k]), c, -Ls[k]));
-            if (need_mask && !visible(p.causal, p.window, q0 + ch * 32 + i + k, key)) e = 0.f;
-            pv[ch * 32 + i + k] = e;
-          }
-          pk[i / 2] = BF16 ? pack_bf16(pv[ch * 32 + i], pv[ch * 32 + i + 1]) : pack_f16(pv[ch * 32 + i], pv[ch * 32 + i + 1]);
-          pk[i / 2 + 1] = BF16 ? pack_bf16(pv[ch * 32 + i + 2], pv[ch * 32 + i + 3])
-                               : pack_f16(pv[ch * 32 + i + 2], pv[ch * 32 + i + 3]);
+          pv[ch * 32 + i + 0] = ex2(fmaf(__uint_as_float(su[i + 0]), c, -L4.x));
+          pv[ch * 32 + i + 1] = ex2(fmaf(__uint_as_float(su[i + 1]), c, -L4.y));
+          pv[ch * 32 + i + 2] = ex2(fmaf(__uint_as_float(su[i + 2]), c, -L4.z));
+          pv[ch * 32 + i + 3] = ex2(fmaf(__uint_as_float(su[i + 3]), c, -L4.w));
         }
+        if (any_mask) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pv[ch * 32 + i] = (ch * 32 + i < lo_i || ch * 32 + i > hi_i) ? 0.f : pv[ch * 32 + i];
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = BF16 ? pack_bf16(pv[ch * 32 + 2 * i], pv[ch * 32 + 2 * i + 1]) : pack_f16(pv[ch * 32 + 2 * i], pv[ch * 32 + 2 * i + 1]);
         tmem_st_x16(tS + ch * 16, pk);
       }
       tmem_wait_st();
@@ -425,11 +426,14 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
       L = p.lse[ri]; Dt = p.dterm[ri];
       if (L == -CUDART_INF_F) L = CUDART_INF_F;
     }
+    const int chi = p.causal ? min(p.Skv - 1, r) : p.Skv - 1;      // visible keys of this row: [clo, chi]
+    const int clo = p.window >= 0 ? max(0, r - p.window) : 0;
     for (int it = 0; it < n; ++it) {
       const int u = it & 1;
       const int k0 = (j_lo + it) * 128 + half * 64;
       const uint32_t tS = tmem + lane_base + u * 128 + half * 64;
-      const bool need_mask = (p.causal && k0 + 63 > r0) || (p.window >= 0 && r0 + 127 - k0 > p.window) || (k0 + 63 >= p.Skv);
+      const bool any_mask = __any_sync(0xffffffffu, k0 < clo || k0 + 63 > chi);
+      const int lo_i = clo - k0, hi_i = chi - k0;
       float pv[64];
       mbar_wait(s_full(u), (it >> 1) & 1);
       tc_fence_after();
@@ -439,11 +443,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
         tmem_ld_x32(tS + ch * 32, su);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = ex2(fmaf(__uint_as_float(su[i]), c, -L));
-          const int kc = k0 + ch * 32 + i;
-          if (need_mask && (kc >= p.Skv || !visible(p.causal, p.window, r, kc))) e = 0.f;
-          pv[ch * 32 + i] = e;
+        for (int i = 0; i < 32; ++i) pv[ch * 32 + i] = ex2(fmaf(__uint_as_float(su[i]), c, -L));
+        if (any_mask) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pv[ch * 32 + i] = (ch * 32 + i < lo_i || ch * 32 + i > hi_i) ? 0.f : pv[ch * 32 + i];
         }
       }
       mbar_wait(dp_full, it & 1);
