@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
   auto st_empty = [&](int s) { return sBar + 64 + 8 * s; };
   const uint32_t tmem_slot = sBar + 80;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
   const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
   const int c0 = jt * 128;
   const int group = p.H / p.Hkv;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw)), 0);
   constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 256 + D;
 
   if (warp == 9) {
@@ -150,54 +150,56 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
       if (lane == 0) mbar_arrive(st_full(s));
     }
   } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && n_it > 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
+    if (n_it > 0) {
       constexpr uint32_t FMT = BF16 ? 1u : 0u;
       constexpr uint32_t IDESC_ST = make_idesc(1, FMT, FMT, 0, 0, 128, 128);   // K-major A and B
       constexpr uint32_t IDESC_ACC = make_idesc(1, FMT, FMT, 0, 1, 128, D);    // A from TMEM, B MN-major
-      auto issue_abt = [&](uint32_t dcol, uint32_t abase, uint32_t bbase) {    // D = A B^T over head_dim
+      const uint32_t k_lo = desc_lo(sK, 16), v_lo = desc_lo(sV, 16);
+      const uint32_t qk_lo = desc_lo(sQ(0), 16), dok_lo = desc_lo(sdO(0), 16);       // K-major views of the stage tiles
+      const uint32_t qm_lo = desc_lo(sQ(0), CHB), dom_lo = desc_lo(sdO(0), CHB);     // MN-major views
+      constexpr uint32_t STG = (2 * TILE) >> 4;                                      // stage stride in descriptor units
+      auto issue_abt = [&](uint32_t dcol, uint32_t a0, uint32_t b0) {                // D = A B^T over head_dim
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * CHB + (kk & 3) * 32;
-          mma_f16_ss(tmem + dcol, smem_desc_sw128(abase + off, 16, 1024), smem_desc_sw128(bbase + off, 16, 1024), IDESC_ST,
-                     kk > 0);
+          const uint32_t off = ((kk >> 2) * CHB + (kk & 3) * 32) >> 4;
+          mma_f16_ss_u(tmem + dcol, a0 + off, kDescHiSw128, b0 + off, kDescHiSw128, IDESC_ST, kk > 0);
         }
       };
-      auto issue_acc = [&](uint32_t dcol, uint32_t acol, uint32_t bbase, bool acc) {   // D += A(tmem) B over 128 queries
+      auto issue_acc = [&](uint32_t dcol, uint32_t acol, uint32_t b0, bool acc) {    // D += A(tmem) B over 128 queries
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          mma_f16_ts(tmem + dcol, tmem + acol + (kk >> 2) * 64 + (kk & 3) * 8, smem_desc_sw128(bbase + kk * 2048, CHB, 1024),
-                     IDESC_ACC, (acc || kk > 0) ? 1u : 0u);
-        }
+        for (int kk = 0; kk < 8; ++kk)
+          mma_f16_ts_u(tmem + dcol, tmem + acol + (kk >> 2) * 64 + (kk & 3) * 8, b0 + kk * (2048 >> 4), kDescHiSw128,
+                       IDESC_ACC, (acc || kk > 0) ? 1u : 0u);
       };
       mbar_wait(kv_full, 0);
       mbar_wait(st_full(0), 0);
       tc_fence_after();
-      issue_abt(T_S, sK, sQ(0));
-      tc_commit(s_full);
-      issue_abt(T_DP, sV, sdO(0));
-      tc_commit(dp_full);
+      issue_abt(T_S, k_lo, qk_lo);
+      tc_commit_u(s_full);
+      issue_abt(T_DP, v_lo, dok_lo);
+      tc_commit_u(dp_full);
       for (int it = 0; it < n_it; ++it) {
-        const int s = it & 1;
+        const uint32_t s = it & 1;
         mbar_wait(p_full, it & 1);
         tc_fence_after();
-        issue_acc(T_DV, T_S, sdO(s), it > 0);
+        issue_acc(T_DV, T_S, dom_lo + s * STG, it > 0);
         if (it + 1 < n_it) {
           mbar_wait(st_full(s ^ 1), ((it + 1) >> 1) & 1);
           tc_fence_after();
-          issue_abt(T_S, sK, sQ(s ^ 1));
-          tc_commit(s_full);
+          issue_abt(T_S, k_lo, qk_lo + (s ^ 1) * STG);
+          tc_commit_u(s_full);
         }
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
-        issue_acc(T_DK, T_DP, sQ(s), it > 0);
-        tc_commit(st_empty(s));
+        issue_acc(T_DK, T_DP, qm_lo + s * STG, it > 0);
+        tc_commit_u(st_empty(s));
         if (it + 1 < n_it) {
-          issue_abt(T_DP, sV, sdO(s ^ 1));
-          tc_commit(dp_full);
+          issue_abt(T_DP, v_lo, dok_lo + (s ^ 1) * STG);
+          tc_commit_u(dp_full);
         }
       }
-      tc_commit(acc_full);
+      tc_commit_u(acc_full);
     }
   } else {
     // ------------------------------------------------------------------ elementwise warpgroups
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
   auto st_empty = [&](int s) { return sBar + 64 + 8 * s; };
   const uint32_t tmem_slot = sBar + 80;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
   const int it_q = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;     // heavy tiles first
   const int h = blockIdx.y, b = blockIdx.z;
   const int hk = h / (p.H / p.Hkv);
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw)), 0);
   constexpr uint32_t T_DP = 256, T_DQ = 384;
 
   if (warp == 9) {
@@ -370,48 +372,49 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
       }
     }
   } else if (warp == 8) {
-    if (lane == 0 && n > 0) {
+    if (n > 0) {
       constexpr uint32_t FMT = BF16 ? 1u : 0u;
       constexpr uint32_t IDESC_ST = make_idesc(1, FMT, FMT, 0, 0, 128, 128);
       constexpr uint32_t IDESC_ACC = make_idesc(1, FMT, FMT, 0, 1, 128, D);
-      auto issue_abt = [&](uint32_t dcol, uint32_t abase, uint32_t bbase) {
+      const uint32_t q_lo = desc_lo(sQ, 16), do_lo = desc_lo(sdO, 16);
+      const uint32_t kk_lo = desc_lo(sK(0), 16), vk_lo = desc_lo(sV(0), 16), km_lo = desc_lo(sK(0), CHB);
+      constexpr uint32_t STG = (2 * TILE) >> 4;
+      auto issue_abt = [&](uint32_t dcol, uint32_t a0, uint32_t b0) {
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * CHB + (kk & 3) * 32;
-          mma_f16_ss(tmem + dcol, smem_desc_sw128(abase + off, 16, 1024), smem_desc_sw128(bbase + off, 16, 1024), IDESC_ST,
-                     kk > 0);
+          const uint32_t off = ((kk >> 2) * CHB + (kk & 3) * 32) >> 4;
+          mma_f16_ss_u(tmem + dcol, a0 + off, kDescHiSw128, b0 + off, kDescHiSw128, IDESC_ST, kk > 0);
         }
       };
       mbar_wait(q_full, 0);
       mbar_wait(st_full(0), 0);
       tc_fence_after();
-      issue_abt(0, sQ, sK(0));
-      tc_commit(s_full(0));
-      issue_abt(T_DP, sdO, sV(0));
-      tc_commit(dp_full);
+      issue_abt(0, q_lo, kk_lo);
+      tc_commit_u(s_full(0));
+      issue_abt(T_DP, do_lo, vk_lo);
+      tc_commit_u(dp_full);
       for (int it = 0; it < n; ++it) {
-        const int s = it & 1;
+        const uint32_t s = it & 1;
         if (it + 1 < n) {
           mbar_wait(st_full(s ^ 1), ((it + 1) >> 1) & 1);
           tc_fence_after();
-          issue_abt((s ^ 1) * 128, sQ, sK(s ^ 1));
-          tc_commit(s_full(s ^ 1));
+          issue_abt((s ^ 1) * 128, q_lo, kk_lo + (s ^ 1) * STG);
+          tc_commit_u(s_full(s ^ 1));
         }
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          mma_f16_ts(tmem + T_DQ, tmem + T_DP + (kk >> 2) * 64 + (kk & 3) * 8, smem_desc_sw128(sK(s) + kk * 2048, CHB, 1024),
-                     IDESC_ACC, (it > 0 || kk > 0) ? 1u : 0u);
-        }
+        for (int kk = 0; kk < 8; ++kk)
+          mma_f16_ts_u(tmem + T_DQ, tmem + T_DP + (kk >> 2) * 64 + (kk & 3) * 8, km_lo + s * STG + kk * (2048 >> 4),
+                       kDescHiSw128, IDESC_ACC, (it > 0 || kk > 0) ? 1u : 0u);
         if (it + 1 < n) {
-          issue_abt(T_DP, sdO, sV(s ^ 1));
-          tc_commit(dp_full);
+          issue_abt(T_DP, do_lo, vk_lo + (s ^ 1) * STG);
+          tc_commit_u(dp_full);
         }
         // K_j / V_j of this stage: last readers are dQ_j (K) and dP_j (V, issued earlier) -> all committed here
-        tc_commit(st_empty(s));
+        tc_commit_u(st_empty(s));
       }
-      tc_commit(acc_full);
+      tc_commit_u(acc_full);
     }
   } else if (warp < 8) {
     const int half = warp >> 2, w = warp & 3;

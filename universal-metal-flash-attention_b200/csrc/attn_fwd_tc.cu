@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
   auto kv_empty = [&](int s) { return sBar + 64 + 8 * NS + 8 * s; };
   const uint32_t tmem_slot = sBar + 64 + 16 * NS;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
   const int qblk = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;   // heavy blocks first
   const int h = blockIdx.y, b = blockIdx.z;
   const int hk = h / (p.H / p.Hkv);
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw)), 0);
 
   if (warp == 9) {
     // ------------------------------------------------------------------ TMA producer
@@ -140,53 +140,52 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       }
     }
   } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
     reg_dealloc<40>();
-    if (lane == 0 && n > 0) {
+    if (n > 0) {
       constexpr uint32_t FMT = BF16 ? 1u : 0u;
       constexpr uint32_t IDESC_S = make_idesc(1, FMT, FMT, 0, 0, 128, 128);
       constexpr uint32_t IDESC_O = make_idesc(1, FMT, FMT, 0, 1, 128, D);
-      auto issue_s = [&](int t, uint32_t kbase) {
-        const uint32_t qbase = sQ + t * TILE;
+      const uint32_t q_lo = desc_lo(sQ, 16), k_lo = desc_lo(sKV, 16), v_lo = desc_lo(sKV, CHB);
+      auto issue_s = [&](int t, int idx) {
+        const uint32_t a0 = q_lo + t * (TILE >> 4), b0 = k_lo + (idx % NS) * (TILE >> 4);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * CHB + (kk & 3) * 32;
-          mma_f16_ss(tmem + t * 128, smem_desc_sw128(qbase + off, 16, 1024), smem_desc_sw128(kbase + off, 16, 1024),
-                     IDESC_S, kk > 0);
+          const uint32_t off = ((kk >> 2) * CHB + (kk & 3) * 32) >> 4;
+          mma_f16_ss_u(tmem + t * 128, a0 + off, kDescHiSw128, b0 + off, kDescHiSw128, IDESC_S, kk > 0);
         }
       };
-      auto issue_o = [&](int t, uint32_t vbase, bool acc) {
+      auto issue_o = [&](int t, int idx, bool acc) {
+        const uint32_t b0 = v_lo + (idx % NS) * (TILE >> 4);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          mma_f16_ts(tmem + 256 + t * D, tmem + t * 128 + kk * 8, smem_desc_sw128(vbase + kk * 2048, CHB, 1024),
-                     IDESC_O, (acc || kk > 0) ? 1u : 0u);
-        }
+        for (int kk = 0; kk < 8; ++kk)
+          mma_f16_ts_u(tmem + 256 + t * D, tmem + t * 128 + kk * 8, b0 + kk * (2048 >> 4), kDescHiSw128, IDESC_O,
+                       (acc || kk > 0) ? 1u : 0u);
       };
-      auto stage_of = [&](int idx) { return sKV + (idx % NS) * TILE; };
       auto wait_full = [&](int idx) { mbar_wait(kv_full(idx % NS), (idx / NS) & 1); };
       wait_full(0);
       for (int t = 0; t < nt; ++t) {
         mbar_wait(q_full(t), 0);
         tc_fence_after();
-        issue_s(t, stage_of(0));
-        tc_commit(s_full(t));
+        issue_s(t, 0);
+        tc_commit_u(s_full(t));
       }
-      tc_commit(kv_empty(0));
+      tc_commit_u(kv_empty(0));
       for (int it = 0; it < n; ++it) {
         const int vi = 2 * it + 1, ki = 2 * it + 2;
         wait_full(vi);
         for (int t = 0; t < nt; ++t) {
           mbar_wait(p_full(t), it & 1);
           tc_fence_after();
-          issue_o(t, stage_of(vi), it > 0);
-          if (t == nt - 1) tc_commit(kv_empty(vi % NS));
+          issue_o(t, vi, it > 0);
+          if (t == nt - 1) tc_commit_u(kv_empty(vi % NS));
           if (it + 1 < n) {
             if (t == 0) { wait_full(ki); tc_fence_after(); }
-            issue_s(t, stage_of(ki));
-            tc_commit(s_full(t));
-            if (t == nt - 1) tc_commit(kv_empty(ki % NS));
+            issue_s(t, ki);
+            tc_commit_u(s_full(t));
+            if (t == nt - 1) tc_commit_u(kv_empty(ki % NS));
           } else {
-            tc_commit(o_full(t));
+            tc_commit_u(o_full(t));
           }
         }
       }
