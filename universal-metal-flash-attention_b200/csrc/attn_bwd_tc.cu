@@ -54,8 +54,9 @@ struct BCfg {
   static constexpr int kTile = 128 * D * 2;
   static constexpr int kChunks = D / 64;
   static constexpr int kChunkBytes = 128 * 128;
-  static constexpr int kStatBytes = 2 * 2 * 128 * 4;            // [stage][L|D][128]
-  static constexpr int kSmem = 6 * kTile + kStatBytes + 256 + 1024;
+  static constexpr int kRA = 3, kRB = 2;                         // ring depths: A = operand used last (Q / K), B = dO / V
+  static constexpr int kStatBytes = 2 * 2 * 128 * 4;             // [slot][L|D][128], own 2-deep ring
+  static constexpr int kSmem = (2 + kRA + kRB) * kTile + kStatBytes + 256 + 512;   // D = 128: 232192 of 232448 B
 };
 
 
@@ -69,20 +70,25 @@ template <int D, bool BF16>
 __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_constant__ BwdTcParams p) {
   using C = BCfg<D>;
   constexpr int TILE = C::kTile, CHB = C::kChunkBytes;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t sK = base, sV = base + TILE;
-  auto sQ = [&](int s) { return base + (2 + 2 * s) * TILE; };
-  auto sdO = [&](int s) { return base + (3 + 2 * s) * TILE; };
-  const uint32_t sStat = base + 6 * TILE;
+  constexpr int RA = C::kRA, RB = C::kRB;
+  auto sQ = [&](int s) { return base + (2 + s) * TILE; };            // ring A: Q_i (read by S^T_i first, dK_i last)
+  auto sdO = [&](int s) { return base + (2 + RA + s) * TILE; };      // ring B: dO_i (dP^T_i, dV_i)
+  const uint32_t sStat = base + (2 + RA + RB) * TILE;
   float* stat = reinterpret_cast<float*>(smem_raw + (sStat - raw));     // [stage][0: L, 1: D][128]
   const uint32_t sBar = sStat + C::kStatBytes;
   const uint32_t kv_full = sBar, s_full = sBar + 8, dp_full = sBar + 16, p_full = sBar + 24, ds_full = sBar + 32,
                  acc_full = sBar + 40;
-  auto st_full = [&](int s) { return sBar + 48 + 8 * s; };
-  auto st_empty = [&](int s) { return sBar + 64 + 8 * s; };
-  const uint32_t tmem_slot = sBar + 80;
+  auto q_full = [&](int s) { return sBar + 48 + 8 * s; };
+  auto q_empty = [&](int s) { return sBar + 80 + 8 * s; };
+  auto do_full = [&](int s) { return sBar + 112 + 8 * s; };
+  auto do_empty = [&](int s) { return sBar + 128 + 8 * s; };
+  auto stat_full = [&](int s) { return sBar + 144 + 8 * s; };
+  auto stat_empty = [&](int s) { return sBar + 160 + 8 * s; };
+  const uint32_t tmem_slot = sBar + 176;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
   const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
@@ -97,7 +103,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
   if (threadIdx.x == 256) {
     mbar_init(kv_full, 1); mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 8); mbar_init(ds_full, 8);
     mbar_init(acc_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(st_full(s), 3); mbar_init(st_empty(s), 1); }
+    for (int s = 0; s < RA; ++s) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
+    for (int s = 0; s < RB; ++s) { mbar_init(do_full(s), 1); mbar_init(do_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(stat_full(s), 2); mbar_init(stat_empty(s), 8); }
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -119,12 +127,14 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
       load_tile_4d(sK, &p.tk, kv_full, c0, hk, b, C::kChunks, CHB);
       load_tile_4d(sV, &p.tv, kv_full, c0, hk, b, C::kChunks, CHB);
       for (int it = 0; it < n_it; ++it) {
-        const int s = it & 1;
+        const int sa = it % RA, sb = it % RB;
         const int head = hk * group + it / nq, q0 = (i_lo + it % nq) * 128;
-        mbar_wait(st_empty(s), ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(st_full(s), 2 * TILE);
-        load_tile_4d(sQ(s), &p.tq, st_full(s), q0, head, b, C::kChunks, CHB);
-        load_tile_4d(sdO(s), &p.tdo, st_full(s), q0, head, b, C::kChunks, CHB);
+        mbar_wait(q_empty(sa), ((it / RA) & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full(sa), TILE);
+        load_tile_4d(sQ(sa), &p.tq, q_full(sa), q0, head, b, C::kChunks, CHB);
+        mbar_wait(do_empty(sb), ((it / RB) & 1) ^ 1);
+        mbar_arrive_expect_tx(do_full(sb), TILE);
+        load_tile_4d(sdO(sb), &p.tdo, do_full(sb), q0, head, b, C::kChunks, CHB);
       }
     }
   } else if (warp >= 10) {
@@ -133,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1;
       const int head = hk * group + it / nq, q0 = (i_lo + it % nq) * 128;
-      mbar_wait(st_empty(s), ((it >> 1) & 1) ^ 1);
+      mbar_wait(stat_empty(s), ((it >> 1) & 1) ^ 1);
       const size_t rb = ((size_t)b * p.H + head) * p.Sq;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
         stat[(s * 2 + 1) * 128 + r] = Dt;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(st_full(s));
+      if (lane == 0) mbar_arrive(stat_full(s));
     }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
@@ -158,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
       const uint32_t k_lo = desc_lo(sK, 16), v_lo = desc_lo(sV, 16);
       const uint32_t qk_lo = desc_lo(sQ(0), 16), dok_lo = desc_lo(sdO(0), 16);       // K-major views of the stage tiles
       const uint32_t qm_lo = desc_lo(sQ(0), CHB), dom_lo = desc_lo(sdO(0), CHB);     // MN-major views
-      constexpr uint32_t STG = (2 * TILE) >> 4;                                      // stage stride in descriptor units
+      constexpr uint32_t STG = TILE >> 4;                                            // ring-slot stride in descriptor units
       auto issue_abt = [&](uint32_t dcol, uint32_t a0, uint32_t b0) {                // D = A B^T over head_dim
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
@@ -173,29 +183,34 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
                        IDESC_ACC, (acc || kk > 0) ? 1u : 0u);
       };
       mbar_wait(kv_full, 0);
-      mbar_wait(st_full(0), 0);
+      mbar_wait(q_full(0), 0);
       tc_fence_after();
       issue_abt(T_S, k_lo, qk_lo);
       tc_commit_u(s_full);
+      mbar_wait(do_full(0), 0);
+      tc_fence_after();
       issue_abt(T_DP, v_lo, dok_lo);
       tc_commit_u(dp_full);
       for (int it = 0; it < n_it; ++it) {
-        const uint32_t s = it & 1;
+        const uint32_t sa = it % RA, sb = it % RB, na = (it + 1) % RA, nb = (it + 1) % RB;
         mbar_wait(p_full, it & 1);
         tc_fence_after();
-        issue_acc(T_DV, T_S, dom_lo + s * STG, it > 0);
+        issue_acc(T_DV, T_S, dom_lo + sb * STG, it > 0);
+        tc_commit_u(do_empty(sb));                       // dO_i: dP^T_i and dV_i were its only readers
         if (it + 1 < n_it) {
-          mbar_wait(st_full(s ^ 1), ((it + 1) >> 1) & 1);
+          mbar_wait(q_full(na), ((it + 1) / RA) & 1);
           tc_fence_after();
-          issue_abt(T_S, k_lo, qk_lo + (s ^ 1) * STG);
+          issue_abt(T_S, k_lo, qk_lo + na * STG);
           tc_commit_u(s_full);
         }
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
-        issue_acc(T_DK, T_DP, qm_lo + s * STG, it > 0);
-        tc_commit_u(st_empty(s));
+        issue_acc(T_DK, T_DP, qm_lo + sa * STG, it > 0);
+        tc_commit_u(q_empty(sa));                        // Q_i (and its L / D rows): last reader was dK_i
         if (it + 1 < n_it) {
-          issue_abt(T_DP, v_lo, dok_lo + (s ^ 1) * STG);
+          mbar_wait(do_full(nb), ((it + 1) / RB) & 1);
+          tc_fence_after();
+          issue_abt(T_DP, v_lo, dok_lo + nb * STG);
           tc_commit_u(dp_full);
         }
       }
@@ -221,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
       const bool any_mask = __any_sync(0xffffffffu, q0 < qlo_r || q0 + 63 > qhi_r);
       const int lo_i = qlo_r - q0, hi_i = qhi_r - q0;
       float pv[64];
-      mbar_wait(st_full(s), (it >> 1) & 1);
+      mbar_wait(stat_full(s), (it >> 1) & 1);
       mbar_wait(s_full, it & 1);
       tc_fence_after();
 #pragma unroll
@@ -275,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
+      if (lane == 0) { mbar_arrive(ds_full); mbar_arrive(stat_empty(s)); }
     }
     // ---------------------------------------------------------------- epilogue: dV, dK (fp32) -> global
     if (n_it > 0) {
@@ -318,18 +333,21 @@ template <int D, bool BF16>
 __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_constant__ BwdTcParams p) {
   using C = BCfg<D>;
   constexpr int TILE = C::kTile, CHB = C::kChunkBytes;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t sQ = base, sdO = base + TILE;
-  auto sK = [&](int s) { return base + (2 + 2 * s) * TILE; };
-  auto sV = [&](int s) { return base + (3 + 2 * s) * TILE; };
-  const uint32_t sBar = base + 6 * TILE;
+  constexpr int RA = C::kRA, RB = C::kRB;
+  auto sK = [&](int s) { return base + (2 + s) * TILE; };            // ring A: K_j (S_j first, dQ_j last)
+  auto sV = [&](int s) { return base + (2 + RA + s) * TILE; };       // ring B: V_j (dP_j only)
+  const uint32_t sBar = base + (2 + RA + RB) * TILE;
   const uint32_t q_full = sBar, dp_full = sBar + 8, ds_full = sBar + 16, acc_full = sBar + 24;
   auto s_full = [&](int u) { return sBar + 32 + 8 * u; };
-  auto st_full = [&](int s) { return sBar + 48 + 8 * s; };
-  auto st_empty = [&](int s) { return sBar + 64 + 8 * s; };
-  const uint32_t tmem_slot = sBar + 80;
+  auto k_full = [&](int s) { return sBar + 48 + 8 * s; };
+  auto k_empty = [&](int s) { return sBar + 80 + 8 * s; };
+  auto v_full = [&](int s) { return sBar + 112 + 8 * s; };
+  auto v_empty = [&](int s) { return sBar + 128 + 8 * s; };
+  const uint32_t tmem_slot = sBar + 144;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
   const int it_q = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;     // heavy tiles first
@@ -343,7 +361,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
 
   if (threadIdx.x == 256) {
     mbar_init(q_full, 1); mbar_init(dp_full, 1); mbar_init(ds_full, 8); mbar_init(acc_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(s_full(s), 1); mbar_init(st_full(s), 1); mbar_init(st_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) mbar_init(s_full(s), 1);
+    for (int s = 0; s < RA; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
+    for (int s = 0; s < RB; ++s) { mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -364,11 +384,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
       load_tile_4d(sQ, &p.tq, q_full, r0, h, b, C::kChunks, CHB);
       load_tile_4d(sdO, &p.tdo, q_full, r0, h, b, C::kChunks, CHB);
       for (int it = 0; it < n; ++it) {
-        const int s = it & 1;
-        mbar_wait(st_empty(s), ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(st_full(s), 2 * TILE);
-        load_tile_4d(sK(s), &p.tk, st_full(s), (j_lo + it) * 128, hk, b, C::kChunks, CHB);
-        load_tile_4d(sV(s), &p.tv, st_full(s), (j_lo + it) * 128, hk, b, C::kChunks, CHB);
+        const int sa = it % RA, sb = it % RB;
+        mbar_wait(k_empty(sa), ((it / RA) & 1) ^ 1);
+        mbar_arrive_expect_tx(k_full(sa), TILE);
+        load_tile_4d(sK(sa), &p.tk, k_full(sa), (j_lo + it) * 128, hk, b, C::kChunks, CHB);
+        mbar_wait(v_empty(sb), ((it / RB) & 1) ^ 1);
+        mbar_arrive_expect_tx(v_full(sb), TILE);
+        load_tile_4d(sV(sb), &p.tv, v_full(sb), (j_lo + it) * 128, hk, b, C::kChunks, CHB);
       }
     }
   } else if (warp == 8) {
@@ -378,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
       constexpr uint32_t IDESC_ACC = make_idesc(1, FMT, FMT, 0, 1, 128, D);
       const uint32_t q_lo = desc_lo(sQ, 16), do_lo = desc_lo(sdO, 16);
       const uint32_t kk_lo = desc_lo(sK(0), 16), vk_lo = desc_lo(sV(0), 16), km_lo = desc_lo(sK(0), CHB);
-      constexpr uint32_t STG = (2 * TILE) >> 4;
+      constexpr uint32_t STG = TILE >> 4;
       auto issue_abt = [&](uint32_t dcol, uint32_t a0, uint32_t b0) {
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
@@ -387,32 +409,37 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
         }
       };
       mbar_wait(q_full, 0);
-      mbar_wait(st_full(0), 0);
+      mbar_wait(k_full(0), 0);
       tc_fence_after();
       issue_abt(0, q_lo, kk_lo);
       tc_commit_u(s_full(0));
+      mbar_wait(v_full(0), 0);
+      tc_fence_after();
       issue_abt(T_DP, do_lo, vk_lo);
       tc_commit_u(dp_full);
+      tc_commit_u(v_empty(0));
       for (int it = 0; it < n; ++it) {
-        const uint32_t s = it & 1;
+        const uint32_t u = it & 1, sa = it % RA, na = (it + 1) % RA, nb = (it + 1) % RB;
         if (it + 1 < n) {
-          mbar_wait(st_full(s ^ 1), ((it + 1) >> 1) & 1);
+          mbar_wait(k_full(na), ((it + 1) / RA) & 1);
           tc_fence_after();
-          issue_abt((s ^ 1) * 128, q_lo, kk_lo + (s ^ 1) * STG);
-          tc_commit_u(s_full(s ^ 1));
+          issue_abt((u ^ 1) * 128, q_lo, kk_lo + na * STG);
+          tc_commit_u(s_full(u ^ 1));
         }
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          mma_f16_ts_u(tmem + T_DQ, tmem + T_DP + (kk >> 2) * 64 + (kk & 3) * 8, km_lo + s * STG + kk * (2048 >> 4),
+          mma_f16_ts_u(tmem + T_DQ, tmem + T_DP + (kk >> 2) * 64 + (kk & 3) * 8, km_lo + sa * STG + kk * (2048 >> 4),
                        kDescHiSw128, IDESC_ACC, (it > 0 || kk > 0) ? 1u : 0u);
+        tc_commit_u(k_empty(sa));                        // K_j: S_j first, dQ_j last
         if (it + 1 < n) {
-          issue_abt(T_DP, do_lo, vk_lo + (s ^ 1) * STG);
+          mbar_wait(v_full(nb), ((it + 1) / RB) & 1);
+          tc_fence_after();
+          issue_abt(T_DP, do_lo, vk_lo + nb * STG);
           tc_commit_u(dp_full);
+          tc_commit_u(v_empty(nb));                      // V_j is only read by dP_j
         }
-        // K_j / V_j of this stage: last readers are dQ_j (K) and dP_j (V, issued earlier) -> all committed here
-        tc_commit_u(st_empty(s));
       }
       tc_commit_u(acc_full);
     }
