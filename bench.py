@@ -43,6 +43,11 @@ WORKLOADS = {
     "long_window": dict(B=1, H=32, Sq=32768, Skv=32768, D=128, causal=True, window=4096, dtype="bf16",
                         label="causal + sliding window 4096, bf16 B=1 H=32 N=32768 D=128 forward"),
     "small": dict(B=1, H=4, Sq=1024, Skv=1024, D=128, causal=False, window=-1, dtype="bf16", label="small"),
+    # config 5: total sequence fixed, split over the ranks (strong scaling); K/V blocks travel over NVLink (umfa/ring.py)
+    "ring128k": dict(B=1, H=32, Sq=131072, Skv=131072, D=128, causal=True, window=-1, dtype="bf16", ring=True,
+                     label="128k-token causal context-parallel ring attention bf16 H=32 D=128"),
+    "ring16k": dict(B=1, H=8, Sq=16384, Skv=16384, D=128, causal=True, window=-1, dtype="bf16", ring=True,
+                    label="16k-token causal ring attention (smoke size)"),
 }
 
 
@@ -76,8 +81,8 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+    def __init__(self, index, interval=0.05):
+        self.index, self.samples, self.stop_flag, self.thread, self.interval = index, [], False, None, interval
 
     def _run(self):
         while not self.stop_flag:
@@ -88,7 +93,7 @@ class ClockSampler:
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 return
-            time.sleep(0.05)
+            time.sleep(self.interval)
 
     def start(self):
         self.thread = threading.Thread(target=self._run, daemon=True)
@@ -154,6 +159,71 @@ def run_reference(args, w, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_ring(args, w, rank, local_rank, world):
+    """Config 5: causal ring attention over `world` GPUs, total sequence fixed (strong scaling)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import umfa
+    from umfa import ring
+    dev = torch.device("cuda", local_rank)
+    B, H, N, D = w["B"], w["H"], w["Sq"], w["D"]
+    C = N // (2 * world)
+    scale = 1.0 / float(np.sqrt(D))
+    tdt = {"bf16": torch.bfloat16, "fp16": torch.float16}[w["dtype"]]
+    ctx = umfa.MFAContext()
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    mk = lambda: torch.randn(B, H, C, D, device=dev, dtype=torch.float32, generator=g).to(tdt)
+    qp, kp, vp = (mk(), mk()), (mk(), mk()), (mk(), mk())
+    be = ring.CudaBackend(ctx, dist if world > 1 else None, dev, w["dtype"])
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        ring.ring_attention_forward(be, qp, kp, vp, rank, world, scale)
+    barrier()
+    l0 = be.launches
+    sampler = ClockSampler(local_rank, interval=0.25)     # the ring driver is host-call heavy: keep fork() traffic low
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        ring.ring_attention_forward(be, qp, kp, vp, rank, world, scale)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    flops = 4.0 * B * H * ring.visible_pairs_causal(N) * D
+    value = flops * args.steps / (ms * 1e-3) / 1e12
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        kv_hop_bytes = 4 * B * H * C * D * 2
+        line = {"metric": "attention forward TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+                "config": {"workload": w["label"], "total_seq": N, "per_gpu_rows": 2 * C, "H": H, "D": D,
+                           "parallelism": f"context parallel x{world}, zig-zag ring, NCCL send/recv of K/V ({kv_hop_bytes / 1e6:.0f} MB per hop) on a side stream",
+                           "cache": "per-rank K/V + O working set >> 126 MB L2" if B * H * C * D * 2 * 6 > 126e6 else "small"},
+                "roofline": {"bound": "tensor", "achieved": value / world, "peak": peak, "unit": "TFLOP/s",
+                             "frac": value / world / peak, "traffic": None, "peak_source": peak_src,
+                             "note": "per-GPU share of the whole-job rate (includes merge kernels and exposed comm)"},
+                "e2e": None, "gpu_launches": int(be.launches - l0), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,6 +254,10 @@ def main():
     os.environ["MFA_CUDA_DEVICE"] = str(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if w.get("ring"):
+        run_ring(args, w, rank, local_rank, world)
+        return
 
     import umfa
     from umfa import _ffi

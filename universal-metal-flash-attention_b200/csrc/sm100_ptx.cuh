@@ -201,6 +201,14 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : MFA_R8(r, 0), MFA_R8(r, 8)
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
