@@ -1,0 +1,100 @@
+"""GPU parity for the int8 tensor-core quantised forward (csrc/attn_fwd_tcq.cu) through mfa_quantized_forward_with_lse.
+
+Oracle: attention (fp64 accumulate) on the oracle's own dequantised operands -- the quantiser is bit-exact
+(tests/test_gpu_quant.py), so both sides see identical int8 / int4 codes and scales.  The kernel differs from the
+oracle only by its bf16 P (and bf16 P*vs in block mode): bound 2e-2 relative to max|ref| like every 16-bit path, plus
+the north_star's quantised-output bounds against the UNQUANTISED oracle: cosine >= 0.99 (int8) / 0.95 (int4) and the
+reference's rel-L2 gate 0.25 (QuantizedAttentionTest.swift:519-520)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import umfa
+    c = umfa.MFAContext()
+    yield c
+    c.close()
+
+
+def fake_quant(x, bits, mode, D):
+    flat = x.reshape(-1, D)
+    S = x.shape[2]
+    if mode == 2:
+        # blocks of 64 tokens inside each (b, h): quantise head by head so blocks never straddle heads
+        out = np.empty_like(flat)
+        for i in range(0, flat.shape[0], S):
+            codes, sc = O.quantize(flat[i:i + S], bits=bits, block_rows=64, clamp_scale_min=1e-8)
+            out[i:i + S] = O.dequantize(codes, sc, S, D, bits=bits, block_rows=64)
+        return out.reshape(x.shape)
+    codes, sc = O.quantize(flat, bits=bits, clamp_scale_min=1e-8)
+    return O.dequantize(codes, sc, flat.shape[0], D, bits=bits).reshape(x.shape)
+
+
+def cosine(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
+
+
+def run_case(ctx, B, H, Sq, Skv, target, mode, causal=False, seed=0, outliers=False, in_prec="fp32"):
+    import umfa
+    D = 128
+    bits = 8 if target == "int8" else 4
+    rng = np.random.default_rng(seed)
+    q, k, v = (rng.standard_normal(s).astype(np.float32) for s in ((B, H, Sq, D), (B, H, Skv, D), (B, H, Skv, D)))
+    if outliers:                                    # FLUX-like: a few K channels carry 8x the energy
+        ch = np.random.default_rng(1).choice(D, 2, replace=False)
+        k[..., ch] *= 8.0
+    if in_prec == "bf16":
+        (q, qb), (k, kb), (v, vb) = (O.round_bf16(x) for x in (q, k, v))
+        args = (qb, kb, vb)
+    else:
+        args = (q, k, v)
+    out, lse = umfa.runtime_quantized_attention(ctx, *args, target_precision=target, quant_mode=mode,
+                                                input_precision=in_prec, causal=causal)
+    assert ctx.last_kernel.startswith("fwd_tcq_"), ctx.last_kernel
+    qd, kd, vd = (fake_quant(x, bits, mode, D) for x in (q, k, v))
+    o_ref, l_ref = O.attention_forward(qd, kd, vd, causal=causal)
+    err = float(np.abs(out - o_ref).max() / np.abs(o_ref).max())
+    assert np.isfinite(out).all()
+    assert err < 2e-2, f"vs dequantised oracle: {err}"
+    assert np.abs(lse - l_ref).max() < 2e-2
+    o_full, _ = O.attention_forward(q, k, v, causal=causal)
+    cs, rl2 = cosine(out, o_full), O.rel_l2(out, o_full)
+    return err, cs, rl2
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("shape", [(1, 2, 256, 256), (1, 1, 128, 128), (2, 2, 300, 777), (1, 2, 1000, 130), (1, 1, 77, 515)])
+def test_tcq_int8_shapes(ctx, mode, shape):
+    B, H, Sq, Skv = shape
+    err, cs, rl2 = run_case(ctx, B, H, Sq, Skv, "int8", mode, seed=Sq)
+    assert cs >= 0.99 and rl2 < 0.25, (cs, rl2)
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_tcq_int8_causal(ctx, mode):
+    err, cs, rl2 = run_case(ctx, 1, 2, 640, 640, "int8", mode, causal=True, seed=3)
+    assert cs >= 0.99 and rl2 < 0.25
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_tcq_int4(ctx, mode):
+    err, cs, rl2 = run_case(ctx, 1, 2, 512, 512, "int4", mode, seed=4)
+    assert cs >= 0.95, cs
+
+
+def test_tcq_outlier_channels_block_scales_help(ctx):
+    """With outlier K channels per-block scales must not be worse than per-tensor scales (SageAttention motivation)."""
+    _, cs_t, _ = run_case(ctx, 1, 2, 512, 512, "int8", 0, seed=5, outliers=True)
+    _, cs_b, _ = run_case(ctx, 1, 2, 512, 512, "int8", 2, seed=5, outliers=True)
+    assert cs_t >= 0.99 and cs_b >= 0.99
+
+
+def test_tcq_bf16_inputs(ctx):
+    err, cs, rl2 = run_case(ctx, 1, 2, 384, 384, "int8", 2, seed=6, in_prec="bf16")
+    assert cs >= 0.99

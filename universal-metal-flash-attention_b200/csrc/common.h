@@ -83,6 +83,13 @@ cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st);
 bool bwd_tc_eligible(const AttnParams& p);
 cudaError_t launch_bwd_tc(const AttnParams& p, cudaStream_t st);
 
+// int8 tensor-core forward (attn_fwd_tcq.cu): int8 / int4 codes, symmetric, D = 128, per-tensor or 64-multiple block scales.
+bool fwd_tcq_eligible(const AttnParams& p);
+size_t fwd_tcq_scratch_bytes(const AttnParams& p);
+cudaError_t launch_fwd_tcq(const AttnParams& p, void* scratch, cudaStream_t st);
+cudaError_t launch_codes_to_bf16(const void* codes, void* dst, uint64_t n, cudaStream_t st);
+cudaError_t launch_int4_to_int8(const void* packed, void* codes, uint64_t n, cudaStream_t st);
+
 // quantiser & friends
 cudaError_t launch_quantize(const void* src, int src_dtype, void* codes, float* scales, uint64_t rows, uint64_t cols,
                             uint32_t block_rows, uint32_t block_cols, int bits, float scale_floor, cudaStream_t st);

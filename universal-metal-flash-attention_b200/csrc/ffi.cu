@@ -52,7 +52,7 @@ struct Context {
   double last_latency = 0.0;
   int refs = 0;
   std::mutex mu;
-  enum { kMask, kLse, kDterm, kQCodes, kKCodes, kVCodes, kQScales, kKScales, kVScales, kTmpO, kNumScratch };
+  enum { kMask, kLse, kDterm, kQCodes, kKCodes, kVCodes, kQScales, kKScales, kVScales, kTmpO, kQTmp, kNumScratch };
   Scratch scratch[kNumScratch];
   std::vector<float> row_scales[3];
   const char* last_kernel = "none";
@@ -476,7 +476,13 @@ mfa_error_t qforward_core(Context* ctx, const QFwdArgs& a) {
     p.mask = a.mask_buf->dev; p.mask_kind = kMaskAdditive; p.mask_scalar = kMaskF32;
     p.mask_sk = 1; p.mask_sq = a.Skv; p.mask_sh = (int64_t)a.Sq * a.Skv; p.mask_sb = (int64_t)a.H * a.Sq * a.Skv;
   }
-  e = launch_fwd_simt(p, st);
+  if (fwd_tcq_eligible(p)) {
+    void* tmp = ctx->scratch[Context::kQTmp].get(fwd_tcq_scratch_bytes(p));
+    if (!tmp) return MFA_ERROR_MEMORY_ALLOCATION;
+    e = launch_fwd_tcq(p, tmp, st);
+  } else {
+    e = launch_fwd_simt(p, st);
+  }
   tm.stop();
   ctx->last_kernel = g_last_kernel;
   if (e != cudaSuccess) return cuda_fail(e, "quantised forward launch");
