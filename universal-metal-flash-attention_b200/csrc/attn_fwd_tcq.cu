@@ -229,13 +229,13 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tcq_kernel(const __grid_const
           l *= alpha;
           if (it > 0) {
 #pragma unroll
-            for (int ch = 0; ch < D / 32; ++ch) {
-              uint32_t ou[32];
-              tmem_ld_x32(tO + ch * 32, ou);
+            for (int ch = 0; ch < D / 16; ++ch) {           // 16 columns at a time: the 128 scores stay live in registers
+              uint32_t ou[16];
+              tmem_ld_x16(tO + ch * 16, ou);
               tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) ou[i] = __float_as_uint(__uint_as_float(ou[i]) * alpha);
-              tmem_st_x32(tO + ch * 32, ou);
+              for (int i = 0; i < 16; ++i) ou[i] = __float_as_uint(__uint_as_float(ou[i]) * alpha);
+              tmem_st_x16(tO + ch * 16, ou);
             }
           }
         }
@@ -251,18 +251,18 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tcq_kernel(const __grid_const
         }
         float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {                 // one 64-key half at a time keeps the live set under 168 registers
+        for (int hh = 0; hh < 2; ++hh) {                 // packed pairs overwrite the registers of scores already consumed
           const float ah = hh ? a1 : a0, nk = hh ? nk1 : nk0, vh = hh ? v1 : v0;
-          uint32_t pk[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float p0 = ex2(fmaf(s[64 * hh + 2 * i], ah, nk));
             const float p1 = ex2(fmaf(s[64 * hh + 2 * i + 1], ah, nk));
             sum0 += p0; sum1 += p1;
-            pk[i] = v_blocks ? pack_bf16(p0 * vh, p1 * vh) : pack_bf16(p0, p1);
+            su[32 * hh + i] = v_blocks ? pack_bf16(p0 * vh, p1 * vh) : pack_bf16(p0, p1);
           }
-          tmem_st_x32(tS + 32 * hh, pk);
         }
+        tmem_st_x32(tS, su);
+        tmem_st_x32(tS + 32, su + 32);
         l += sum0 + sum1;
         tmem_wait_st();
         tc_fence_before();

@@ -113,6 +113,54 @@ __global__ void __launch_bounds__(256) quant_span_kernel(const T* __restrict__ s
   }
 }
 
+// ---- per-tensor fast path (one scale for the whole array, n % 8 == 0): vectorised absmax with one atomicMax per CTA,
+// then a vectorised apply; both HBM-bound (read 2x, write once).
+template <typename T>
+__global__ void __launch_bounds__(256) absmax_flat_kernel(const T* __restrict__ src, unsigned int* __restrict__ amax_bits,
+                                                          uint64_t n8) {
+  __shared__ float red[8];
+  float amax = 0.f;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (uint64_t)gridDim.x * blockDim.x) {
+    float x[8];
+    Vec8<T>::load(src + i * 8, x);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(x[k]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) amax = fmaxf(amax, red[i]);
+    atomicMax(amax_bits, __float_as_uint(amax));
+  }
+}
+
+template <typename T, int BITS>
+__global__ void __launch_bounds__(256) quant_flat_kernel(const T* __restrict__ src, uint8_t* __restrict__ codes,
+                                                         const float* __restrict__ scale, uint64_t n8) {
+  const float sc = *scale;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (uint64_t)gridDim.x * blockDim.x) {
+    float x[8];
+    Vec8<T>::load(src + i * 8, x);
+    int q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[k] = quant_code(x[k], sc, BITS);
+    if (BITS == 8) {
+      uint2 out;
+      out.x = (q[0] & 0xFF) | ((q[1] & 0xFF) << 8) | ((q[2] & 0xFF) << 16) | ((uint32_t)(q[3] & 0xFF) << 24);
+      out.y = (q[4] & 0xFF) | ((q[5] & 0xFF) << 8) | ((q[6] & 0xFF) << 16) | ((uint32_t)(q[7] & 0xFF) << 24);
+      reinterpret_cast<uint2*>(codes)[i] = out;
+    } else {
+      uint32_t out = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out |= (uint32_t)((q[k] + 8) & 0xF) << (4 * k);
+      reinterpret_cast<uint32_t*>(codes)[i] = out;
+    }
+  }
+}
+
 // ---- generic path, kernel 1: absmax of arbitrary block_rows x block_cols tiles via uint-bit atomicMax
 // (|x| >= 0, so the IEEE bit pattern orders like the value -- the reference GPU path does the same,
 // GEMMRuntimeQuantization.swift:22-41).
@@ -312,6 +360,16 @@ cudaError_t quantize_typed(const T* src, uint8_t* codes, float* scales, uint64_t
   cudaError_t e = cudaMemsetAsync(scales, 0, nblocks * sizeof(float), st);
   if (e != cudaSuccess) return e;
   const uint64_t n = rows * cols;
+  if (nblocks == 1 && (n % 8) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(codes) & 7) == 0) {
+    const unsigned grid = grid_for(n / 8, 256) < 148u * 8 ? grid_for(n / 8, 256) : 148u * 8;
+    absmax_flat_kernel<T><<<grid, 256, 0, st>>>(src, reinterpret_cast<unsigned int*>(scales), n / 8);
+    finalize_scales_kernel<<<1, 32, 0, st>>>(scales, 1, bits, floor_v);
+    if (bits == 8) quant_flat_kernel<T, 8><<<grid, 256, 0, st>>>(src, codes, scales, n / 8);
+    else quant_flat_kernel<T, 4><<<grid, 256, 0, st>>>(src, codes, scales, n / 8);
+    g_launch_count += 3;
+    g_last_kernel = "quant_flat";
+    return cudaGetLastError();
+  }
   absmax_generic_kernel<T><<<grid_for((n + 63) / 64, 256), 256, 0, st>>>(
       src, reinterpret_cast<unsigned int*>(scales), rows, cols, br, bc, group_rows, nb_per_group, nbc);
   finalize_scales_kernel<<<(unsigned)((nblocks + 255) / 256), 256, 0, st>>>(scales, nblocks, bits, floor_v);
