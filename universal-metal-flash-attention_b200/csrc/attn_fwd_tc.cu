@@ -59,20 +59,54 @@ struct Cfg {
   static constexpr int kSmem = (2 + kStages) * kTile + kBarBytes + 1024;
 };
 
-// 2^x for x <= ~8 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max rel err 8.6e-5): relieves
-// the MUFU pipe, which is co-critical with the tensor pipe at head_dim 128 (16 ex2/clk/SM vs 8192 FLOP/clk/SM).
-__device__ __forceinline__ float exp2_poly(float x) {
-  x = fmaxf(x, -125.f);
-  float xr;
-  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(xr) : "f"(x), "f"(12582912.f));     // 1.5 * 2^23: low bits = floor(x)
-  const float f = x - (xr - 12582912.f);                                       // [0, 1)
-  float pz = fmaf(f, 0.07706582f, 0.22764632f);
-  pz = fmaf(pz, f, 0.69511649f);
-  pz = fmaf(pz, f, 1.0f);
-  return __int_as_float(__float_as_int(pz) + (__float_as_int(xr) << 23));
+// 2^x for a pair of x <= ~8 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max rel err 8.6e-5),
+// in packed f32x2 arithmetic: relieves the MUFU pipe, which is co-critical with the tensor pipe at head_dim 128
+// (16 ex2/clk/SM vs 8192 FLOP/clk/SM).
+__device__ __forceinline__ f32x2 exp2_poly2(f32x2 x) {
+  float x0, x1;
+  unpack2(x, x0, x1);
+  x = pack2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  const f32x2 magic = pack2(12582912.f, 12582912.f);                  // 1.5 * 2^23: low mantissa bits = floor(x)
+  const f32x2 xr = add2_rm(x, magic);
+  const f32x2 f = sub2(x, sub2(xr, magic));                           // [0, 1)
+  f32x2 pz = fma2(f, pack2(0.07706582f, 0.07706582f), pack2(0.22764632f, 0.22764632f));
+  pz = fma2(pz, f, pack2(0.69511649f, 0.69511649f));
+  pz = fma2(pz, f, pack2(1.0f, 1.0f));
+  float p0, p1, r0, r1;
+  unpack2(pz, p0, p1);
+  unpack2(xr, r0, r1);
+  return pack2(__int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23)),
+               __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23)));
 }
 
-// POLY = n > 0: one element in every 2n goes through exp2_poly instead of MUFU.EX2 (only on tiles without masking,
+// P = exp2(s c - m c) for the 128 scores of one row, packed to 16-bit pairs; row sum of the fp32 values.
+// NP of every 8 element pairs take the polynomial (compile-time pattern, so the loop body is branch-free).
+template <bool BF16, int NP>
+__device__ __forceinline__ void exp_phase(const float* s, float c, float neg_mc, uint32_t* pk, float& sum0, float& sum1) {
+  constexpr int kSel[5] = {0x00, 0x08, 0x22, 0x52, 0xAA};
+  const f32x2 c2 = pack2(c, c), nm2 = pack2(neg_mc, neg_mc);
+  f32x2 acc_a = pack2(0.f, 0.f), acc_b = acc_a;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    const f32x2 x = fma2(pack2(s[2 * i], s[2 * i + 1]), c2, nm2);
+    f32x2 pp;
+    float p0, p1;
+    if ((kSel[NP] >> (i & 7)) & 1) {
+      pp = exp2_poly2(x);
+      unpack2(pp, p0, p1);
+    } else {
+      float x0, x1;
+      unpack2(x, x0, x1);
+      p0 = ex2(x0); p1 = ex2(x1);
+      pp = pack2(p0, p1);
+    }
+    if (i & 1) acc_b = add2(acc_b, pp); else acc_a = add2(acc_a, pp);
+    pk[i] = BF16 ? pack_bf16(p0, p1) : pack_f16(p0, p1);
+  }
+  unpack2(add2(acc_a, acc_b), sum0, sum1);
+}
+
+// POLY = n in 0..4: n of every 8 element pairs go through exp2_poly2 instead of MUFU.EX2 (only on tiles without masking,
 // so masked elements always get an exact zero weight).
 template <int D, bool BF16, int POLY>
 __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_constant__ FwdTcParams p) {
@@ -249,26 +283,10 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         }
         m = m_new;
         const float neg_mc = (m == -CUDART_INF_F) ? 0.f : -m * c;
-        float sum0 = 0.f, sum1 = 0.f;
         uint32_t pk[64];
-        if (POLY > 0 && !any_mask) {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const float x0 = fmaf(s[2 * i], c, neg_mc), x1 = fmaf(s[2 * i + 1], c, neg_mc);
-            const float p0 = ex2(x0);
-            const float p1 = (POLY > 0 && (i % POLY) == POLY - 1) ? exp2_poly(x1) : ex2(x1);
-            sum0 += p0; sum1 += p1;
-            pk[i] = BF16 ? pack_bf16(p0, p1) : pack_f16(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const float p0 = ex2(fmaf(s[2 * i], c, neg_mc));
-            const float p1 = ex2(fmaf(s[2 * i + 1], c, neg_mc));
-            sum0 += p0; sum1 += p1;
-            pk[i] = BF16 ? pack_bf16(p0, p1) : pack_f16(p0, p1);
-          }
-        }
+        float sum0, sum1;
+        if (POLY > 0 && !any_mask) exp_phase<BF16, POLY>(s, c, neg_mc, pk, sum0, sum1);
+        else exp_phase<BF16, 0>(s, c, neg_mc, pk, sum0, sum1);
         l += sum0 + sum1;
         tmem_st_x32(tS, pk);
         tmem_st_x32(tS + 32, pk + 32);
@@ -336,7 +354,7 @@ bool view_ok(const TensorView& t, int64_t, int64_t Hn, int64_t B) { return tc::v
 
 int poly_setting() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MFA_FWD_POLY"); v = e ? atoi(e) : 0; }
+  if (v < 0) { const char* e = getenv("MFA_FWD_POLY"); v = e ? atoi(e) : 2; }
   return v;
 }
 
@@ -356,10 +374,10 @@ cudaError_t launch_k(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
 template <int D, bool BF16>
 cudaError_t launch(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
   switch (poly_setting()) {
-    case 0: return launch_k<D, BF16, 0>(prm, grid, st);
     case 1: return launch_k<D, BF16, 1>(prm, grid, st);
-    case 4: return launch_k<D, BF16, 4>(prm, grid, st);
     case 2: return launch_k<D, BF16, 2>(prm, grid, st);
+    case 3: return launch_k<D, BF16, 3>(prm, grid, st);
+    case 4: return launch_k<D, BF16, 4>(prm, grid, st);
     default: return launch_k<D, BF16, 0>(prm, grid, st);
   }
 }
