@@ -67,6 +67,16 @@ def fwd_flops(w):
     return 4.0 * w["B"] * w["H"] * visible_pairs(w["Sq"], w["Skv"], w["causal"], w["window"]) * w["D"]
 
 
+def load_traffic(workload, kernel):
+    """dram read+write bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            d = json.load(f)[workload][kernel]
+        return (d["read_mb"] + d["write_mb"]) * 1e6
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -396,7 +406,10 @@ def main():
                            "cache": f"inputs rotate over {nsets} buffer sets ({nsets * (in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2)",
                            "kernel": kernel_name, "mode": args.mode, "output": "fp32 O (reference contract)"},
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / peak,
+                             "traffic": load_traffic(args.workload, kernel_name) if args.mode == "fwd" else None,
+                             "traffic_unit": "bytes per launch (ncu dram read+write, profiles/ncu_traffic.json)",
+                             "peak_source": peak_src,
                              "flops_per_launch": flops, "launch_ms_median": med,
                              "frac_of_nominal_2250": achieved / 2250.0},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
