@@ -106,3 +106,30 @@ def test_tc_matches_simt_bitwise_stats_close(ctx, monkeypatch):
     b = umfa.flash_attention_forward(ctx, q, k, v, input_precision="bf16", output_precision="fp32", layout="bhsd", causal=True)
     assert ctx.last_kernel == "fwd_simt"
     assert rel_max(a, b) < 2e-2
+
+
+@pytest.mark.parametrize("shape,D,causal", [((2, 12, 1024, 1024), 128, False), ((1, 20, 900, 1300), 64, True),
+                                            ((3, 5, 1536, 1536), 128, True)])
+def test_tc_host_pipeline_matches_single_shot(ctx, shape, D, causal, monkeypatch):
+    """Host-buffer calls above the chunk threshold run as an H2D / kernel / D2H pipeline over (batch, head-group)
+    chunks (ffi.cu forward_pipelined).  Same kernel on the same data: outputs must equal the single-shot path bit for
+    bit, and both must match the oracle."""
+    import umfa
+    B, H, Sq, Skv = shape
+    rng = np.random.default_rng(11)
+    q, k, v = (rng.standard_normal((B, H, S, D)).astype(np.float32) for S in (Sq, Skv, Skv))
+    (qa, qv), (ka, kv), (va, vv) = (to_dtype(x, "bf16") for x in (q, k, v))
+    kw = dict(input_precision="bf16", output_precision="fp32", layout="bhsd", causal=causal, return_lse=True)
+    monkeypatch.setenv("MFA_PIPELINE_CHUNK_MB", "1.5")        # read once per process: several chunks at these sizes
+    out_p, lse_p = umfa.flash_attention_forward(ctx, qa, ka, va, **kw)
+    assert ctx.last_kernel.startswith("fwd_tc_"), ctx.last_kernel
+    lat = ctx.gpu_latency
+    assert lat > 0
+    monkeypatch.setenv("MFA_DISABLE_PIPELINE", "1")
+    out_s, lse_s = umfa.flash_attention_forward(ctx, qa, ka, va, **kw)
+    monkeypatch.delenv("MFA_DISABLE_PIPELINE")
+    assert np.array_equal(out_p, out_s)
+    assert np.array_equal(lse_p, lse_s)
+    ref, lref = O.attention_forward(qv, kv, vv, causal=causal)
+    assert rel_max(out_p, ref) < 2e-2
+    assert np.abs(lse_p - lref).max() < 2e-2

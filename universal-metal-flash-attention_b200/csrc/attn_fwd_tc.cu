@@ -3,28 +3,41 @@
 // Replaces the reference's `attention` kernel, type = forward
 // (metal-flash-attention/Sources/FlashAttention/Attention/AttentionKernel/AttentionKernel+Source.swift:372-416,
 //  online softmax +Softmax.swift:641-702, finalisation +Caching.swift:396-400) for bf16/fp16 operands with
-// head_dim 64 or 128.  Same math, re-derived for Blackwell:
+// head_dim 64 or 128, and -- operand mode kFwdI8 -- the quantised forward (QuantizedAttention.swift:71-91,358-463)
+// for symmetric int8 codes at head_dim 128.  Same math, re-derived for Blackwell:
 //
 //   one CTA = 2 query tiles of 128 rows (one per softmax warpgroup) sharing one K/V stream
-//   warp 9  : TMA producer   Q tiles once, then K_j, V_j tiles through an NS-stage mbarrier ring (128B swizzle)
-//   warp 8  : MMA issuer     S_t = Q_t K_j^T   (tcgen05.mma SS, fp32 accumulator in TMEM columns [t*128, +128))
-//                            O_t += P_t V_j    (tcgen05.mma TS: P read straight from TMEM, V MN-major from smem)
+//   warp 9       : TMA producer   Q tiles once, then K_j, V_j tiles through an NS-stage mbarrier ring (128B swizzle)
+//   warp 8 / 10  : MMA issuer of tile 0 / 1 (each tile has its own in-order chain, the tensor pipe interleaves them)
+//                    S_t = Q_t K_j^T  (tcgen05.mma SS, fp32 -- or s32 for int8 codes -- accumulator in TMEM columns
+//                                      [t*128, +128))
+//                    O_t += P_t V_j   (tcgen05.mma TS: P read straight from TMEM, V MN-major from smem)
 //   warps 0-3 / 4-7 : softmax warpgroup of tile 0 / 1; thread i owns row i of its tile (tcgen05.ld 32x32b), so
 //                     row max / row sum need no shuffles; P is written back over S as packed 16-bit pairs.
 //
-// The two tiles ping-pong on the tensor pipe: while warpgroup 0 runs exp2 on S_0, the pipe works on tile 1.
+// P is handed to the MMA warp in four 32-key parts: the P V MMAs of part k run while the softmax warps are still in
+// exp2 on part k+1, so only the last quarter of P V and the next S sit on the per-tile dependency chain
+// (ld S -> max -> exp2 -> P V -> S, which -- not pipe throughput -- bounds this kernel; profiles/).
 // O is only rescaled when the running row max grew by more than 2^8 (the stale max is kept otherwise; the final
 // division by l absorbs it), so the O read-modify-write in TMEM is rare.
 // KV tiles that are fully hidden by the causal / sliding-window rule are never loaded (loop bounds), tiles that
 // are partly hidden get an element mask, tiles that are fully visible skip the mask code.
 // Outputs follow the reference contract: O fp32 (or fp16/bf16 on request) and L = m + log2(l) in log2 units.
+//
+// int8 mode: S_int = Q_i8 K_i8^T on kind::i8 (2x the bf16 MMA rate); the softmax warps widen it with I2FP (exact, ALU
+// pipe -- not the I2F that shares the 16/clk MUFU pipe with ex2) and fold every scale into the one packed FFMA that
+// forms the exponent:   x = s_int * a_h + (log2 v_h - m),   a_h = qs[row block] * ks[h] * scale * log2(e),
+// h = 64-key half of the tile.  P' = P v_h (the V block scale rides in the exponent) feeds the P V MMA, which runs on
+// kind::f16 with V's int8 codes widened to bf16 (exact); the row sum takes sum(P') / v_h per half.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <cstdio>
 #include <mutex>
 
 #include "common.h"
+#include "fwd_tc.h"
 #include "sm100_ptx.cuh"
 #include "tc_host.h"
 
@@ -34,29 +47,23 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kThreads = 384;           // warpgroups: softmax 0, softmax 1, {MMA, TMA, 2 idle warps}
+constexpr int kThreads = 384;           // warpgroups: softmax 0, softmax 1, {MMA 0, TMA, MMA 1, idle}
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.f;     // log2 units
+constexpr int kParts = 4;                    // P hand-off granularity: 32 keys = 16 packed TMEM columns
 
-struct FwdTcParams {
-  CUtensorMap tq, tk, tv;
-  void* o;
-  long long o_sb, o_sh, o_ss;
-  float* lse;
-  int o_dtype;
-  int H, Hkv, Sq, Skv;
-  float c;                 // softmax_scale * log2(e)
-  int causal, window;
-};
-
-template <int D>
+template <int D, int MODE>
 struct Cfg {
-  static constexpr int kTile = 128 * D * 2;              // bytes of one 128-row operand tile
-  static constexpr int kChunks = D / 64;                 // 128-byte swizzle chunks per row
-  static constexpr int kChunkBytes = 128 * 128;          // one chunk of 128 rows
+  static constexpr bool kI8 = MODE == kFwdI8;
+  static constexpr int kChunkBytes = 128 * 128;                      // one 128-byte swizzle chunk of 128 rows
+  static constexpr int kQChunks = kI8 ? 1 : D / 64;                  // chunks per Q / K tile
+  static constexpr int kVChunks = D / 64;                            // V is always 16-bit
+  static constexpr int kQTile = kQChunks * kChunkBytes;
+  static constexpr int kVTile = kVChunks * kChunkBytes;
+  static constexpr int kStage = kVTile;                              // ring stage (K tiles may use part of it)
   static constexpr int kStages = D == 128 ? 5 : 10;
-  static constexpr int kBarBytes = 64 + 16 * kStages + 16;
-  static constexpr int kSmem = (2 + kStages) * kTile + kBarBytes + 1024;
+  static constexpr int kBarBytes = 112 + 16 * kStages + 16;
+  static constexpr int kSmem = 2 * kQTile + kStages * kStage + kBarBytes + 1024;
 };
 
 // 2^x for a pair of x <= ~8 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max rel err 8.6e-5),
@@ -79,50 +86,82 @@ __device__ __forceinline__ f32x2 exp2_poly2(f32x2 x) {
                __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23)));
 }
 
-// P = exp2(s c - m c) for the 128 scores of one row, packed to 16-bit pairs; row sum of the fp32 values.
-// NP of every 8 element pairs take the polynomial (compile-time pattern, so the loop body is branch-free).
+// P = exp2(s a + nk) for 32 scores of one row (one hand-off part), packed to 16-bit pairs; the fp32 row sum
+// accumulates in a packed register.  NP of every 8 element pairs take the polynomial (compile-time pattern, so the
+// loop body is branch-free).
 template <bool BF16, int NP>
-__device__ __forceinline__ void exp_phase(const float* s, float c, float neg_mc, uint32_t* pk, float& sum0, float& sum1) {
+__device__ __forceinline__ void exp_part(const float* s, f32x2 a2, f32x2 nk2, uint32_t* pk, f32x2& acc_a, f32x2& acc_b) {
   constexpr int kSel[5] = {0x00, 0x08, 0x22, 0x52, 0xAA};
-  const f32x2 c2 = pack2(c, c), nm2 = pack2(neg_mc, neg_mc);
-  f32x2 acc_a = pack2(0.f, 0.f), acc_b = acc_a;
 #pragma unroll
-  for (int i = 0; i < 64; ++i) {
-    const f32x2 x = fma2(pack2(s[2 * i], s[2 * i + 1]), c2, nm2);
+  for (int i = 0; i < 16; ++i) {
+    const f32x2 x = fma2(pack2(s[2 * i], s[2 * i + 1]), a2, nk2);
     f32x2 pp;
     float p0, p1;
     if ((kSel[NP] >> (i & 7)) & 1) {
       pp = exp2_poly2(x);
-      unpack2(pp, p0, p1);
     } else {
       float x0, x1;
       unpack2(x, x0, x1);
-      p0 = ex2(x0); p1 = ex2(x1);
-      pp = pack2(p0, p1);
+      pp = pack2(ex2(x0), ex2(x1));
     }
     if (i & 1) acc_b = add2(acc_b, pp); else acc_a = add2(acc_a, pp);
+    unpack2(pp, p0, p1);
     pk[i] = BF16 ? pack_bf16(p0, p1) : pack_f16(p0, p1);
   }
-  unpack2(add2(acc_a, acc_b), sum0, sum1);
+}
+
+// The whole exp2 phase of one KV step: four 32-key parts, each stored to TMEM and published to the MMA warp one part
+// of arithmetic later (so tcgen05.wait::st never stalls on the store just issued).  One straight-line block: ptxas
+// interleaves the MUFU and polynomial work of neighbouring parts.  Sums of the two 64-key halves are kept apart
+// (int8 mode folds the V block scale of each half into its exponent).
+template <bool BF16, int NP, bool TR>
+__device__ __forceinline__ void exp_phase(const float* s, float a0, float a1, float nk0, float nk1, uint32_t tS,
+                                          uint32_t bar0, int lane, float& sum_lo, float& sum_hi, unsigned long long* tr) {
+  f32x2 acc[2][2] = {{pack2(0.f, 0.f), pack2(0.f, 0.f)}, {pack2(0.f, 0.f), pack2(0.f, 0.f)}};
+  uint32_t pk[kParts][16];
+#pragma unroll
+  for (int part = 0; part < kParts; ++part) {
+    const bool hi = part >= kParts / 2;
+    const float ah = hi ? a1 : a0, nk = hi ? nk1 : nk0;
+    exp_part<BF16, NP>(s + 32 * part, pack2(ah, ah), pack2(nk, nk), pk[part], acc[hi ? 1 : 0][0], acc[hi ? 1 : 0][1]);
+    if (part > 0) {            // part-1's store was issued a whole part of arithmetic ago: publish it
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8 * (part - 1));
+      if (TR && tr) tr[3 + part - 1] = clock64();
+    }
+    tmem_st_x16(tS + 16 * part, pk[part]);
+  }
+  tmem_wait_st();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar0 + 8 * (kParts - 1));
+  if (TR && tr) tr[3 + kParts - 1] = clock64();
+  float x0, x1;
+  unpack2(add2(acc[0][0], acc[0][1]), x0, x1); sum_lo = x0 + x1;
+  unpack2(add2(acc[1][0], acc[1][1]), x0, x1); sum_hi = x0 + x1;
 }
 
 // POLY = n in 0..4: n of every 8 element pairs go through exp2_poly2 instead of MUFU.EX2 (only on tiles without masking,
 // so masked elements always get an exact zero weight).
-template <int D, bool BF16, int POLY>
+template <int D, int MODE, int POLY, bool TR = false>
 __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_constant__ FwdTcParams p) {
-  using C = Cfg<D>;
-  constexpr int TILE = C::kTile, NS = C::kStages, CHB = C::kChunkBytes;
+  using C = Cfg<D, MODE>;
+  constexpr bool I8 = C::kI8;
+  constexpr bool PBF16 = MODE != kFwdF16;                 // 16-bit format of P (and of V)
+  constexpr int QT = C::kQTile, VT = C::kVTile, STG = C::kStage, NS = C::kStages, CHB = C::kChunkBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t sQ = base, sKV = base + 2 * TILE, sBar = sKV + NS * TILE;
+  const uint32_t sQ = base, sKV = base + 2 * QT, sBar = sKV + NS * STG;
   auto q_full = [&](int t) { return sBar + 8 * t; };
   auto s_full = [&](int t) { return sBar + 16 + 8 * t; };
-  auto p_full = [&](int t) { return sBar + 32 + 8 * t; };
-  auto o_full = [&](int t) { return sBar + 48 + 8 * t; };
-  auto kv_full = [&](int s) { return sBar + 64 + 8 * s; };
-  auto kv_empty = [&](int s) { return sBar + 64 + 8 * NS + 8 * s; };
-  const uint32_t tmem_slot = sBar + 64 + 16 * NS;
+  auto o_full = [&](int t) { return sBar + 32 + 8 * t; };
+  auto p_part = [&](int t, int k) { return sBar + 48 + 8 * (t * kParts + k); };
+  auto kv_full = [&](int s) { return sBar + 112 + 8 * s; };
+  auto kv_empty = [&](int s) { return sBar + 112 + 8 * NS + 8 * s; };
+  const uint32_t tmem_slot = sBar + 112 + 16 * NS;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
   const int qblk = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;   // heavy blocks first
@@ -137,9 +176,10 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
 
   if (threadIdx.x == 256) {
     for (int t = 0; t < 2; ++t) {
-      mbar_init(q_full(t), 1); mbar_init(s_full(t), 1); mbar_init(p_full(t), 4); mbar_init(o_full(t), 1);
+      mbar_init(q_full(t), 1); mbar_init(s_full(t), 1); mbar_init(o_full(t), 1);
+      for (int k = 0; k < kParts; ++k) mbar_init(p_part(t, k), 4);
     }
-    for (int s = 0; s < NS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), nt); }
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -157,70 +197,90 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     // ------------------------------------------------------------------ TMA producer
     reg_dealloc<40>();
     if (lane == 0 && n > 0) {
-      auto load_tile = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int row, int head) {
-        mbar_arrive_expect_tx(bar, TILE);
+      auto load_qk = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int row, int head) {
+        mbar_arrive_expect_tx(bar, QT);
 #pragma unroll
-        for (int c = 0; c < C::kChunks; ++c) tma_load_4d(dst + c * CHB, m, bar, c * 64, row, head, b);
+        for (int c = 0; c < C::kQChunks; ++c) tma_load_4d(dst + c * CHB, m, bar, c * (I8 ? 128 : 64), row, head, b);
       };
-      load_tile(sQ, &p.tq, q_full(0), r0, h);
-      for (int it = 0; it < n; ++it) {
+      auto load_v = [&](uint32_t dst, uint32_t bar, int row) {
+        mbar_arrive_expect_tx(bar, VT);
 #pragma unroll
-        for (int kv = 0; kv < 2; ++kv) {
-          const int idx = 2 * it + kv, s = idx % NS, ph = (idx / NS) & 1;
-          mbar_wait(kv_empty(s), ph ^ 1);
-          load_tile(sKV + s * TILE, kv ? &p.tv : &p.tk, kv_full(s), (j_lo + it) * 128, hk);
-          if (it == 0 && kv == 0 && nt == 2) load_tile(sQ + TILE, &p.tq, q_full(1), r0 + 128, h);
-        }
+        for (int c = 0; c < C::kVChunks; ++c) tma_load_4d(dst + c * CHB, &p.tv, bar, c * 64, row, hk, b);
+      };
+      load_qk(sQ, &p.tq, q_full(0), r0, h);
+      for (int it = 0; it < n; ++it) {
+        const int row = (j_lo + it) * 128;
+        int idx = 2 * it, s = idx % NS;
+        mbar_wait(kv_empty(s), ((idx / NS) & 1) ^ 1);
+        load_qk(sKV + s * STG, &p.tk, kv_full(s), row, hk);
+        if (it == 0 && nt == 2) load_qk(sQ + QT, &p.tq, q_full(1), r0 + 128, h);
+        idx = 2 * it + 1; s = idx % NS;
+        mbar_wait(kv_empty(s), ((idx / NS) & 1) ^ 1);
+        load_v(sKV + s * STG, kv_full(s), row);
       }
     }
-  } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
+  } else if (warp == 8 || warp == 10) {
+    // ------------------------------------------------------------------ MMA issuer of tile t (whole warp, one elected lane issues)
     reg_dealloc<40>();
-    if (n > 0) {
-      constexpr uint32_t FMT = BF16 ? 1u : 0u;
-      constexpr uint32_t IDESC_S = make_idesc(1, FMT, FMT, 0, 0, 128, 128);
-      constexpr uint32_t IDESC_O = make_idesc(1, FMT, FMT, 0, 1, 128, D);
-      const uint32_t q_lo = desc_lo(sQ, 16), k_lo = desc_lo(sKV, 16), v_lo = desc_lo(sKV, CHB);
-      auto issue_s = [&](int t, int idx) {
-        const uint32_t a0 = q_lo + t * (TILE >> 4), b0 = k_lo + (idx % NS) * (TILE >> 4);
+    const int t = (warp - 8) >> 1;
+    if (n > 0 && t < nt) {
+      constexpr uint32_t FMT = PBF16 ? 1u : 0u;
+      constexpr uint32_t IDESC_S = I8 ? make_idesc(2, 1, 1, 0, 0, 128, 128)        // s32 += s8 * s8, K-major A and B
+                                      : make_idesc(1, FMT, FMT, 0, 0, 128, 128);
+      constexpr uint32_t IDESC_O = make_idesc(1, FMT, FMT, 0, 1, 128, D);          // f32 += P (tmem) * V, V MN-major
+      const uint32_t q_lo = desc_lo(sQ, 16) + t * (QT >> 4), k_lo = desc_lo(sKV, 16), v_lo = desc_lo(sKV, CHB);
+      const uint32_t tS = tmem + t * 128, tO = tmem + 256 + t * D;
+      auto issue_s = [&](int idx) {
+        const uint32_t b0 = k_lo + (idx % NS) * (STG >> 4);
+        if constexpr (I8) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = ((kk >> 2) * CHB + (kk & 3) * 32) >> 4;
-          mma_f16_ss_u(tmem + t * 128, a0 + off, kDescHiSw128, b0 + off, kDescHiSw128, IDESC_S, kk > 0);
+          for (int kk = 0; kk < 4; ++kk)           // 32 int8 per MMA = 32 bytes of the 128-byte row
+            mma_i8_ss_u(tS, q_lo + kk * 2, kDescHiSw128, b0 + kk * 2, kDescHiSw128, IDESC_S, kk > 0);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = ((kk >> 2) * CHB + (kk & 3) * 32) >> 4;
+            mma_f16_ss_u(tS, q_lo + off, kDescHiSw128, b0 + off, kDescHiSw128, IDESC_S, kk > 0);
+          }
         }
       };
-      auto issue_o = [&](int t, int idx, bool acc) {
-        const uint32_t b0 = v_lo + (idx % NS) * (TILE >> 4);
+      auto issue_o_part = [&](int idx, int part, bool acc) {
+        const uint32_t b0 = v_lo + (idx % NS) * (STG >> 4);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          mma_f16_ts_u(tmem + 256 + t * D, tmem + t * 128 + kk * 8, b0 + kk * (2048 >> 4), kDescHiSw128, IDESC_O,
-                       (acc || kk > 0) ? 1u : 0u);
+        for (int kk = 2 * part; kk < 2 * part + 2; ++kk)
+          mma_f16_ts_u(tO, tS + kk * 8, b0 + kk * (2048 >> 4), kDescHiSw128, IDESC_O, (acc || kk > 0) ? 1u : 0u);
       };
       auto wait_full = [&](int idx) { mbar_wait(kv_full(idx % NS), (idx / NS) & 1); };
+      unsigned long long* tr = nullptr;            // timeline of CTA (0,0,0): MFA_FWD_TRACE (debug builds of the launch only)
+      if (TR && p.trace && blockIdx.x + blockIdx.y + blockIdx.z == 0 && lane == 0) tr = p.trace + (size_t)t * 64 * 16;
+      mbar_wait(q_full(t), 0);
       wait_full(0);
-      for (int t = 0; t < nt; ++t) {
-        mbar_wait(q_full(t), 0);
-        tc_fence_after();
-        issue_s(t, 0);
-        tc_commit_u(s_full(t));
-      }
+      tc_fence_after();
+      issue_s(0);
+      tc_commit_u(s_full(t));
       tc_commit_u(kv_empty(0));
       for (int it = 0; it < n; ++it) {
         const int vi = 2 * it + 1, ki = 2 * it + 2;
         wait_full(vi);
-        for (int t = 0; t < nt; ++t) {
-          mbar_wait(p_full(t), it & 1);
+        if (TR && tr && it < 64) tr[it * 16 + 13] = clock64();
+#pragma unroll
+        for (int part = 0; part < kParts; ++part) {
+          mbar_wait(p_part(t, part), it & 1);
           tc_fence_after();
-          issue_o(t, vi, it > 0);
-          if (t == nt - 1) tc_commit_u(kv_empty(vi % NS));
-          if (it + 1 < n) {
-            if (t == 0) { wait_full(ki); tc_fence_after(); }
-            issue_s(t, ki);
-            tc_commit_u(s_full(t));
-            if (t == nt - 1) tc_commit_u(kv_empty(ki % NS));
-          } else {
-            tc_commit_u(o_full(t));
-          }
+          if (TR && tr && it < 64) tr[it * 16 + 8 + part] = clock64();
+          issue_o_part(vi, part, it > 0);
+        }
+        tc_commit_u(kv_empty(vi % NS));
+        if (it + 1 < n) {
+          wait_full(ki);
+          tc_fence_after();
+          if (TR && tr && it < 64) tr[it * 16 + 14] = clock64();
+          issue_s(ki);
+          tc_commit_u(s_full(t));
+          tc_commit_u(kv_empty(ki % NS));
+          if (TR && tr && it < 64) tr[it * 16 + 12] = clock64();
+        } else {
+          tc_commit_u(o_full(t));
         }
       }
     }
@@ -233,16 +293,45 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tS = tmem + lane_base + t * 128;
     const uint32_t tO = tmem + lane_base + 256 + t * D;
-    const float c = p.c;
-    float m = -CUDART_INF_F, l = 0.f;
+    float m = -CUDART_INF_F, l = 0.f;                      // m in scaled log2 units (score * scale * log2 e)
     const int chi = p.causal ? min(p.Skv - 1, r) : p.Skv - 1;
     const int clo = p.window >= 0 ? max(0, r - p.window) : 0;
+    // int8 mode: per-row Q scale (folded with c), per-64-key K and V block scales
+    float qsc = p.c;
+    const float* ksp = nullptr;
+    const float* vsp = nullptr;
+    if constexpr (I8) {
+      const int rq = min(r, p.Sq - 1);
+      qsc = (p.qs ? p.qs[((size_t)b * p.H + h) * p.sq_ + rq / p.qbr] : p.qs1) * p.c;
+      ksp = p.ks ? p.ks + ((size_t)b * p.Hkv + hk) * p.sk_ : nullptr;
+      vsp = p.vs ? p.vs + ((size_t)b * p.Hkv + hk) * p.sv_ : nullptr;
+    }
+    const bool v_blocks = I8 && vsp != nullptr;
+    const bool pingpong = nt == 2 && p.pingpong;
 
     if (t < nt) {
       for (int it = 0; it < n; ++it) {
         const int c0 = (j_lo + it) * 128;
+        // multipliers of the two 64-key halves of this tile (int8: blocks are multiples of 64 keys)
+        float a0 = qsc, a1 = qsc, lv0 = 0.f, lv1 = 0.f, iv0 = 1.f, iv1 = 1.f;
+        if constexpr (I8) {
+          a0 = a1 = qsc * p.ks1;
+          if (ksp) {
+            a0 = qsc * ksp[min(c0 / p.kbr, p.nbk - 1)];
+            a1 = qsc * ksp[min((c0 + 64) / p.kbr, p.nbk - 1)];
+          }
+          if (v_blocks) {
+            const float v0 = vsp[min(c0 / p.vbr, p.nbv - 1)], v1 = vsp[min((c0 + 64) / p.vbr, p.nbv - 1)];
+            lv0 = log2f(v0); lv1 = log2f(v1);        // bf16 P' = P v_h has fp32's exponent range: no reference scale needed
+            iv0 = 1.f / v0; iv1 = 1.f / v1;
+          }
+        }
+        unsigned long long* tr = nullptr;
+        if (TR && p.trace && blockIdx.x + blockIdx.y + blockIdx.z == 0 && (threadIdx.x & 127) == 0 && it < 64)
+          tr = p.trace + ((size_t)t * 64 + it) * 16;
         mbar_wait(s_full(t), it & 1);
         tc_fence_after();
+        if (TR && tr) tr[0] = clock64();
         uint32_t su[128];
         tmem_ld_x32(tS, su);
         tmem_ld_x32(tS + 32, su + 32);
@@ -250,6 +339,11 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         tmem_ld_x32(tS + 96, su + 96);
         tmem_wait_ld();
         float* s = reinterpret_cast<float*>(su);
+        if (TR && tr) tr[1] = clock64();
+        if constexpr (I8) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i) s[i] = __int2float_rn((int)su[i]);     // exact (|s| < 2^24); I2FP, not the MUFU-pipe I2F
+        }
         const bool need_mask = (c0 < clo) || (c0 + 127 > chi);
         const bool any_mask = __any_sync(0xffffffffu, need_mask);
         if (any_mask) {
@@ -257,50 +351,62 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
 #pragma unroll
           for (int i = 0; i < 128; ++i) s[i] = (i < lo_i || i > hi_i) ? -CUDART_INF_F : s[i];
         }
-        float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+        float mxa = s[0], mxb = s[1], mxc = s[64], mxd = s[65];
 #pragma unroll
-        for (int i = 4; i < 128; i += 4) {
-          mx0 = fmaxf(mx0, s[i]); mx1 = fmaxf(mx1, s[i + 1]); mx2 = fmaxf(mx2, s[i + 2]); mx3 = fmaxf(mx3, s[i + 3]);
+        for (int i = 2; i < 64; i += 2) {
+          mxa = fmaxf(mxa, s[i]); mxb = fmaxf(mxb, s[i + 1]); mxc = fmaxf(mxc, s[64 + i]); mxd = fmaxf(mxd, s[65 + i]);
         }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        // per-half maxima to scaled log2 units; a_h > 0 so the max commutes with the scaling (-inf if all masked)
+        float mx;
+        if constexpr (I8) mx = fmaxf(fmaxf(mxa, mxb) * a0, fmaxf(mxc, mxd) * a1);
+        else mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd)) * a0;
         float m_new = fmaxf(m, mx);
-        const bool grow = (m_new - m) * c > kRescaleThreshold;      // false when both are -inf (NaN compare)
+        const bool grow = (m_new - m) > kRescaleThreshold;          // false when both are -inf (NaN compare)
         if (!grow) m_new = m;
         if (__any_sync(0xffffffffu, grow)) {
-          const float alpha = grow ? ex2((m - m_new) * c) : 1.f;    // m = -inf -> 0
+          const float alpha = grow ? ex2(m - m_new) : 1.f;          // m = -inf -> 0
           l *= alpha;
           if (it > 0) {
 #pragma unroll
-            for (int ch = 0; ch < D / 32; ++ch) {
-              uint32_t ou[32];
-              tmem_ld_x32(tO + ch * 32, ou);
+            for (int ch = 0; ch < D / 16; ++ch) {           // 16 columns at a time: the 128 scores stay live in registers
+              uint32_t ou[16];
+              tmem_ld_x16(tO + ch * 16, ou);
               tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) ou[i] = __float_as_uint(__uint_as_float(ou[i]) * alpha);
-              tmem_st_x32(tO + ch * 32, ou);
+              for (int i = 0; i < 16; ++i) ou[i] = __float_as_uint(__uint_as_float(ou[i]) * alpha);
+              tmem_st_x16(tO + ch * 16, ou);
             }
           }
         }
         m = m_new;
-        const float neg_mc = (m == -CUDART_INF_F) ? 0.f : -m * c;
-        uint32_t pk[64];
-        float sum0, sum1;
-        if (POLY > 0 && !any_mask) exp_phase<BF16, POLY>(s, c, neg_mc, pk, sum0, sum1);
-        else exp_phase<BF16, 0>(s, c, neg_mc, pk, sum0, sum1);
-        l += sum0 + sum1;
-        tmem_st_x32(tS, pk);
-        tmem_st_x32(tS + 32, pk + 32);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full(t));
+        const float mm = (m == -CUDART_INF_F) ? 0.f : m;
+        // int8 mode: the V scale of each 64-key half rides in the exponent (P' = P v_h feeds the P V MMA; l takes
+        // sum(P') / v_h), so the inner loop is the same as the 16-bit one.
+        const float nk0 = lv0 - mm, nk1 = lv1 - mm;
+        float sum_lo, sum_hi;
+        // exp2 turn-taking: the two tiles' exp2 phases are MUFU-bound and share the four SMSPs, so run them one after
+        // the other (tile 0 first) -- this locks the tiles in anti-phase: one is in exp2 while the tensor pipe works
+        // for the other.  Left alone they drift in phase (the in-order tensor pipe queues S_1 right behind S_0) and
+        // each exp2 phase takes twice as long (profiles/: timeline).
+        if (pingpong) {
+          if (t == 0) { if (it > 0) named_bar_sync(2, 256); }
+          else named_bar_sync(3, 256);
+        }
+        if (TR && tr) tr[2] = clock64();
+        if (POLY > 0 && !any_mask) exp_phase<PBF16, POLY, TR>(s, a0, a1, nk0, nk1, tS, p_part(t, 0), lane, sum_lo, sum_hi, tr);
+        else exp_phase<PBF16, 0, TR>(s, a0, a1, nk0, nk1, tS, p_part(t, 0), lane, sum_lo, sum_hi, tr);
+        if (pingpong) {
+          if (t == 0) named_bar_arrive(3, 256);
+          else if (it + 1 < n) named_bar_arrive(2, 256);
+        }
+        l += sum_lo * iv0 + sum_hi * iv1;
       }
       // ---------------------------------------------------------------- epilogue: O / l, L = m + log2(l)
       if (n > 0) {
         mbar_wait(o_full(t), 0);
         tc_fence_after();
       }
-      const float inv = l > 0.f ? 1.f / l : 0.f;
+      const float inv = (l > 0.f ? 1.f / l : 0.f) * ((I8 && !v_blocks) ? p.vs1 : 1.f);
       const bool live = r < p.Sq;
       const size_t orow = (size_t)b * p.o_sb + (size_t)h * p.o_sh + (size_t)r * p.o_ss;
 #pragma unroll
@@ -335,11 +441,11 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           }
         }
       }
-      if (live && p.lse) p.lse[((size_t)b * p.H + h) * p.Sq + r] = l > 0.f ? fmaf(m, c, log2f(l)) : -CUDART_INF_F;
+      if (live && p.lse) p.lse[((size_t)b * p.H + h) * p.Sq + r] = l > 0.f ? m + log2f(l) : -CUDART_INF_F;
     }
   }
   else {
-    reg_dealloc<40>();      // idle warps of the third warpgroup (setmaxnreg is warpgroup-wide)
+    reg_dealloc<40>();      // idle warp of the third warpgroup (setmaxnreg is warpgroup-wide)
   }
   tc_fence_before();
   __syncthreads();
@@ -352,37 +458,90 @@ using tc::make_map;
 
 bool view_ok(const TensorView& t, int64_t, int64_t Hn, int64_t B) { return tc::view_ok(t, Hn, B); }
 
-int poly_setting() {
+}  // namespace
+
+int fwd_tc_pingpong() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MFA_FWD_POLY"); v = e ? atoi(e) : 2; }
+  if (v < 0) { const char* e = getenv("MFA_FWD_PINGPONG"); v = e ? atoi(e) : 1; }
   return v;
 }
 
-template <int D, bool BF16, int POLY>
+namespace {
+
+int poly_setting() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MFA_FWD_POLY"); v = e ? atoi(e) : 3; }
+  return v;
+}
+
+template <int D, int MODE, int POLY>
 cudaError_t launch_k(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = fwd_tc_kernel<D, BF16, POLY>;
+  auto kern = fwd_tc_kernel<D, MODE, POLY>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D, MODE>::kSmem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<grid, kThreads, Cfg<D>::kSmem, st>>>(prm);
+  kern<<<grid, kThreads, Cfg<D, MODE>::kSmem, st>>>(prm);
   return cudaGetLastError();
 }
 
-template <int D, bool BF16>
+// MFA_FWD_TRACE=<file>: run the instrumented build of the D=128 kernel and dump the clock64 timeline of CTA (0,0,0)
+// (rows: tile, step; 16 stamps: 0 S ready, 1 S in registers, 2 max done, 3-6 P part published, 8-11 part seen by the
+// MMA warp, 12 next S issued, 13 V tile landed, 14 K tile landed).  Debug aid; synchronises the stream.
+template <int MODE, int POLY>
+cudaError_t launch_traced(FwdTcParams prm, dim3 grid, cudaStream_t st, const char* path) {
+  constexpr size_t kWords = 2 * 64 * 16;
+  unsigned long long* dev = nullptr;
+  if (cudaMalloc(&dev, kWords * 8) != cudaSuccess) return cudaErrorMemoryAllocation;
+  cudaMemsetAsync(dev, 0, kWords * 8, st);
+  prm.trace = dev;
+  auto kern = fwd_tc_kernel<128, MODE, POLY, true>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128, MODE>::kSmem);
+  kern<<<grid, kThreads, Cfg<128, MODE>::kSmem, st>>>(prm);
+  cudaError_t e = cudaStreamSynchronize(st);
+  static unsigned long long host[kWords];
+  cudaMemcpy(host, dev, kWords * 8, cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (FILE* f = fopen(path, "w")) {
+    for (int t = 0; t < 2; ++t)
+      for (int it = 0; it < 64; ++it) {
+        const unsigned long long* r = host + ((size_t)t * 64 + it) * 16;
+        if (!r[0] && !r[8]) continue;
+        fprintf(f, "%d %d", t, it);
+        for (int k = 0; k < 16; ++k) fprintf(f, " %llu", r[k]);
+        fprintf(f, "\n");
+      }
+    fclose(f);
+  }
+  return e;
+}
+
+template <int D, int MODE>
 cudaError_t launch(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
+  if constexpr (D == 128 && MODE != kFwdF16) {
+    if (const char* path = getenv("MFA_FWD_TRACE"))
+      return poly_setting() == 2 ? launch_traced<MODE, 2>(prm, grid, st, path) : launch_traced<MODE, 0>(prm, grid, st, path);
+  }
   switch (poly_setting()) {
-    case 1: return launch_k<D, BF16, 1>(prm, grid, st);
-    case 2: return launch_k<D, BF16, 2>(prm, grid, st);
-    case 3: return launch_k<D, BF16, 3>(prm, grid, st);
-    case 4: return launch_k<D, BF16, 4>(prm, grid, st);
-    default: return launch_k<D, BF16, 0>(prm, grid, st);
+    case 1: return launch_k<D, MODE, 1>(prm, grid, st);
+    case 2: return launch_k<D, MODE, 2>(prm, grid, st);
+    case 3: return launch_k<D, MODE, 3>(prm, grid, st);
+    case 4: return launch_k<D, MODE, 4>(prm, grid, st);
+    default: return launch_k<D, MODE, 0>(prm, grid, st);
   }
 }
 
 }  // namespace
+
+cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm, int D, int mode, cudaStream_t st, int B) {
+  dim3 grid((prm.Sq + 255) / 256, prm.H, B);
+  if (mode == kFwdI8) return D == 128 ? launch<128, kFwdI8>(prm, grid, st) : cudaErrorInvalidValue;
+  if (D == 128) return mode == kFwdBF16 ? launch<128, kFwdBF16>(prm, grid, st) : launch<128, kFwdF16>(prm, grid, st);
+  if (D == 64) return mode == kFwdBF16 ? launch<64, kFwdBF16>(prm, grid, st) : launch<64, kFwdF16>(prm, grid, st);
+  return cudaErrorInvalidValue;
+}
 
 bool fwd_tc_eligible(const AttnParams& p) {
   if (getenv("MFA_DISABLE_TC")) return false;
@@ -400,7 +559,7 @@ bool fwd_tc_eligible(const AttnParams& p) {
 }
 
 cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st) {
-  FwdTcParams prm;
+  FwdTcParams prm = {};
   if (!make_map(&prm.tq, p.q, p.in_dtype, p.B, p.H, p.Sq, p.D) || !make_map(&prm.tk, p.k, p.in_dtype, p.B, p.Hkv, p.Skv, p.D) ||
       !make_map(&prm.tv, p.v, p.in_dtype, p.B, p.Hkv, p.Skv, p.D))
     return cudaErrorInvalidValue;
@@ -411,16 +570,11 @@ cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st) {
   prm.H = p.H; prm.Hkv = p.Hkv; prm.Sq = p.Sq; prm.Skv = p.Skv;
   prm.c = p.scale * kLog2e;
   prm.causal = p.causal; prm.window = p.window;
-  dim3 grid((p.Sq + 255) / 256, p.H, p.B);
-  cudaError_t e;
+  prm.pingpong = fwd_tc_pingpong();
   const bool bf = p.in_dtype == kBF16;
-  if (p.D == 128) {
-    e = bf ? launch<128, true>(prm, grid, st) : launch<128, false>(prm, grid, st);
-    g_last_kernel = bf ? "fwd_tc_bf16_d128" : "fwd_tc_fp16_d128";
-  } else {
-    e = bf ? launch<64, true>(prm, grid, st) : launch<64, false>(prm, grid, st);
-    g_last_kernel = bf ? "fwd_tc_bf16_d64" : "fwd_tc_fp16_d64";
-  }
+  cudaError_t e = launch_fwd_tc_kernel(prm, p.D, bf ? kFwdBF16 : kFwdF16, st, p.B);
+  if (p.D == 128) g_last_kernel = bf ? "fwd_tc_bf16_d128" : "fwd_tc_fp16_d128";
+  else g_last_kernel = bf ? "fwd_tc_bf16_d64" : "fwd_tc_fp16_d64";
   ++g_launch_count;
   return e;
 }

@@ -5,6 +5,7 @@
 // results visible in caller memory on return, a process-wide retained context singleton, strdup'd error strings.
 // There is no CPU fallback anywhere: without an sm_100 device every compute entry point returns
 // MFA_ERROR_DEVICE_NOT_SUPPORTED.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -49,6 +50,9 @@ struct Context {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // host-buffer pipeline (forward_pipelined): copy-in / copy-out streams and per-chunk events, created on first use
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_k0, ev_k1;
   double last_latency = 0.0;
   int refs = 0;
   std::mutex mu;
@@ -229,6 +233,97 @@ struct FwdArgs {
 
 bool valid_float_dtype(int d) { return d == kF16 || d == kBF16 || d == kF32; }
 
+// Host-buffer forward as a three-stage pipeline over (batch, head-group) chunks: H2D of chunk c+1, the attention
+// kernel on chunk c and D2H of chunk c-1 overlap on separate streams (PCIe is full duplex), so the blocking call costs
+// about max(H2D, D2H) instead of H2D + kernel + D2H.  (batch, head) units are independent (MultiHeadAttention.swift:
+// 373-377), so each chunk is a complete attention problem on a contiguous slab of the caller's BHSD arrays.
+// Used when Q, K, V and O are contiguous host mirrors and the tensor-core kernel applies; everything else takes the
+// single-shot path below.
+bool ensure_pipeline(Context* ctx, size_t chunks) {
+  if (!ctx->h2d && cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking) != cudaSuccess) return false;
+  if (!ctx->d2h && cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking) != cudaSuccess) return false;
+  while (ctx->ev_in.size() < chunks) {
+    cudaEvent_t a, b, c;
+    if (cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess ||
+        cudaEventCreate(&c) != cudaSuccess)
+      return false;
+    ctx->ev_in.push_back(a); ctx->ev_k0.push_back(b); ctx->ev_k1.push_back(c);
+  }
+  return true;
+}
+
+size_t pipeline_chunk_bytes() {
+  static size_t v = 0;
+  if (!v) { const char* e = getenv("MFA_PIPELINE_CHUNK_MB"); v = (size_t)((e ? atof(e) : 16.0) * 1048576.0); if (!v) v = 1; }
+  return v;
+}
+
+bool forward_pipeline_ok(const FwdArgs& a, int o_dtype) {
+  if (a.async || getenv("MFA_DISABLE_PIPELINE")) return false;
+  if (!a.q->mirrored || !a.k->mirrored || !a.v->mirrored || !a.out->mirrored || (a.lse && !a.lse->mirrored)) return false;
+  if (a.q->ndim || a.k->ndim || a.v->ndim || a.out->ndim) return false;
+  if (a.tq || a.tk || a.tv || a.to) return false;
+  if (a.mask.type != MFA_MASK_TYPE_NONE && a.mask.ptr && a.mask.bytes) return false;
+  if (a.in_dtype != kBF16 && a.in_dtype != kF16) return false;
+  if (a.D != 64 && a.D != 128) return false;
+  (void)o_dtype;
+  const size_t per_head = ((size_t)a.Sq + 2 * (size_t)a.Skv) * a.D * 2;
+  return (size_t)a.B * a.H * per_head >= 2 * pipeline_chunk_bytes();     // small problems: one shot is as fast
+}
+
+mfa_error_t forward_pipelined(Context* ctx, const FwdArgs& a, int o_dtype) {
+  const size_t esz = 2, oes = dtype_bytes(o_dtype);
+  const size_t q_head = (size_t)a.Sq * a.D, kv_head = (size_t)a.Skv * a.D;
+  const size_t per_head = (q_head + 2 * kv_head) * esz;
+  uint32_t hc = (uint32_t)std::max<size_t>(1, (pipeline_chunk_bytes() + per_head / 2) / per_head);
+  if (hc > a.H) hc = a.H;
+  const uint32_t groups = (a.H + hc - 1) / hc;
+  const size_t chunks = (size_t)a.B * groups;
+  if (!ensure_pipeline(ctx, chunks)) return MFA_ERROR_MEMORY_ALLOCATION;
+  cudaStream_t st = ctx->stream;
+  cudaError_t e = cudaSuccess;
+  size_t c = 0;
+  auto at = [](void* base, size_t off) { return reinterpret_cast<uint8_t*>(base) + off; };
+  for (uint32_t b = 0; b < a.B && e == cudaSuccess; ++b) {
+    for (uint32_t g = 0; g < groups && e == cudaSuccess; ++g, ++c) {
+      const uint32_t h0 = g * hc, hn = std::min(hc, a.H - h0);
+      const size_t qo = ((size_t)b * a.H + h0) * q_head, ko = ((size_t)b * a.H + h0) * kv_head;
+      if ((e = cudaMemcpyAsync(at(a.q->dev, qo * esz), at(a.q->host, qo * esz), hn * q_head * esz, cudaMemcpyHostToDevice, ctx->h2d)) != cudaSuccess) break;
+      if ((e = cudaMemcpyAsync(at(a.k->dev, ko * esz), at(a.k->host, ko * esz), hn * kv_head * esz, cudaMemcpyHostToDevice, ctx->h2d)) != cudaSuccess) break;
+      if ((e = cudaMemcpyAsync(at(a.v->dev, ko * esz), at(a.v->host, ko * esz), hn * kv_head * esz, cudaMemcpyHostToDevice, ctx->h2d)) != cudaSuccess) break;
+      cudaEventRecord(ctx->ev_in[c], ctx->h2d);
+      cudaStreamWaitEvent(st, ctx->ev_in[c], 0);
+      AttnParams p;
+      init_params(p, 1, hn, a.Sq, a.Skv, a.D, a.scale, a.causal, a.window);
+      p.q = contiguous_view(at(a.q->dev, qo * esz), hn, a.Sq, a.D, false);
+      p.k = contiguous_view(at(a.k->dev, ko * esz), hn, a.Skv, a.D, false);
+      p.v = contiguous_view(at(a.v->dev, ko * esz), hn, a.Skv, a.D, false);
+      p.o = contiguous_view(at(a.out->dev, qo * oes), hn, a.Sq, a.D, false);
+      const size_t lo = ((size_t)b * a.H + h0) * a.Sq;
+      p.lse = a.lse ? reinterpret_cast<float*>(a.lse->dev) + lo : nullptr;
+      p.in_dtype = a.in_dtype; p.o_dtype = o_dtype;
+      if (!fwd_tc_eligible(p)) { e = cudaErrorNotSupported; break; }
+      cudaEventRecord(ctx->ev_k0[c], st);
+      if ((e = launch_fwd_tc(p, st)) != cudaSuccess) break;
+      cudaEventRecord(ctx->ev_k1[c], st);
+      cudaStreamWaitEvent(ctx->d2h, ctx->ev_k1[c], 0);
+      if ((e = cudaMemcpyAsync(at(a.out->host, qo * oes), at(a.out->dev, qo * oes), hn * q_head * oes, cudaMemcpyDeviceToHost, ctx->d2h)) != cudaSuccess) break;
+      if (a.lse) e = cudaMemcpyAsync(at(a.lse->host, lo * 4), at(a.lse->dev, lo * 4), (size_t)hn * a.Sq * 4, cudaMemcpyDeviceToHost, ctx->d2h);
+    }
+  }
+  cudaError_t e1 = cudaStreamSynchronize(ctx->d2h), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(ctx->h2d);
+  ctx->last_kernel = g_last_kernel;
+  if (e != cudaSuccess) return cuda_fail(e, "pipelined forward");
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return cuda_fail(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3, "pipelined forward sync");
+  double total = 0.0;                      // mfa_get_gpu_latency: kernel time only, summed over the chunks
+  for (size_t i = 0; i < chunks; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_k0[i], ctx->ev_k1[i]) == cudaSuccess) total += ms * 1e-3; else cudaGetLastError();
+  }
+  ctx->last_latency = total;
+  return MFA_SUCCESS;
+}
+
 mfa_error_t forward_core(Context* ctx, const FwdArgs& a) {
   if (!ctx || !a.q || !a.k || !a.v || !a.out) return MFA_ERROR_INVALID_ARGS;
   if (!valid_float_dtype(a.in_dtype)) return MFA_ERROR_INVALID_ARGS;
@@ -250,6 +345,7 @@ mfa_error_t forward_core(Context* ctx, const FwdArgs& a) {
 
   std::lock_guard<std::mutex> lock(ctx->mu);
   cudaSetDevice(ctx->device);
+  if (nq != 0 && nkv != 0 && forward_pipeline_ok(a, o_dtype)) return forward_pipelined(ctx, a, o_dtype);
   cudaStream_t st = a.async ? a.user_stream : ctx->stream;
   Sync sync{ctx, st, a.async, {}};
   cudaError_t e;
@@ -613,6 +709,9 @@ void mfa_destroy_context(mfa_context_t context) {
   cudaStreamSynchronize(c->stream);
   for (auto& s : c->scratch) s.release();
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  for (auto* v : {&c->ev_in, &c->ev_k0, &c->ev_k1}) { for (cudaEvent_t ev : *v) cudaEventDestroy(ev); v->clear(); }
+  if (c->h2d) cudaStreamDestroy(c->h2d);
+  if (c->d2h) cudaStreamDestroy(c->d2h);
   cudaStreamDestroy(c->stream);
   cudaGetLastError();
   delete c;

@@ -1,0 +1,37 @@
+// fwd_tc.h -- parameter block and launcher of the fused tcgen05 attention forward (attn_fwd_tc.cu), shared with the
+// quantised front end (attn_fwd_tcq.cu), which runs the same kernel with the int8 Q K^T operand mode.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace mfa {
+
+enum FwdMode : int { kFwdF16 = 0, kFwdBF16 = 1, kFwdI8 = 2 };
+
+struct FwdTcParams {
+  CUtensorMap tq, tk, tv;
+  void* o;
+  long long o_sb, o_sh, o_ss;
+  float* lse;
+  int o_dtype;
+  int H, Hkv, Sq, Skv;
+  float c;                 // softmax_scale * log2(e)
+  int causal, window;
+  // kFwdI8 only: symmetric scales of the int8 codes (value = code * scale)
+  const float* qs; const float* ks; const float* vs;   // per-block scale arrays (device) or nullptr
+  float qs1, ks1, vs1;                                  // per-tensor scales when the array is null
+  int qbr, kbr, vbr;                                    // tokens per block (multiple of 64 for K / V)
+  int nbq, nbk, nbv;                                    // blocks per (b, h)
+  int sq_, sk_, sv_;                                    // scale-array stride per (b, h): nb, or 0 for a single device scale
+  int pingpong;                                         // exp2 turn-taking between the two tiles (MFA_FWD_PINGPONG, default 1)
+  unsigned long long* trace;                            // debug timeline buffer (MFA_FWD_TRACE), normally null
+};
+
+int fwd_tc_pingpong();
+
+// grid = (ceil(Sq / 256), H, B).  mode kFwdI8 needs D == 128 (Q / K tiles are int8, V tiles bf16).
+cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm, int D, int mode, cudaStream_t st, int B);
+
+}  // namespace mfa
