@@ -7,6 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "universal-metal-flash-attention_b200")); sys.path.insert(0, ROOT)
 mode = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 poly = sys.argv[2] if len(sys.argv) > 2 else "0"
+qmode = int(sys.argv[3]) if len(sys.argv) > 3 else 2          # 0 per-tensor scales, 2 per-block (64 tokens)
 os.environ["MFA_FWD_POLY"] = poly
 import torch
 import umfa
@@ -25,10 +26,10 @@ scale = 1.0 / np.sqrt(D)
 def call():
     if mode == "bf16":
         return lib.mfa_attention_forward_with_lse(ctx.handle, *h, B, S, S, H, D, scale, False, 1, 2, False, False, False, False)
-    return lib.mfa_quantized_forward_with_lse(ctx.handle, *h, None, B, S, S, H, D, scale, False, 3, 2, 1)
+    return lib.mfa_quantized_forward_with_lse(ctx.handle, *h, None, B, S, S, H, D, scale, False, 3, qmode, 1)
 for _ in range(3):
     assert call() == 0
-path = f"/tmp/fwd_trace_{mode}_{poly}.txt"
+path = os.path.join(ROOT, "gpurun_out", f"fwd_trace_{mode}_{poly}_q{qmode}.txt"); os.makedirs(os.path.dirname(path), exist_ok=True)
 os.environ["MFA_FWD_TRACE"] = path
 assert call() == 0
 del os.environ["MFA_FWD_TRACE"]

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(192, 1) probe(long long* out, int iters, int l
       constexpr uint32_t I_TS = make_idesc(1, 1, 1, 0, 1, 128, NN);
       constexpr uint32_t I_I8 = make_idesc(2, 1, 1, 0, 0, 128, NN);
       constexpr uint32_t I_F8 = make_idesc(1, 0, 0, 0, 1, 128, NN);
+      constexpr uint32_t I_F8K = make_idesc(1, 0, 0, 0, 0, 128, NN);
       long long t0 = clock64();
       for (int i = 0; i < iters; ++i) {
 #pragma unroll
@@ -79,6 +80,22 @@ __global__ void __launch_bounds__(192, 1) probe(long long* out, int iters, int l
             if (kk & 1) mma_f16_ts(tmem + 256, tmem + 128 + kk * 8, smem_desc_sw128(sB + kk * 2048, 16384, 1024), I_TS, 1);
             else mma_f16_ss(tmem + 0, smem_desc_sw128(sA + off, 16, 1024), smem_desc_sw128(sB + off, 16, 1024), I_SS, 1);
           }
+          else if (MODE == 18) {     // int8 forward pattern: 4 x i8 SS (S = Q K^T) then 8 x f16 TS (O += P V): kind switches
+            if (i & 1) mma_f16_ts(tmem + 256, tmem + 128 + kk * 8, smem_desc_sw128(sB + kk * 2048, 16384, 1024), I_TS, 1);
+            else if (kk < 4) mma_i8_ss(tmem + 0, smem_desc_sw128(sA + kk * 32, 16, 1024), smem_desc_sw128(sB + kk * 32, 16, 1024), I_I8, kk > 0);
+          } else if (MODE == 19) {   // 4 x i8 SS then 4 x f8 TS (K = 32 each)
+            if (i & 1) { if (kk < 4) mma_f8_ts(tmem + 256, tmem + 128 + kk * 8, smem_desc_sw128(sB + kk * 4096, 16384, 1024), I_F8, 1); }
+            else if (kk < 4) mma_i8_ss(tmem + 0, smem_desc_sw128(sA + kk * 32, 16, 1024), smem_desc_sw128(sB + kk * 32, 16, 1024), I_I8, kk > 0);
+          } else if (MODE == 20) {   // i8 SS / f16 TS alternate every MMA
+            if (kk & 1) mma_f16_ts(tmem + 256, tmem + 128 + kk * 8, smem_desc_sw128(sB + kk * 2048, 16384, 1024), I_TS, 1);
+            else mma_i8_ss(tmem + 0, smem_desc_sw128(sA + (kk >> 1) * 32, 16, 1024), smem_desc_sw128(sB + (kk >> 1) * 32, 16, 1024), I_I8, 1);
+          } else if (MODE == 21) {   // 4 x f8 SS (e4m3 Q K^T) then 4 x f8 TS: one kind throughout
+            if (i & 1) { if (kk < 4) mma_f8_ts(tmem + 256, tmem + 128 + kk * 8, smem_desc_sw128(sB + kk * 4096, 16384, 1024), I_F8, 1); }
+            else if (kk < 4) mma_f8_ss(tmem + 0, smem_desc_sw128(sA + kk * 32, 16, 1024), smem_desc_sw128(sB + kk * 32, 16, 1024), I_F8K, kk > 0);
+          } else if (MODE == 22) {   // 4 x i8 SS then 2 x f16 TS, 4 times (the 4-part P hand-off granularity)
+            if (i & 1) mma_f16_ts(tmem + 256, tmem + 128 + kk * 8, smem_desc_sw128(sB + kk * 2048, 16384, 1024), I_TS, 1);
+            else if (kk < 4) mma_i8_ss(tmem + 128 * (kk & 1), smem_desc_sw128(sA + kk * 32, 16, 1024), smem_desc_sw128(sB + kk * 32, 16, 1024), I_I8, 1);
+          }
           else if (MODE == 4)
             mma_i8_ss(tmem + 0, smem_desc_sw128(sA + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                       smem_desc_sw128(sB + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024), I_I8, 1);
@@ -117,6 +134,11 @@ void run(const char* name, long long* d, int ld_warps) {
   cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
   const double per = (double)h / (iters * 8.0);
   const int kdepth = (MODE == 4 || MODE == 5) ? 32 : 16;
+  if (MODE >= 18) {
+    const int ideal = MODE == 18 ? 768 : MODE == 20 ? 1024 : MODE == 22 ? 768 : 512;
+    printf("%-60s %7.1f clk per (S, PV) pair   ideal %d  %s\n", name, (double)h / (iters / 2.0), ideal, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    return;
+  }
   printf("%-44s N=%3d ld_warps=%d  %7.1f clk/MMA  (%5.1f%% of 8192 dense-bf16 FLOP/clk/SM)  %s\n", name, NN, ld_warps, per,
          100.0 * (2.0 * 128 * NN * kdepth / per) / 8192.0, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
@@ -146,5 +168,10 @@ int main() {
   run<17, 128>("SS / TS alternate every MMA", d, 0);
   run<4, 128>("i8 SS K-major (K=32 per MMA)", d, 0);
   run<5, 128>("f8 TS B MN-major (K=32 per MMA)", d, 0);
+  run<18, 128>("int8 fwd pattern: 4 i8 SS + 8 f16 TS", d, 0);
+  run<19, 128>("4 i8 SS + 4 f8 TS", d, 0);
+  run<20, 128>("i8 SS / f16 TS alternate every MMA (4+4 per iter)", d, 0);
+  run<21, 128>("4 f8 SS + 4 f8 TS (single kind)", d, 0);
+  run<22, 128>("4 i8 SS (2 accumulators) + 8 f16 TS", d, 0);
   return 0;
 }

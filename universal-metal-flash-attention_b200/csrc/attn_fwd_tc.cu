@@ -24,9 +24,8 @@
 // are partly hidden get an element mask, tiles that are fully visible skip the mask code.
 // Outputs follow the reference contract: O fp32 (or fp16/bf16 on request) and L = m + log2(l) in log2 units.
 //
-// int8 mode: S_int = Q_i8 K_i8^T on kind::i8 (2x the bf16 MMA rate); the softmax warps widen it with I2FP (exact, ALU
-// pipe -- not the I2F that shares the 16/clk MUFU pipe with ex2) and fold every scale into the one packed FFMA that
-// forms the exponent:   x = s_int * a_h + (log2 v_h - m),   a_h = qs[row block] * ks[h] * scale * log2(e),
+// int8 mode: S_int = Q_i8 K_i8^T on kind::i8 (2x the bf16 MMA rate); the softmax warps widen it with I2FP (exact)
+// and fold every scale into the one packed FFMA that forms the exponent:   x = s_int * a_h + (log2 v_h - m),   a_h = qs[row block] * ks[h] * scale * log2(e),
 // h = 64-key half of the tile.  P' = P v_h (the V block scale rides in the exponent) feeds the P V MMA, which runs on
 // kind::f16 with V's int8 codes widened to bf16 (exact); the row sum takes sum(P') / v_h per half.
 #include <cuda.h>
@@ -310,20 +309,34 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     const bool pingpong = nt == 2 && p.pingpong;
 
     if (t < nt) {
+      // int8 mode: raw K / V block scales of the two 64-key halves of a tile.  They are fetched one KV step ahead (right
+      // after S of the current step has been read), so the L2 / HBM latency of these loads never sits between the
+      // s_full wait and the exp2 phase (it cost ~900 clk per step when the loads were issued at the top of the step).
+      float ksn0 = p.ks1, ksn1 = p.ks1, vsn0 = 1.f, vsn1 = 1.f;
+      auto fetch_scales = [&](int it) {
+        if constexpr (I8) {
+          const int c0 = (j_lo + it) * 128;
+          if (ksp) {
+            ksn0 = __ldg(ksp + min(c0 / p.kbr, p.nbk - 1));
+            ksn1 = __ldg(ksp + min((c0 + 64) / p.kbr, p.nbk - 1));
+          }
+          if (v_blocks) {
+            vsn0 = __ldg(vsp + min(c0 / p.vbr, p.nbv - 1));
+            vsn1 = __ldg(vsp + min((c0 + 64) / p.vbr, p.nbv - 1));
+          }
+        }
+      };
+      if (n > 0) fetch_scales(0);
       for (int it = 0; it < n; ++it) {
         const int c0 = (j_lo + it) * 128;
         // multipliers of the two 64-key halves of this tile (int8: blocks are multiples of 64 keys)
         float a0 = qsc, a1 = qsc, lv0 = 0.f, lv1 = 0.f, iv0 = 1.f, iv1 = 1.f;
         if constexpr (I8) {
-          a0 = a1 = qsc * p.ks1;
-          if (ksp) {
-            a0 = qsc * ksp[min(c0 / p.kbr, p.nbk - 1)];
-            a1 = qsc * ksp[min((c0 + 64) / p.kbr, p.nbk - 1)];
-          }
+          a0 = qsc * ksn0;
+          a1 = qsc * ksn1;
           if (v_blocks) {
-            const float v0 = vsp[min(c0 / p.vbr, p.nbv - 1)], v1 = vsp[min((c0 + 64) / p.vbr, p.nbv - 1)];
-            lv0 = log2f(v0); lv1 = log2f(v1);        // bf16 P' = P v_h has fp32's exponent range: no reference scale needed
-            iv0 = 1.f / v0; iv1 = 1.f / v1;
+            lv0 = log2f(vsn0); lv1 = log2f(vsn1);    // bf16 P' = P v_h has fp32's exponent range: no reference scale needed
+            iv0 = 1.f / vsn0; iv1 = 1.f / vsn1;
           }
         }
         unsigned long long* tr = nullptr;
@@ -340,10 +353,16 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         tmem_wait_ld();
         float* s = reinterpret_cast<float*>(su);
         if (TR && tr) tr[1] = clock64();
+        if (it + 1 < n) fetch_scales(it + 1);
         if constexpr (I8) {
+          // exact widening (|s| <= 2^21).  Measured alternatives (profiles/r01d_int8_notes.txt): I2FP here = 3553 clk per
+          // KV step pair, integer add onto the bits of 1.5 * 2^23 + packed subtract = 3750; the bf16 kernel = 2757.  The
+          // softmax warps issue at ~0.5 IPC per SMSP in either mode, so every extra instruction per score lengthens the
+          // step by ~2 x 128 x 2 clk -- more than the 2 x 256 clk the int8 Q K^T saves on the tensor pipe.
 #pragma unroll
-          for (int i = 0; i < 128; ++i) s[i] = __int2float_rn((int)su[i]);     // exact (|s| < 2^24); I2FP, not the MUFU-pipe I2F
+          for (int i = 0; i < 128; ++i) s[i] = __int2float_rn((int)su[i]);
         }
+        if (TR && tr) tr[15] = clock64();
         const bool need_mask = (c0 < clo) || (c0 + 127 > chi);
         const bool any_mask = __any_sync(0xffffffffu, need_mask);
         if (any_mask) {
@@ -388,6 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         // the other (tile 0 first) -- this locks the tiles in anti-phase: one is in exp2 while the tensor pipe works
         // for the other.  Left alone they drift in phase (the in-order tensor pipe queues S_1 right behind S_0) and
         // each exp2 phase takes twice as long (profiles/: timeline).
+        if (TR && tr) tr[7] = clock64();
         if (pingpong) {
           if (t == 0) { if (it > 0) named_bar_sync(2, 256); }
           else named_bar_sync(3, 256);

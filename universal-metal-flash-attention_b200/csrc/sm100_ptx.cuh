@@ -113,6 +113,13 @@ __device__ __forceinline__ void mma_f8_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum)
       : "memory");
 }
+__device__ __forceinline__ void mma_f8_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
 // ---- warp-uniform issue path.  The whole MMA warp runs the issue loop in uniform control flow and one elected lane
 // executes the instruction; descriptors arrive as (lo, hi) 32-bit halves so the per-MMA address update is a single
 // uniform add.  (Issuing from inside `if (lane == 0)` makes ptxas wrap every UTCHMMA in an ELECT/BRA.U.ANY waterfall
