@@ -140,6 +140,18 @@ mfa_error_t mfa_attention_forward_ex(
     uint32_t mask_ndim, mfa_mask_type_t mask_type, mfa_mask_scalar_t mask_scalar_type,
     void* stream);
 
+/* One ring-attention step (no reference counterpart): attention of seq_len_q query rows against a visiting
+ * K/V block, merged in place -- L = log2(2^L_old + 2^L_new), O = O_old 2^(L_old-L) + O_new 2^(L_new-L) -- into rows
+ * [acc_row_offset, acc_row_offset + seq_len_q) of every (b, h) of out_acc (fp32 [B,H,acc_rows,D]) and lse_acc
+ * (fp32 [B,H,acc_rows], log2 units; rows holding -inf are simply overwritten).  bf16 / fp16 operands with head_dim 64 or
+ * 128 only (MFA_ERROR_INVALID_ARGS otherwise); q / k / v may be strided handles; all buffers device-resident.
+ * stream as in mfa_attention_forward_ex. */
+mfa_error_t mfa_attention_forward_accumulate(
+    mfa_context_t context, mfa_buffer_t q, mfa_buffer_t k, mfa_buffer_t v, mfa_buffer_t out_acc, mfa_buffer_t lse_acc,
+    uint32_t batch_size, uint32_t seq_len_q, uint32_t seq_len_kv, uint32_t num_heads, uint16_t head_dim,
+    float softmax_scale, bool causal, int32_t window_size, mfa_precision_t input_precision,
+    uint32_t acc_row_offset, uint32_t acc_rows, void* stream);
+
 /* Backward twin of the above (mask and window honoured; the reference's backward takes neither). */
 mfa_error_t mfa_attention_backward_ex(
     mfa_context_t context,

@@ -133,3 +133,102 @@ def test_tc_host_pipeline_matches_single_shot(ctx, shape, D, causal, monkeypatch
     ref, lref = O.attention_forward(qv, kv, vv, causal=causal)
     assert rel_max(out_p, ref) < 2e-2
     assert np.abs(lse_p - lref).max() < 2e-2
+
+
+# ---- external masks on the tensor-core path (PyTorch placement softmax(scale * QK^T + mask)) ------------------
+MASK_KINDS = ["bool2d", "bool4d_bcast_heads", "bool_key_padding", "add_fp32", "add_fp16", "add_bf16", "add_fp32_rows_bcast",
+              "bool_rows_empty", "add_neg_inf"]
+
+
+def _make_mask(kind, rng, B, H, Sq, Skv):
+    """-> (array handed to the adapter, oracle mask, extra kwargs)"""
+    kw = {}
+    if kind == "bool2d":
+        m = rng.random((Sq, Skv)) > 0.4
+        m[:, 0] = True
+        return m, m, kw
+    if kind == "bool4d_bcast_heads":
+        m = rng.random((B, 1, Sq, Skv)) > 0.5
+        m[..., 3] = True
+        return m, m, kw
+    if kind == "bool_key_padding":
+        m = np.ones((B, 1, 1, Skv), dtype=bool)
+        for b in range(B):
+            m[b, 0, 0, Skv - 1 - 17 * (b + 1):] = False
+        return m, m, kw
+    if kind == "bool_rows_empty":
+        m = rng.random((B, H, Sq, Skv)) > 0.5
+        m[0, H - 1, 5, :] = False
+        m[B - 1, 0, Sq - 1, :] = False
+        return m, m, kw
+    if kind == "add_neg_inf":
+        base = rng.standard_normal((B, H, Sq, Skv)).astype(np.float32)
+        base[rng.random((B, H, Sq, Skv)) > 0.7] = -np.inf
+        base[..., 0] = 0.5
+        return base, base, kw
+    if kind == "add_fp32_rows_bcast":
+        base = (2.0 * rng.standard_normal((B, H, 1, Skv))).astype(np.float32)
+        return base, base, kw
+    base = (2.0 * rng.standard_normal((B, H, Sq, Skv))).astype(np.float32)
+    if kind == "add_fp16":
+        m = base.astype(np.float16)
+        return m, m.astype(np.float32), kw
+    if kind == "add_bf16":
+        om, bits = O.round_bf16(base)
+        kw["mask_precision"] = "bf16"
+        return bits, om, kw
+    return base, base, kw
+
+
+@pytest.mark.parametrize("kind", MASK_KINDS)
+@pytest.mark.parametrize("shape", [(2, 3, 256, 384, 128, "bf16"), (2, 2, 300, 333, 64, "fp16"), (1, 2, 70, 90, 128, "bf16")])
+def test_tc_external_masks(ctx, kind, shape):
+    """aligned tiles take the 16-byte mask loads, ragged ones the element path; both against the oracle"""
+    import umfa
+    B, H, Sq, Skv, D, dtype = shape
+    rng = np.random.default_rng(11)
+    q, k, v = (rng.standard_normal(s).astype(np.float32) for s in ((B, H, Sq, D), (B, H, Skv, D), (B, H, Skv, D)))
+    (qa, qv), (ka, kv), (va, vv) = (to_dtype(x, dtype) for x in (q, k, v))
+    m, om, kw = _make_mask(kind, rng, B, H, Sq, Skv)
+    out, lse = umfa.flash_attention_forward(ctx, qa, ka, va, input_precision=dtype, output_precision="fp32", layout="bhsd",
+                                            attn_mask=m, return_lse=True, **kw)
+    assert ctx.last_kernel.startswith("fwd_tc_") and ctx.last_kernel.endswith("_mask"), ctx.last_kernel
+    ref, lref = O.attention_forward(qv, kv, vv, mask=om)
+    assert np.isfinite(out).all()
+    assert rel_max(out, ref) < 2e-2
+    fin = np.isfinite(lref)
+    assert (np.isfinite(lse) == fin).all()
+    assert np.abs(lse[fin] - lref[fin]).max() < 2e-2
+    if kind == "bool_rows_empty":
+        assert (out[0, H - 1, 5] == 0).all() and lse[0, H - 1, 5] == -np.inf
+
+
+def test_tc_mask_with_causal(ctx):
+    import umfa
+    B, H, S, D = 1, 2, 512, 128
+    rng = np.random.default_rng(12)
+    q, k, v = (rng.standard_normal((B, H, S, D)).astype(np.float32) for _ in range(3))
+    (qa, qv), (ka, kv), (va, vv) = (to_dtype(x, "bf16") for x in (q, k, v))
+    m = rng.random((S, S)) > 0.3
+    m[:, 0] = True
+    out, lse = umfa.flash_attention_forward(ctx, qa, ka, va, input_precision="bf16", output_precision="fp32", layout="bhsd",
+                                            attn_mask=m, causal=True, return_lse=True)
+    assert ctx.last_kernel.endswith("_mask")
+    ref, lref = O.attention_forward(qv, kv, vv, mask=m, causal=True)
+    assert rel_max(out, ref) < 2e-2 and np.abs(lse - lref).max() < 2e-2
+
+
+def test_tc_mask_matches_exact_path(ctx, monkeypatch):
+    """the tensor-core masked kernel and the exact fp32-math kernel agree on identical bf16 inputs"""
+    import umfa
+    B, H, Sq, Skv, D = 1, 4, 384, 640, 128
+    rng = np.random.default_rng(13)
+    q, k, v = (rng.standard_normal(s).astype(np.float32) for s in ((B, H, Sq, D), (B, H, Skv, D), (B, H, Skv, D)))
+    (qa, _), (ka, _), (va, _) = (to_dtype(x, "bf16") for x in (q, k, v))
+    m = (3.0 * rng.standard_normal((1, H, Sq, Skv))).astype(np.float32)
+    out = umfa.flash_attention_forward(ctx, qa, ka, va, input_precision="bf16", output_precision="fp32", layout="bhsd", attn_mask=m)
+    assert ctx.last_kernel.endswith("_mask")
+    monkeypatch.setenv("MFA_DISABLE_TC_MASK", "1")
+    out2 = umfa.flash_attention_forward(ctx, qa, ka, va, input_precision="bf16", output_precision="fp32", layout="bhsd", attn_mask=m)
+    assert not ctx.last_kernel.startswith("fwd_tc_")
+    assert rel_max(out, out2) < 1e-2

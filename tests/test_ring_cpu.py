@@ -41,6 +41,24 @@ def test_schedule_is_exact_and_balanced(G):
     assert seen == want
 
 
+@pytest.mark.parametrize("G", [1, 2, 3, 4, 8])
+def test_fused_step_plan_covers_the_schedule(G):
+    """The one-launch-per-step plan (rectangular problem over the [low | high] layout) does exactly the chunk pairs of
+    step_schedule, with the diagonal pairs -- and only those -- handled by the causal rule on local indices."""
+    for r in range(G):
+        for s in range(G):
+            (q0, qn), (k0, kn), causal = ring.step_plan(r, G, s)
+            got = set()
+            for qi in range(q0, q0 + qn):
+                for ki in range(k0, k0 + kn):
+                    if causal:
+                        if ki <= qi:
+                            got.add((qi, ki, qi == ki))
+                    else:
+                        got.add((qi, ki, False))
+            assert got == set(ring.step_schedule(r, G, s)), (G, r, s)
+
+
 def test_merge_matches_joint_softmax():
     rng = np.random.default_rng(0)
     q = rng.standard_normal((1, 2, 40, 16)).astype(np.float32)

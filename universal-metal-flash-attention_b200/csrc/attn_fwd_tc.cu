@@ -30,6 +30,7 @@
 // kind::f16 with V's int8 codes widened to bf16 (exact); the row sum takes sum(P') / v_h per half.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 #include <cstdio>
@@ -144,7 +145,10 @@ __device__ __forceinline__ void exp_phase(const float* s, float a0, float a1, fl
 
 // POLY = n in 0..4: n of every 8 element pairs go through exp2_poly2 instead of MUFU.EX2 (only on tiles without masking,
 // so masked elements always get an exact zero weight).
-template <int D, int MODE, int POLY, bool TR = false>
+// MASKED: an external mask (bool or additive, SURVEY A4 with the PyTorch placement softmax(scale * QK^T + mask)) is read by
+// the softmax warps straight from global memory -- each thread owns one row, so it reads the 128 mask values of its row
+// and tile with 16-byte loads; no dense fp32 expansion pass like the reference's mfa_prepare_mask (MFABridge.swift:153-243).
+template <int D, int MODE, int POLY, bool TR = false, bool MASKED = false>
 __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_constant__ FwdTcParams p) {
   using C = Cfg<D, MODE>;
   constexpr bool I8 = C::kI8;
@@ -363,6 +367,70 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           for (int i = 0; i < 128; ++i) s[i] = __int2float_rn((int)su[i]);
         }
         if (TR && tr) tr[15] = clock64();
+        if constexpr (MASKED) {
+          const int rq = min(r, p.Sq - 1);
+          const long long eoff = (long long)b * p.mask_sb + (long long)h * p.mask_sh + (long long)rq * p.mask_sq + c0;
+          const int ncol = min(128, p.Skv - c0);
+          if (p.mask_kind == kMaskBool) {
+            const uint8_t* mp = reinterpret_cast<const uint8_t*>(p.mask) + eoff;
+            if (ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 15) == 0) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(mp) + c);
+                const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                  if (((w[k >> 2] >> (8 * (k & 3))) & 0xffu) == 0) s[16 * c + k] = -CUDART_INF_F;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 128; ++i)
+                if (i < ncol && __ldg(mp + i) == 0) s[i] = -CUDART_INF_F;
+            }
+          } else {
+            // additive: fold the scale now (s <- s a_h + mask log2 e), the multipliers become 1 for the rest of the step
+            if (p.mask_scalar == kMaskF32) {
+              const float* mp = reinterpret_cast<const float*>(p.mask) + eoff;
+              if (ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 15) == 0) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                  const float4 w = __ldg(reinterpret_cast<const float4*>(mp) + c);
+                  const float ah = c < 16 ? a0 : a1;
+                  s[4 * c] = fmaf(s[4 * c], ah, w.x * kLog2e); s[4 * c + 1] = fmaf(s[4 * c + 1], ah, w.y * kLog2e);
+                  s[4 * c + 2] = fmaf(s[4 * c + 2], ah, w.z * kLog2e); s[4 * c + 3] = fmaf(s[4 * c + 3], ah, w.w * kLog2e);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 128; ++i)
+                  s[i] = fmaf(s[i], i < 64 ? a0 : a1, (i < ncol ? __ldg(mp + i) : 0.f) * kLog2e);
+              }
+            } else {
+              const uint16_t* mp = reinterpret_cast<const uint16_t*>(p.mask) + eoff;
+              const bool bf = p.mask_scalar == kMaskBF16;
+              auto widen = [&](uint32_t bits) {
+                return bf ? __uint_as_float(bits << 16) : __half2float(__ushort_as_half((unsigned short)bits));
+              };
+              if (ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 15) == 0) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                  const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(mp) + c);
+                  const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+                  const float ah = c < 8 ? a0 : a1;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    s[8 * c + 2 * k] = fmaf(s[8 * c + 2 * k], ah, widen(w[k] & 0xffffu) * kLog2e);
+                    s[8 * c + 2 * k + 1] = fmaf(s[8 * c + 2 * k + 1], ah, widen(w[k] >> 16) * kLog2e);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 128; ++i)
+                  s[i] = fmaf(s[i], i < 64 ? a0 : a1, (i < ncol ? widen(__ldg(mp + i)) : 0.f) * kLog2e);
+              }
+            }
+            a0 = a1 = 1.f;
+          }
+        }
         const bool need_mask = (c0 < clo) || (c0 + 127 > chi);
         const bool any_mask = __any_sync(0xffffffffu, need_mask);
         if (any_mask) {
@@ -426,9 +494,26 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         mbar_wait(o_full(t), 0);
         tc_fence_after();
       }
-      const float inv = (l > 0.f ? 1.f / l : 0.f) * ((I8 && !v_blocks) ? p.vs1 : 1.f);
+      float inv = (l > 0.f ? 1.f / l : 0.f) * ((I8 && !v_blocks) ? p.vs1 : 1.f);
       const bool live = r < p.Sq;
       const size_t orow = (size_t)b * p.o_sb + (size_t)h * p.o_sh + (size_t)r * p.o_ss;
+      const size_t lrow = ((size_t)b * p.H + h) * p.lse_sh + r;
+      float l_out = l > 0.f ? m + log2f(l) : -CUDART_INF_F;
+      // accumulate mode (ring attention): the partial of this launch is merged in place with the (O, L) already there,
+      //   L = log2(2^L_old + 2^L_new),  O = O_old 2^(L_old - L) + O_new 2^(L_new - L)      (fp32 O only)
+      float c_old = 0.f;
+      const bool acc_mode = p.accumulate && p.o_dtype == kF32;
+      if (acc_mode && live) {
+        const float l_old = p.lse[lrow];
+        const float mx = fmaxf(l_old, l_out);
+        if (mx != -CUDART_INF_F) {
+          const float w_old = exp2f(l_old - mx), w_new = exp2f(l_out - mx);     // exp2(-inf) = 0
+          const float tot = w_old + w_new;
+          c_old = w_old / tot;
+          inv *= w_new / tot;
+          l_out = mx + log2f(tot);
+        }
+      }
 #pragma unroll
       for (int ch = 0; ch < D / 32; ++ch) {
         uint32_t ou[32];
@@ -442,10 +527,22 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         if (live) {
           if (p.o_dtype == kF32) {
             float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.o) + orow + ch * 32);
+            if (acc_mode) {
+              float4 old[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              dst[i] = make_float4(__uint_as_float(ou[4 * i]) * inv, __uint_as_float(ou[4 * i + 1]) * inv,
-                                   __uint_as_float(ou[4 * i + 2]) * inv, __uint_as_float(ou[4 * i + 3]) * inv);
+              for (int i = 0; i < 8; ++i) old[i] = dst[i];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                dst[i] = make_float4(fmaf(old[i].x, c_old, __uint_as_float(ou[4 * i]) * inv),
+                                     fmaf(old[i].y, c_old, __uint_as_float(ou[4 * i + 1]) * inv),
+                                     fmaf(old[i].z, c_old, __uint_as_float(ou[4 * i + 2]) * inv),
+                                     fmaf(old[i].w, c_old, __uint_as_float(ou[4 * i + 3]) * inv));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                dst[i] = make_float4(__uint_as_float(ou[4 * i]) * inv, __uint_as_float(ou[4 * i + 1]) * inv,
+                                     __uint_as_float(ou[4 * i + 2]) * inv, __uint_as_float(ou[4 * i + 3]) * inv);
+            }
           } else {
             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) + orow + ch * 32);
 #pragma unroll
@@ -461,7 +558,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           }
         }
       }
-      if (live && p.lse) p.lse[((size_t)b * p.H + h) * p.Sq + r] = l > 0.f ? m + log2f(l) : -CUDART_INF_F;
+      if (live && p.lse) p.lse[lrow] = l_out;
     }
   }
   else {
@@ -539,7 +636,21 @@ cudaError_t launch_traced(FwdTcParams prm, dim3 grid, cudaStream_t st, const cha
 }
 
 template <int D, int MODE>
+cudaError_t launch_masked(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = fwd_tc_kernel<D, MODE, 0, false, true>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D, MODE>::kSmem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<grid, kThreads, Cfg<D, MODE>::kSmem, st>>>(prm);
+  return cudaGetLastError();
+}
+
+template <int D, int MODE>
 cudaError_t launch(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
+  if (prm.mask) return launch_masked<D, MODE>(prm, grid, st);
   if constexpr (D == 128 && MODE != kFwdF16) {
     if (const char* path = getenv("MFA_FWD_TRACE"))
       return poly_setting() == 2 ? launch_traced<MODE, 2>(prm, grid, st, path) : launch_traced<MODE, 0>(prm, grid, st, path);
@@ -563,11 +674,24 @@ cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm, int D, int mode, cudaSt
   return cudaErrorInvalidValue;
 }
 
+// external masks the tensor-core forward reads itself: keys contiguous (the row of a tile is one 128-element run)
+bool fwd_tc_mask_ok(const AttnParams& p) {
+  if (p.mask_kind == kMaskNone || !p.mask) return true;
+  if (getenv("MFA_DISABLE_TC_MASK")) return false;
+  return p.mask_sk == 1;
+}
+
+void fwd_tc_set_mask(FwdTcParams& prm, const AttnParams& p) {
+  if (p.mask_kind == kMaskNone || !p.mask) return;
+  prm.mask = p.mask; prm.mask_kind = p.mask_kind; prm.mask_scalar = p.mask_scalar;
+  prm.mask_sb = p.mask_sb; prm.mask_sh = p.mask_sh; prm.mask_sq = p.mask_sq;
+}
+
 bool fwd_tc_eligible(const AttnParams& p) {
   if (getenv("MFA_DISABLE_TC")) return false;
   if (p.in_dtype != kBF16 && p.in_dtype != kF16) return false;
   if (p.D != 64 && p.D != 128) return false;
-  if (p.mask_kind != kMaskNone) return false;
+  if (!fwd_tc_mask_ok(p)) return false;
   if (!(p.scale > 0.f) || p.Sq <= 0 || p.Skv <= 0 || p.B <= 0 || p.H <= 0 || p.Hkv <= 0 || p.H % p.Hkv) return false;
   if (p.B > 65535 || p.H > 65535) return false;
   if (!view_ok(p.q, p.Sq, p.H, p.B) || !view_ok(p.k, p.Skv, p.Hkv, p.B) || !view_ok(p.v, p.Skv, p.Hkv, p.B)) return false;
@@ -586,15 +710,18 @@ cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st) {
   prm.o = const_cast<void*>(p.o.ptr);
   prm.o_sb = p.o.sb; prm.o_sh = p.o.sh; prm.o_ss = p.o.ss;
   prm.lse = p.lse;
+  prm.lse_sh = p.lse_sh > 0 ? p.lse_sh : p.Sq;
+  prm.accumulate = p.accumulate && p.lse && p.o_dtype == kF32;
   prm.o_dtype = p.o_dtype;
   prm.H = p.H; prm.Hkv = p.Hkv; prm.Sq = p.Sq; prm.Skv = p.Skv;
   prm.c = p.scale * kLog2e;
   prm.causal = p.causal; prm.window = p.window;
   prm.pingpong = fwd_tc_pingpong();
+  fwd_tc_set_mask(prm, p);
   const bool bf = p.in_dtype == kBF16;
   cudaError_t e = launch_fwd_tc_kernel(prm, p.D, bf ? kFwdBF16 : kFwdF16, st, p.B);
-  if (p.D == 128) g_last_kernel = bf ? "fwd_tc_bf16_d128" : "fwd_tc_fp16_d128";
-  else g_last_kernel = bf ? "fwd_tc_bf16_d64" : "fwd_tc_fp16_d64";
+  if (p.D == 128) g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d128_mask" : "fwd_tc_fp16_d128_mask") : (bf ? "fwd_tc_bf16_d128" : "fwd_tc_fp16_d128");
+  else g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d64_mask" : "fwd_tc_fp16_d64_mask") : (bf ? "fwd_tc_bf16_d64" : "fwd_tc_fp16_d64");
   ++g_launch_count;
   return e;
 }

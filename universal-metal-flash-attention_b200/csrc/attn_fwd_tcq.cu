@@ -103,7 +103,7 @@ cudaError_t launch_int4_to_int8(const void* packed, void* codes, uint64_t n, cud
 bool fwd_tcq_eligible(const AttnParams& p) {
   if (getenv("MFA_DISABLE_TC") || getenv("MFA_DISABLE_TCQ")) return false;
   if (p.in_dtype != kI8 && p.in_dtype != kI4) return false;
-  if (p.D != 128 || p.mask_kind != kMaskNone) return false;
+  if (p.D != 128 || !fwd_tc_mask_ok(p)) return false;
   if (!(p.scale > 0.f) || p.Sq <= 0 || p.Skv <= 0 || p.B <= 0 || p.H <= 0 || p.Hkv <= 0 || p.H % p.Hkv) return false;
   if (p.B > 65535 || p.H > 65535) return false;
   if (!scales_ok(p.qq, false) || !scales_ok(p.qk, true) || !scales_ok(p.qv, true)) return false;
@@ -152,10 +152,12 @@ cudaError_t launch_fwd_tcq(const AttnParams& p, void* scratch, cudaStream_t st) 
   prm.o = const_cast<void*>(p.o.ptr);
   prm.o_sb = p.o.sb; prm.o_sh = p.o.sh; prm.o_ss = p.o.ss;
   prm.lse = p.lse; prm.o_dtype = p.o_dtype;
+  prm.lse_sh = p.lse_sh > 0 ? p.lse_sh : p.Sq;
   prm.H = p.H; prm.Hkv = p.Hkv; prm.Sq = p.Sq; prm.Skv = p.Skv;
   prm.c = p.scale * kLog2e;
   prm.causal = p.causal; prm.window = p.window;
   prm.pingpong = fwd_tc_pingpong();
+  fwd_tc_set_mask(prm, p);
   auto setq = [](const QuantView& q, int S, const float*& arr, float& one, int& br, int& nb, int& stride) {
     arr = q.scales; one = q.scale;
     const bool blocks = q.scales && q.block_rows > 0;

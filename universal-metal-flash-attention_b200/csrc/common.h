@@ -35,6 +35,8 @@ struct AttnParams {
   TensorView q, k, v;       // inputs, in_dtype
   TensorView o;             // output (forward) or saved O (backward), o_dtype
   float* lse;               // [B,H,Sq] fp32, log2 units (L = log2e * logsumexp); may be null in forward
+  int64_t lse_sh;           // forward, tensor-core path: elements between L rows of consecutive (b,h) (0 = Sq)
+  int accumulate;           // forward, tensor-core path: merge the result into the (O, L) already in o / lse
   // backward only
   TensorView d_o;           // dO, do_dtype
   float* dq;                // fp32, contiguous BHSD

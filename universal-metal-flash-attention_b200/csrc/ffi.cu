@@ -840,6 +840,53 @@ mfa_error_t mfa_attention_forward_ex(
   return forward_core(C_(context), a);
 }
 
+// Ring attention step: attention of `seq_len_q` query rows against one visiting K/V block, merged in place into rows
+// [acc_row_offset, acc_row_offset + seq_len_q) of every (b, h) of the running fp32 result out_acc [B, H, acc_rows, D] /
+// lse_acc [B, H, acc_rows] (log2-domain merge).  Tensor-core operands only (bf16 / fp16, head_dim 64 / 128):
+// the merge happens in the kernel epilogue, so no partial O is ever written to HBM.
+mfa_error_t mfa_attention_forward_accumulate(
+    mfa_context_t context, mfa_buffer_t q, mfa_buffer_t k, mfa_buffer_t v, mfa_buffer_t out_acc, mfa_buffer_t lse_acc,
+    uint32_t batch_size, uint32_t seq_len_q, uint32_t seq_len_kv, uint32_t num_heads, uint16_t head_dim,
+    float softmax_scale, bool causal, int32_t window_size, mfa_precision_t input_precision,
+    uint32_t acc_row_offset, uint32_t acc_rows, void* stream) {
+  if (!context || !q || !k || !v || !out_acc || !lse_acc) return MFA_ERROR_INVALID_ARGS;
+  Context* ctx = C_(context);
+  Buffer *bq = B_(q), *bk = B_(k), *bv = B_(v), *bo = B_(out_acc), *bl = B_(lse_acc);
+  const int in_dtype = header_precision_to_dtype(input_precision);
+  if (in_dtype != kBF16 && in_dtype != kF16) return MFA_ERROR_INVALID_ARGS;
+  if ((uint64_t)acc_row_offset + seq_len_q > acc_rows) return MFA_ERROR_INVALID_ARGS;
+  if (bq->mirrored || bk->mirrored || bv->mirrored || bo->mirrored || bl->mirrored) return MFA_ERROR_INVALID_ARGS;
+  if (bo->bytes < elems(batch_size, num_heads, acc_rows, head_dim) * 4 || bl->bytes < (size_t)batch_size * num_heads * acc_rows * 4)
+    return MFA_ERROR_INVALID_ARGS;
+  if (!device_ok()) return MFA_ERROR_DEVICE_NOT_SUPPORTED;
+  if (batch_size == 0 || num_heads == 0 || seq_len_q == 0 || seq_len_kv == 0) return MFA_SUCCESS;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
+  AttnParams p;
+  init_params(p, batch_size, num_heads, seq_len_q, seq_len_kv, head_dim, softmax_scale, causal, window_size < 0 ? -1 : window_size);
+  p.q = view_of(bq, num_heads, seq_len_q, head_dim, false);
+  p.k = view_of(bk, num_heads, seq_len_kv, head_dim, false);
+  p.v = view_of(bv, num_heads, seq_len_kv, head_dim, false);
+  const int64_t D = head_dim, T = acc_rows;
+  p.o = TensorView{reinterpret_cast<float*>(bo->dev) + (size_t)acc_row_offset * D, (int64_t)num_heads * T * D, T * D, D, 1};
+  p.lse = reinterpret_cast<float*>(bl->dev) + acc_row_offset;
+  p.lse_sh = T;
+  p.accumulate = 1;
+  p.in_dtype = in_dtype; p.o_dtype = kF32;
+  if (!fwd_tc_eligible(p)) return MFA_ERROR_INVALID_ARGS;
+  Timer tm(ctx, st, stream == nullptr);
+  cudaError_t e = launch_fwd_tc(p, st);
+  tm.stop();
+  ctx->last_kernel = g_last_kernel;
+  if (e != cudaSuccess) return cuda_fail(e, "forward accumulate launch");
+  if (!stream) {
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "forward accumulate sync");
+    tm.read();
+  }
+  return MFA_SUCCESS;
+}
+
 mfa_error_t mfa_attention_encode_mtl(
     mfa_context_t context, void* command_buffer,
     void* q_buffer, int64_t q_offset, const int64_t* q_strides,

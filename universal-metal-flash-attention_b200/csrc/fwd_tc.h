@@ -15,6 +15,8 @@ struct FwdTcParams {
   void* o;
   long long o_sb, o_sh, o_ss;
   float* lse;
+  long long lse_sh;        // elements between the L rows of consecutive (b, h) pairs (Sq unless the output is a row window)
+  int accumulate;          // merge this launch's partial (O, L) with what lse / o already hold (fp32 O, lse required)
   int o_dtype;
   int H, Hkv, Sq, Skv;
   float c;                 // softmax_scale * log2(e)
@@ -25,11 +27,18 @@ struct FwdTcParams {
   int qbr, kbr, vbr;                                    // tokens per block (multiple of 64 for K / V)
   int nbq, nbk, nbv;                                    // blocks per (b, h)
   int sq_, sk_, sv_;                                    // scale-array stride per (b, h): nb, or 0 for a single device scale
+  // external mask (kernels instantiated with MASKED): bool bytes (non-zero = attend) or additive values, element strides
+  // over [B, H, Sq, Skv] with broadcast dims = 0 and mask_sk == 1
+  const void* mask;
+  int mask_kind, mask_scalar;
+  long long mask_sb, mask_sh, mask_sq;
   int pingpong;                                         // exp2 turn-taking between the two tiles (MFA_FWD_PINGPONG, default 1)
   unsigned long long* trace;                            // debug timeline buffer (MFA_FWD_TRACE), normally null
 };
 
 int fwd_tc_pingpong();
+bool fwd_tc_mask_ok(const AttnParams& p);
+void fwd_tc_set_mask(FwdTcParams& prm, const AttnParams& p);
 
 // grid = (ceil(Sq / 256), H, B).  mode kFwdI8 needs D == 128 (Q / K tiles are int8, V tiles bf16).
 cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm, int D, int mode, cudaStream_t st, int B);

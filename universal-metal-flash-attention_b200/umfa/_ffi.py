@@ -126,6 +126,7 @@ SIGNATURES = {
     # additive B200 symbols (mfa_ffi_ext.h part 2)
     "mfa_attention_forward_ex": (_i32, [_ctx, _buf, _buf, _buf, _buf, _buf] + _DIMS + [_f32, _b, _i32, _i32, _i32] +
                                  _MASK + [_vp]),
+    "mfa_attention_forward_accumulate": (_i32, [_ctx, _buf, _buf, _buf, _buf, _buf] + _DIMS + [_f32, _b, _i32, _i32, _u32, _u32, _vp]),
     "mfa_attention_backward_ex": (_i32, [_ctx] + [_buf] * 10 + _DIMS + [_f32, _b, _i32, _i32] + _MASK + [_vp]),
     "mfa_quantize": (_i32, [_ctx, _buf, _buf, _buf, _u64, _u64, _u32, _u32, _i32, _i32, _f32, _vp]),
     "mfa_dequantize": (_i32, [_ctx, _buf, _buf, _buf, _u64, _u64, _u32, _u32, _i32, _vp]),

@@ -4,12 +4,13 @@ The reference is a single-device library (SURVEY 8e: "Reference support: none");
 BASELINE.json's north_star asks for: one process per GPU, the sequence split into 2G chunks, rank r owning chunks r and
 2G-1-r so causal work is balanced; Q stays put while the K/V chunks travel round the ring (G-1 hops of
 torch.distributed send/recv -- NCCL over NVLink on GPUs, gloo in the CPU tests) overlapped with the attention of the
-previous block.  Every (q chunk, kv chunk) pair is either fully visible, the causal diagonal, or fully hidden and
-skipped before any work is issued, so the kernels only ever see the two mask modes they already have.  Partial results
-carry L = log2-domain logsumexp (the library's A3 convention) and are merged as
-    L = log2(2^L1 + 2^L2),  O = O1 2^(L1-L) + O2 2^(L2-L).
+previous block.  Every (q chunk, kv chunk) pair is either fully visible, the causal diagonal, or fully hidden; with the rank's two
+chunks stored next to each other the visible pairs of a step form ONE rectangular problem (step_plan), so a ring step is
+a single kernel launch.  Partial results carry L = log2-domain logsumexp (the library's A3 convention) and are merged as
+    L = log2(2^L1 + 2^L2),  O = O1 2^(L1-L) + O2 2^(L2-L)
+inside the attention kernel's epilogue (mfa_attention_forward_accumulate): no partial O is written to HBM.
 
-The driver is generic over a small backend (attend / merge / exchange) so the schedule and merge logic run unchanged
+The driver is generic over a small backend (attend / attend_accumulate / exchange) so the schedule and merge logic run unchanged
 on CPU tensors in the world_size-2 gloo tests; `CudaBackend` binds it to libMFAFFI.so.
 """
 import ctypes
@@ -42,10 +43,11 @@ def shard_sequence(x, rank: int, world: int, dim: int = 2):
 
 
 def step_schedule(rank: int, world: int, step: int) -> List[Tuple[int, int, bool]]:
-    """Work of `rank` at ring step `step` (the K/V on hand come from rank (rank - step) mod world).
+    """Work of `rank` at ring step `step` (the K/V on hand come from rank (rank - step) mod world), chunk by chunk.
 
     Returns [(q_chunk, kv_chunk, causal)] with chunk = 0 (low) / 1 (high) of the local / visiting pair; pairs whose
-    keys all lie in the future of the queries are omitted.  Every step costs two chunk-pairs of work on every rank."""
+    keys all lie in the future of the queries are omitted.  Every step costs two chunk-pairs of work on every rank.
+    (The definition the fused plan below is tested against.)"""
     src = (rank - step) % world
     q_lo, q_hi = chunk_ids(rank, world)
     k_lo, k_hi = chunk_ids(src, world)
@@ -59,6 +61,22 @@ def step_schedule(rank: int, world: int, step: int) -> List[Tuple[int, int, bool
     return out
 
 
+def step_plan(rank: int, world: int, step: int) -> Tuple[Tuple[int, int], Tuple[int, int], bool]:
+    """The same work as `step_schedule`, as ONE rectangular attention problem over the rank's sequence-adjacent
+    [low | high] layout: ((q_row0, q_rows), (kv_row0, kv_rows), causal) in units of chunks.
+
+      step 0 (own K/V): the zig-zag pair is causal on local indices (low chunk first)      -> 2 x 2 chunks, causal
+      source rank < rank: both local query chunks see the visitor's low chunk only          -> 2 x 1 chunks, full
+      source rank > rank: only the high query chunk sees the visitor, and sees both chunks  -> 1 x 2 chunks, full
+    One launch per step instead of two or three, and no tile is launched only to be skipped."""
+    src = (rank - step) % world
+    if src == rank:
+        return (0, 2), (0, 2), True
+    if src < rank:
+        return (0, 2), (0, 1), False
+    return (1, 1), (0, 2), False
+
+
 def visible_pairs_causal(n: int) -> int:
     return n * (n + 1) // 2
 
@@ -66,24 +84,29 @@ def visible_pairs_causal(n: int) -> int:
 # ------------------------------------------------------------------------------------------------ generic driver
 def ring_attention_forward(backend, q_pair, k_pair, v_pair, rank: int, world: int, scale: float):
     """q_pair/k_pair/v_pair: (low, high) chunk tensors [B, H, C, D] of this rank.  Returns ((o_lo, l_lo), (o_hi, l_hi)):
-    fp32 O [B,H,C,D] and L [B,H,C] (log2 units) of the two local query chunks."""
-    acc = [None, None]
-    kv_cur = backend.pack_kv(k_pair, v_pair)
+    fp32 O [B,H,C,D] and L [B,H,C] (log2 units) of the two local query chunks (views of one [B,H,2C,.] result)."""
+    C = q_pair[0].shape[2]
+    q_all = backend.cat_seq(q_pair)                      # [B, H, 2C, D], low chunk first
+    kv_cur = backend.pack_kv(k_pair, v_pair)             # [2, B, H, 2C, D]: K and V, low | high adjacent along the sequence
+    acc = None
     for step in range(world):
         handle = None
         if step + 1 < world:
             handle = backend.exchange_start(kv_cur, (rank + 1) % world, (rank - 1) % world, step)
-        k_c, v_c = backend.unpack_kv(kv_cur)
-        for qi, ki, causal in step_schedule(rank, world, step):
-            if acc[qi] is None:
-                acc[qi] = backend.attend(q_pair[qi], k_c[ki], v_c[ki], causal, scale, out=None)
-            else:
-                part = backend.attend(q_pair[qi], k_c[ki], v_c[ki], causal, scale, out="scratch")
-                backend.merge(acc[qi], part)
+        k_all, v_all = backend.unpack_kv(kv_cur)
+        (q0, qn), (k0, kn), causal = step_plan(rank, world, step)
+        q = q_all[:, :, q0 * C:(q0 + qn) * C]
+        k = k_all[:, :, k0 * C:(k0 + kn) * C]
+        v = v_all[:, :, k0 * C:(k0 + kn) * C]
+        if acc is None:
+            acc = backend.attend(q, k, v, causal, scale)             # step 0 covers every local row
+        else:
+            backend.attend_accumulate(acc, q0 * C, q, k, v, causal, scale)
         if handle is not None:
             kv_cur = backend.exchange_finish(handle, step)
     backend.finish()
-    return acc[0], acc[1]
+    o, l = acc
+    return (o[:, :, :C], l[:, :, :C]), (o[:, :, C:], l[:, :, C:])
 
 
 def merge_partials_numpy(o_acc, l_acc, o_part, l_part):
@@ -108,18 +131,27 @@ class HostBackend:
         self.attend_fn = attend_fn
         self.dist = dist
 
+    def cat_seq(self, pair):
+        return np.ascontiguousarray(np.concatenate([pair[0], pair[1]], axis=2))
+
     def pack_kv(self, k_pair, v_pair):
-        return np.ascontiguousarray(np.stack([k_pair[0], k_pair[1], v_pair[0], v_pair[1]]))
+        return np.ascontiguousarray(np.stack([self.cat_seq(k_pair), self.cat_seq(v_pair)]))
 
     def unpack_kv(self, buf):
-        return (buf[0], buf[1]), (buf[2], buf[3])
+        return buf[0], buf[1]
 
-    def attend(self, q, k, v, causal, scale, out=None):
+    def attend(self, q, k, v, causal, scale):
         o, l = self.attend_fn(q, k, v, causal, scale)
         return [np.array(o, np.float32), np.array(l, np.float32)]
 
-    def merge(self, acc, part):
-        merge_partials_numpy(acc[0], acc[1], part[0], part[1])
+    def attend_accumulate(self, acc, row0, q, k, v, causal, scale):
+        o, l = self.attend_fn(q, k, v, causal, scale)
+        rows = q.shape[2]
+        o_acc = np.ascontiguousarray(acc[0][:, :, row0:row0 + rows])
+        l_acc = np.ascontiguousarray(acc[1][:, :, row0:row0 + rows])
+        merge_partials_numpy(o_acc, l_acc, np.asarray(o, np.float32), np.asarray(l, np.float32))
+        acc[0][:, :, row0:row0 + rows] = o_acc
+        acc[1][:, :, row0:row0 + rows] = l_acc
 
     def exchange_start(self, buf, dst, src, step):
         import torch
@@ -162,32 +194,35 @@ class CudaBackend:
         from .core import MFABuffer
         return MFABuffer(self.ctx, device_ptr=t.data_ptr(), size=t.numel() * t.element_size())
 
+    def _view(self, t):
+        """handle over a (possibly sequence-sliced) [B, H, S, D] tensor: element strides travel with the handle"""
+        from .core import MFABuffer
+        span = sum((n - 1) * st for n, st in zip(t.shape, t.stride())) + 1
+        return MFABuffer(self.ctx, device_ptr=t.data_ptr(), size=span * t.element_size(), shape=tuple(t.shape),
+                         strides=tuple(t.stride()))
+
+    def cat_seq(self, pair):
+        return self.torch.cat([pair[0], pair[1]], dim=2)
+
     def pack_kv(self, k_pair, v_pair):
         torch = self.torch
-        buf = torch.stack([k_pair[0], k_pair[1], v_pair[0], v_pair[1]]).contiguous()
+        buf = torch.stack([self.cat_seq(k_pair), self.cat_seq(v_pair)]).contiguous()
         self.kv_bufs[0] = buf
         self.kv_bufs[1] = torch.empty_like(buf)
         self.cur = 0
         return buf
 
     def unpack_kv(self, buf):
-        return (buf[0], buf[1]), (buf[2], buf[3])
+        return buf[0], buf[1]
 
-    def attend(self, q, k, v, causal, scale, out=None):
+    def attend(self, q, k, v, causal, scale):
         torch = self.torch
-        B, H, C, D = q.shape
+        B, H, S, D = q.shape
         Skv = k.shape[2]
-        if out == "scratch":
-            key = (B, H, C, D)
-            if key not in self.scratch:
-                self.scratch[key] = [torch.empty(B, H, C, D, device=self.device, dtype=torch.float32),
-                                     torch.empty(B, H, C, device=self.device, dtype=torch.float32)]
-            o, l = self.scratch[key]
-        else:
-            o = torch.empty(B, H, C, D, device=self.device, dtype=torch.float32)
-            l = torch.empty(B, H, C, device=self.device, dtype=torch.float32)
-        bufs = [self._buf(t) for t in (q, k, v, o, l)]
-        rc = self.lib.mfa_attention_forward_ex(self.ctx.handle, *[b.handle for b in bufs], B, C, Skv, H, D, scale, causal,
+        o = torch.empty(B, H, S, D, device=self.device, dtype=torch.float32)
+        l = torch.empty(B, H, S, device=self.device, dtype=torch.float32)
+        bufs = [self._view(q), self._view(k), self._view(v), self._buf(o), self._buf(l)]
+        rc = self.lib.mfa_attention_forward_ex(self.ctx.handle, *[b.handle for b in bufs], B, S, Skv, H, D, scale, causal,
                                                -1, self.prec, 2, None, 0, None, None, 0, 0, 0, self.stream_ptr)
         for b in bufs:
             b.close()
@@ -195,6 +230,19 @@ class CudaBackend:
             raise RuntimeError(f"mfa_attention_forward_ex failed: {rc}")
         self.launches += 1
         return [o, l]
+
+    def attend_accumulate(self, acc, row0, q, k, v, causal, scale):
+        B, H, S, D = q.shape
+        Skv = k.shape[2]
+        T = acc[1].shape[2]
+        bufs = [self._view(q), self._view(k), self._view(v), self._buf(acc[0]), self._buf(acc[1])]
+        rc = self.lib.mfa_attention_forward_accumulate(self.ctx.handle, *[b.handle for b in bufs], B, S, Skv, H, D, scale,
+                                                       causal, -1, self.prec, row0, T, self.stream_ptr)
+        for b in bufs:
+            b.close()
+        if rc != 0:
+            raise RuntimeError(f"mfa_attention_forward_accumulate failed: {rc}")
+        self.launches += 1
 
     def merge(self, acc, part):
         rows = acc[1].numel()
