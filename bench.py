@@ -263,6 +263,9 @@ def main():
     torch.cuda.set_device(local_rank)
     os.environ["MFA_CUDA_DEVICE"] = str(local_rank)
     if world > 1:
+        # ring hops must not queue behind the attention grid that fills every SM: NCCL's internal stream gets CTA
+        # dispatch priority (profiles/r01e_ring_notes.txt)
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     if w.get("ring"):

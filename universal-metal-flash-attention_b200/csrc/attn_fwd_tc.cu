@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         tc_fence_after();
       }
       float inv = (l > 0.f ? 1.f / l : 0.f) * ((I8 && !v_blocks) ? p.vs1 : 1.f);
-      const bool live = r < p.Sq;
+      const bool live = r < p.Sq && !p.debug_skip_store;
       const size_t orow = (size_t)b * p.o_sb + (size_t)h * p.o_sh + (size_t)r * p.o_ss;
       const size_t lrow = ((size_t)b * p.H + h) * p.lse_sh + r;
       float l_out = l > 0.f ? m + log2f(l) : -CUDART_INF_F;
@@ -503,6 +503,11 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       //   L = log2(2^L_old + 2^L_new),  O = O_old 2^(L_old - L) + O_new 2^(L_new - L)      (fp32 O only)
       float c_old = 0.f;
       const bool acc_mode = p.accumulate && p.o_dtype == kF32;
+      const bool tma_out = p.o_tma && !acc_mode && !p.debug_skip_store;
+      if (tma_out) {
+        // the staging area reuses the operand memory: wait until the other tile has retired its last MMA too
+        if (n > 0 && nt == 2) { mbar_wait(o_full(t ^ 1), 0); tc_fence_after(); }
+      }
       if (acc_mode && live) {
         const float l_old = p.lse[lrow];
         const float mx = fmaxf(l_old, l_out);
@@ -524,7 +529,15 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
 #pragma unroll
           for (int i = 0; i < 32; ++i) ou[i] = 0u;
         }
-        if (live) {
+        if (tma_out) {
+          // 32 columns of this row -> one 128-byte line of the swizzled staging chunk (16-byte unit j lands at j ^ (row & 7):
+          // the layout the fp32 output tensor map expects, and conflict-free for the 32 rows of a warp)
+          const uint32_t line = base + (uint32_t)(t * (D / 32) + ch) * (128u * 128u) + (uint32_t)row * 128u;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            st_shared_v4(line + (uint32_t)((i ^ (row & 7)) << 4), __uint_as_float(ou[4 * i]) * inv, __uint_as_float(ou[4 * i + 1]) * inv,
+                         __uint_as_float(ou[4 * i + 2]) * inv, __uint_as_float(ou[4 * i + 3]) * inv);
+        } else if (live) {
           if (p.o_dtype == kF32) {
             float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.o) + orow + ch * 32);
             if (acc_mode) {
@@ -556,6 +569,17 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
               dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
+        }
+      }
+      if (tma_out) {
+        fence_proxy_async_smem();
+        named_bar_sync(4 + t, 128);
+        if ((threadIdx.x & 127) == 0) {
+#pragma unroll
+          for (int ch = 0; ch < D / 32; ++ch)
+            tma_store_4d(&p.to, base + (uint32_t)(t * (D / 32) + ch) * (128u * 128u), ch * 32, r0 + t * 128, h, b);
+          bulk_commit();
+          bulk_wait_read();           // the CTA may exit (and free its shared memory) once the TMA has read the tile
         }
       }
       if (live && p.lse) p.lse[lrow] = l_out;
@@ -687,6 +711,15 @@ void fwd_tc_set_mask(FwdTcParams& prm, const AttnParams& p) {
   prm.mask_sb = p.mask_sb; prm.mask_sh = p.mask_sh; prm.mask_sq = p.mask_sq;
 }
 
+// fp32 O goes out through TMA bulk stores from a swizzled staging tile (coalesced, asynchronous) when the view allows a
+// tensor map; otherwise (and for 16-bit O or the accumulate mode) the row-owner threads store directly.
+void fwd_tc_set_out_map(FwdTcParams& prm, const AttnParams& p) {
+  prm.o_tma = 0;
+  if (p.o_dtype != kF32 || p.accumulate || getenv("MFA_DISABLE_TMA_STORE")) return;
+  if (!tc::view_ok(p.o, p.H, p.B, 4)) return;
+  if (tc::make_map(&prm.to, p.o, kF32, p.B, p.H, p.Sq, p.D)) prm.o_tma = 1;
+}
+
 bool fwd_tc_eligible(const AttnParams& p) {
   if (getenv("MFA_DISABLE_TC")) return false;
   if (p.in_dtype != kBF16 && p.in_dtype != kF16) return false;
@@ -717,6 +750,8 @@ cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st) {
   prm.c = p.scale * kLog2e;
   prm.causal = p.causal; prm.window = p.window;
   prm.pingpong = fwd_tc_pingpong();
+  prm.debug_skip_store = getenv("MFA_DEBUG_SKIP_STORE") ? 1 : 0;       // timing experiment only: O / L are not written
+  fwd_tc_set_out_map(prm, p);
   fwd_tc_set_mask(prm, p);
   const bool bf = p.in_dtype == kBF16;
   cudaError_t e = launch_fwd_tc_kernel(prm, p.D, bf ? kFwdBF16 : kFwdF16, st, p.B);

@@ -12,6 +12,8 @@ enum FwdMode : int { kFwdF16 = 0, kFwdBF16 = 1, kFwdI8 = 2 };
 
 struct FwdTcParams {
   CUtensorMap tq, tk, tv;
+  CUtensorMap to;          // fp32 O, box = 32 floats x 128 rows (valid when o_tma != 0)
+  int o_tma;               // epilogue stages O in shared memory and writes it with TMA bulk stores
   void* o;
   long long o_sb, o_sh, o_ss;
   float* lse;
@@ -32,6 +34,7 @@ struct FwdTcParams {
   const void* mask;
   int mask_kind, mask_scalar;
   long long mask_sb, mask_sh, mask_sq;
+  int debug_skip_store;                                 // MFA_DEBUG_SKIP_STORE: epilogue writes nothing (timing experiments)
   int pingpong;                                         // exp2 turn-taking between the two tiles (MFA_FWD_PINGPONG, default 1)
   unsigned long long* trace;                            // debug timeline buffer (MFA_FWD_TRACE), normally null
 };
@@ -39,6 +42,7 @@ struct FwdTcParams {
 int fwd_tc_pingpong();
 bool fwd_tc_mask_ok(const AttnParams& p);
 void fwd_tc_set_mask(FwdTcParams& prm, const AttnParams& p);
+void fwd_tc_set_out_map(FwdTcParams& prm, const AttnParams& p);
 
 // grid = (ceil(Sq / 256), H, B).  mode kFwdI8 needs D == 128 (Q / K tiles are int8, V tiles bf16).
 cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm, int D, int mode, cudaStream_t st, int B);

@@ -31,11 +31,12 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // [B, Hn, S, D] view with unit inner stride -> 4-D tensor map, box = (128 bytes of a row) x box_rows rows, 128B
-// swizzle.  elem_bytes: 2 for fp16/bf16, 1 for int8/fp8 operands (box is then 128 elements wide).
+// swizzle.  elem_bytes: 2 for fp16/bf16, 1 for int8/fp8 operands (box is then 128 elements wide), 4 for the fp32 output
+// map of the forward's TMA-store epilogue (box = 32 floats).
 inline bool make_map(CUtensorMap* out, const TensorView& t, int dtype, int B, int Hn, int S, int D, int box_rows = 128) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
-  const cuuint64_t eb = (dtype == kI8) ? 1 : 2;
+  const cuuint64_t eb = (dtype == kI8) ? 1 : (dtype == kF32) ? 4 : 2;
   cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)Hn, (cuuint64_t)B};
   cuuint64_t st[3] = {(cuuint64_t)t.ss * eb, (cuuint64_t)t.sh * eb, (cuuint64_t)t.sb * eb};
   if (Hn == 1) st[1] = st[0] * (cuuint64_t)S;
@@ -45,6 +46,7 @@ inline bool make_map(CUtensorMap* out, const TensorView& t, int dtype, int B, in
   cuuint32_t es[4] = {1, 1, 1, 1};
   const CUtensorMapDataType ty = dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                : dtype == kF16  ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                               : dtype == kF32  ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                                 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
   CUresult r = fn(out, ty, 4, const_cast<void*>(t.ptr), dims, st, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -183,7 +183,7 @@ class CudaBackend:
         self.lib = _ffi._lib
         self.prec = {"bf16": 1, "fp16": 0}[dtype]
         self.compute = torch.cuda.current_stream(device)
-        self.comm = torch.cuda.Stream(device)
+        self.comm = torch.cuda.Stream(device, priority=-1)
         self.stream_ptr = ctypes.c_void_p(self.compute.cuda_stream)
         self.kv_bufs = [None, None]
         self.compute_done = [None, None]
