@@ -232,3 +232,61 @@ def test_tc_mask_matches_exact_path(ctx, monkeypatch):
     out2 = umfa.flash_attention_forward(ctx, qa, ka, va, input_precision="bf16", output_precision="fp32", layout="bhsd", attn_mask=m)
     assert not ctx.last_kernel.startswith("fwd_tc_")
     assert rel_max(out, out2) < 1e-2
+
+
+def _packing_mask(S, nblk):
+    """block-diagonal bool mask (sequence packing): tokens attend only inside their own block"""
+    seg = np.repeat(np.arange(nblk), S // nblk)
+    return seg[:, None] == seg[None, :]
+
+
+@pytest.mark.parametrize("kind", ["bool", "add_fp32"])
+def test_tc_mask_tile_skipping_matches_oracle(ctx, kind, monkeypatch):
+    """KV tiles the mask hides completely are never loaded (visible-tile lists built by the pre-pass); the result is the
+    same as visiting every tile and as the oracle.  Ragged sizes, blocks that do not line up with the 128-key tiles."""
+    import umfa
+    B, H, Sq, Skv, D = 2, 2, 900, 900, 128
+    rng = np.random.default_rng(21)
+    q, k, v = (rng.standard_normal(s).astype(np.float32) for s in ((B, H, Sq, D), (B, H, Skv, D), (B, H, Skv, D)))
+    (qa, qv), (ka, kv), (va, vv) = (to_dtype(x, "bf16") for x in (q, k, v))
+    vis = _packing_mask(Sq, 6)[None, None]                                  # 150-token segments
+    vis = np.broadcast_to(vis, (B, 1, Sq, Skv)).copy()
+    vis[1, 0, 700:, :] = False                                              # some fully hidden query rows
+    if kind == "bool":
+        m, om = vis, vis
+    else:
+        m = np.where(vis, rng.standard_normal(vis.shape), -np.inf).astype(np.float32)
+        om = m
+    out, lse = umfa.flash_attention_forward(ctx, qa, ka, va, input_precision="bf16", output_precision="fp32", layout="bhsd",
+                                            attn_mask=m, return_lse=True)
+    assert ctx.last_kernel.endswith("_mask")
+    ref, lref = O.attention_forward(qv, kv, vv, mask=om)
+    assert rel_max(out, ref) < 2e-2
+    fin = np.isfinite(lref)
+    assert (np.isfinite(lse) == fin).all() and np.abs(lse[fin] - lref[fin]).max() < 2e-2
+    assert (out[1, :, 700:] == 0).all()
+    monkeypatch.setenv("MFA_DISABLE_MASK_SKIP", "1")
+    out2, lse2 = umfa.flash_attention_forward(ctx, qa, ka, va, input_precision="bf16", output_precision="fp32", layout="bhsd",
+                                              attn_mask=m, return_lse=True)
+    assert rel_max(out, out2) < 1e-6 and np.array_equal(np.isfinite(lse), np.isfinite(lse2))
+
+
+def test_tc_mask_tile_skipping_saves_time(ctx, monkeypatch):
+    """a 16-segment packing mask leaves ~1/16 of the KV tiles visible: the launch must be several times shorter than with
+    every tile visited (device time from mfa_get_gpu_latency)"""
+    import umfa
+    B, H, S, D = 1, 8, 8192, 128
+    rng = np.random.default_rng(22)
+    q, k, v = (to_dtype(rng.standard_normal((B, H, S, D)).astype(np.float32), "bf16")[0] for _ in range(3))
+    m = _packing_mask(S, 16)
+
+    def run():
+        best = 1e9
+        for _ in range(3):
+            umfa.flash_attention_forward(ctx, q, k, v, input_precision="bf16", output_precision="fp32", layout="bhsd", attn_mask=m)
+            best = min(best, ctx.gpu_latency)
+        return best
+    t_skip = run()
+    monkeypatch.setenv("MFA_DISABLE_MASK_SKIP", "1")
+    t_all = run()
+    assert t_skip < 0.5 * t_all, f"skip {t_skip * 1e3:.3f} ms vs all tiles {t_all * 1e3:.3f} ms"

@@ -62,7 +62,7 @@ struct Cfg {
   static constexpr int kVTile = kVChunks * kChunkBytes;
   static constexpr int kStage = kVTile;                              // ring stage (K tiles may use part of it)
   static constexpr int kStages = D == 128 ? 5 : 10;
-  static constexpr int kBarBytes = 112 + 16 * kStages + 16;
+  static constexpr int kBarBytes = 112 + 16 * kStages + 16 + 32;      // + q_empty, o_empty
   static constexpr int kSmem = 2 * kQTile + kStages * kStage + kBarBytes + 1024;
 };
 
@@ -165,24 +165,51 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
   auto kv_full = [&](int s) { return sBar + 112 + 8 * s; };
   auto kv_empty = [&](int s) { return sBar + 112 + 8 * NS + 8 * s; };
   const uint32_t tmem_slot = sBar + 112 + 16 * NS;
+  auto q_empty = [&](int t) { return sBar + 112 + 16 * NS + 16 + 8 * t; };   // MMA warp: Q_t smem may be reloaded
+  auto o_empty = [&](int t) { return sBar + 112 + 16 * NS + 32 + 8 * t; };   // softmax warps: O_t left TMEM (epilogue read it)
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
-  const int qblk = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;   // heavy blocks first
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int hk = h / (p.H / p.Hkv);
-  const int r0 = qblk * 256;
-  const int nt = (r0 + 128 < p.Sq) ? 2 : 1;
-  int klo, khi;
-  visible_key_range(p.causal, p.window, p.Skv, r0, min(r0 + 256, p.Sq), klo, khi);
-  const int j_lo = klo >> 7;
-  const int n = khi > klo ? ((khi + 127) >> 7) - j_lo : 0;
+  // Work items = (batch, head, 256-row query block), x fastest so the CTAs of one head run together (K/V stay in L2).
+  // The grid is either one CTA per item or -- persistent mode, uniform-cost problems -- one CTA per SM striding over the
+  // items: the producer then prefetches the next item's Q/K/V and the MMA warps start its first S while the softmax warps
+  // are still in the epilogue of the previous one, so the per-item prologue / epilogue latency is hidden.
+  const int nqb = (p.Sq + 255) / 256;
+  const int n_items = nqb * p.H * p.nbatch;
+  struct Item { int r0, h, b, hk, nt, j_lo, n, lid; };
+  auto decode = [&](int w) {
+    Item it;
+    const int x = w % nqb, hb = w / nqb;
+    const int qblk = p.causal ? nqb - 1 - x : x;                                     // heavy blocks first
+    it.h = hb % p.H; it.b = hb / p.H;
+    it.hk = it.h / (p.H / p.Hkv);
+    it.r0 = qblk * 256;
+    it.nt = (it.r0 + 128 < p.Sq) ? 2 : 1;
+    int klo, khi;
+    visible_key_range(p.causal, p.window, p.Skv, it.r0, min(it.r0 + 256, p.Sq), klo, khi);
+    it.j_lo = klo >> 7;
+    it.n = khi > klo ? ((khi + 127) >> 7) - it.j_lo : 0;
+    it.lid = 0;
+    if constexpr (MASKED) {
+      if (p.mtiles) {        // the list already folds in the causal / window range
+        it.lid = ((p.mask_sb ? it.b : 0) * (p.mask_sh ? p.H : 1) + (p.mask_sh ? it.h : 0)) * nqb + qblk;
+        it.n = __ldg(p.mcounts + it.lid);
+      }
+    }
+    return it;
+  };
+  // KV tile visited at step `it` of an item
+  auto tile_of = [&](const Item& im, int it) {
+    if constexpr (MASKED) { if (p.mtiles) return __ldg(p.mtiles + (size_t)im.lid * p.m_nkt + it); }
+    return im.j_lo + it;
+  };
 
   if (threadIdx.x == 256) {
     for (int t = 0; t < 2; ++t) {
       mbar_init(q_full(t), 1); mbar_init(s_full(t), 1); mbar_init(o_full(t), 1);
       for (int k = 0; k < kParts; ++k) mbar_init(p_part(t, k), 4);
     }
-    for (int s = 0; s < NS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), nt); }
+    for (int s = 0; s < NS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2); }   // a lone tile releases twice
+    for (int t = 0; t < 2; ++t) { mbar_init(q_empty(t), 1); mbar_init(o_empty(t), 4); }
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -199,103 +226,135 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
   if (warp == 9) {
     // ------------------------------------------------------------------ TMA producer
     reg_dealloc<40>();
-    if (lane == 0 && n > 0) {
-      auto load_qk = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int row, int head) {
-        mbar_arrive_expect_tx(bar, QT);
+    if (lane == 0) {
+      int kvi = 0, qc[2] = {0, 0};                      // running ring index; items in which tile t took part
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const Item im = decode(w);
+        const int r0 = im.r0, h = im.h, b = im.b, hk = im.hk, nt = im.nt, n = im.n;
+        if (n == 0) continue;
+        auto load_qk = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int row, int head) {
+          mbar_arrive_expect_tx(bar, QT);
 #pragma unroll
-        for (int c = 0; c < C::kQChunks; ++c) tma_load_4d(dst + c * CHB, m, bar, c * (I8 ? 128 : 64), row, head, b);
-      };
-      auto load_v = [&](uint32_t dst, uint32_t bar, int row) {
-        mbar_arrive_expect_tx(bar, VT);
+          for (int c = 0; c < C::kQChunks; ++c) tma_load_4d(dst + c * CHB, m, bar, c * (I8 ? 128 : 64), row, head, b);
+        };
+        auto load_v = [&](uint32_t dst, uint32_t bar, int row) {
+          mbar_arrive_expect_tx(bar, VT);
 #pragma unroll
-        for (int c = 0; c < C::kVChunks; ++c) tma_load_4d(dst + c * CHB, &p.tv, bar, c * 64, row, hk, b);
-      };
-      load_qk(sQ, &p.tq, q_full(0), r0, h);
-      for (int it = 0; it < n; ++it) {
-        const int row = (j_lo + it) * 128;
-        int idx = 2 * it, s = idx % NS;
-        mbar_wait(kv_empty(s), ((idx / NS) & 1) ^ 1);
-        load_qk(sKV + s * STG, &p.tk, kv_full(s), row, hk);
-        if (it == 0 && nt == 2) load_qk(sQ + QT, &p.tq, q_full(1), r0 + 128, h);
-        idx = 2 * it + 1; s = idx % NS;
-        mbar_wait(kv_empty(s), ((idx / NS) & 1) ^ 1);
-        load_v(sKV + s * STG, kv_full(s), row);
+          for (int c = 0; c < C::kVChunks; ++c) tma_load_4d(dst + c * CHB, &p.tv, bar, c * 64, row, hk, b);
+        };
+        if (qc[0] > 0) mbar_wait(q_empty(0), (qc[0] - 1) & 1);
+        load_qk(sQ, &p.tq, q_full(0), r0, h);
+        ++qc[0];
+        for (int it = 0; it < n; ++it) {
+          const int row = tile_of(im, it) * 128;
+          int s = kvi % NS;
+          mbar_wait(kv_empty(s), ((kvi / NS) & 1) ^ 1);
+          load_qk(sKV + s * STG, &p.tk, kv_full(s), row, hk);
+          ++kvi;
+          if (it == 0 && nt == 2) {
+            if (qc[1] > 0) mbar_wait(q_empty(1), (qc[1] - 1) & 1);
+            load_qk(sQ + QT, &p.tq, q_full(1), r0 + 128, h);
+            ++qc[1];
+          }
+          s = kvi % NS;
+          mbar_wait(kv_empty(s), ((kvi / NS) & 1) ^ 1);
+          load_v(sKV + s * STG, kv_full(s), row);
+          ++kvi;
+        }
       }
     }
   } else if (warp == 8 || warp == 10) {
     // ------------------------------------------------------------------ MMA issuer of tile t (whole warp, one elected lane issues)
     reg_dealloc<40>();
     const int t = (warp - 8) >> 1;
-    if (n > 0 && t < nt) {
-      constexpr uint32_t FMT = PBF16 ? 1u : 0u;
-      constexpr uint32_t IDESC_S = I8 ? make_idesc(2, 1, 1, 0, 0, 128, 128)        // s32 += s8 * s8, K-major A and B
-                                      : make_idesc(1, FMT, FMT, 0, 0, 128, 128);
-      constexpr uint32_t IDESC_O = make_idesc(1, FMT, FMT, 0, 1, 128, D);          // f32 += P (tmem) * V, V MN-major
-      const uint32_t q_lo = desc_lo(sQ, 16) + t * (QT >> 4), k_lo = desc_lo(sKV, 16), v_lo = desc_lo(sKV, CHB);
-      const uint32_t tS = tmem + t * 128, tO = tmem + 256 + t * D;
-      auto issue_s = [&](int idx) {
-        const uint32_t b0 = k_lo + (idx % NS) * (STG >> 4);
-        if constexpr (I8) {
+    constexpr uint32_t FMT = PBF16 ? 1u : 0u;
+    constexpr uint32_t IDESC_S = I8 ? make_idesc(2, 1, 1, 0, 0, 128, 128)        // s32 += s8 * s8, K-major A and B
+                                    : make_idesc(1, FMT, FMT, 0, 0, 128, 128);
+    constexpr uint32_t IDESC_O = make_idesc(1, FMT, FMT, 0, 1, 128, D);          // f32 += P (tmem) * V, V MN-major
+    const uint32_t q_lo = desc_lo(sQ, 16) + t * (QT >> 4), k_lo = desc_lo(sKV, 16), v_lo = desc_lo(sKV, CHB);
+    const uint32_t tS = tmem + t * 128, tO = tmem + 256 + t * D;
+    auto issue_s = [&](int idx) {
+      const uint32_t b0 = k_lo + (idx % NS) * (STG >> 4);
+      if constexpr (I8) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)           // 32 int8 per MMA = 32 bytes of the 128-byte row
-            mma_i8_ss_u(tS, q_lo + kk * 2, kDescHiSw128, b0 + kk * 2, kDescHiSw128, IDESC_S, kk > 0);
-        } else {
+        for (int kk = 0; kk < 4; ++kk)           // 32 int8 per MMA = 32 bytes of the 128-byte row
+          mma_i8_ss_u(tS, q_lo + kk * 2, kDescHiSw128, b0 + kk * 2, kDescHiSw128, IDESC_S, kk > 0);
+      } else {
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            const uint32_t off = ((kk >> 2) * CHB + (kk & 3) * 32) >> 4;
-            mma_f16_ss_u(tS, q_lo + off, kDescHiSw128, b0 + off, kDescHiSw128, IDESC_S, kk > 0);
-          }
-        }
-      };
-      auto issue_o_part = [&](int idx, int part, bool acc) {
-        const uint32_t b0 = v_lo + (idx % NS) * (STG >> 4);
-#pragma unroll
-        for (int kk = 2 * part; kk < 2 * part + 2; ++kk)
-          mma_f16_ts_u(tO, tS + kk * 8, b0 + kk * (2048 >> 4), kDescHiSw128, IDESC_O, (acc || kk > 0) ? 1u : 0u);
-      };
-      auto wait_full = [&](int idx) { mbar_wait(kv_full(idx % NS), (idx / NS) & 1); };
-      unsigned long long* tr = nullptr;            // timeline of CTA (0,0,0): MFA_FWD_TRACE (debug builds of the launch only)
-      if (TR && p.trace && blockIdx.x + blockIdx.y + blockIdx.z == 0 && lane == 0) tr = p.trace + (size_t)t * 64 * 16;
-      mbar_wait(q_full(t), 0);
-      wait_full(0);
-      tc_fence_after();
-      issue_s(0);
-      tc_commit_u(s_full(t));
-      tc_commit_u(kv_empty(0));
-      for (int it = 0; it < n; ++it) {
-        const int vi = 2 * it + 1, ki = 2 * it + 2;
-        wait_full(vi);
-        if (TR && tr && it < 64) tr[it * 16 + 13] = clock64();
-#pragma unroll
-        for (int part = 0; part < kParts; ++part) {
-          mbar_wait(p_part(t, part), it & 1);
-          tc_fence_after();
-          if (TR && tr && it < 64) tr[it * 16 + 8 + part] = clock64();
-          issue_o_part(vi, part, it > 0);
-        }
-        tc_commit_u(kv_empty(vi % NS));
-        if (it + 1 < n) {
-          wait_full(ki);
-          tc_fence_after();
-          if (TR && tr && it < 64) tr[it * 16 + 14] = clock64();
-          issue_s(ki);
-          tc_commit_u(s_full(t));
-          tc_commit_u(kv_empty(ki % NS));
-          if (TR && tr && it < 64) tr[it * 16 + 12] = clock64();
-        } else {
-          tc_commit_u(o_full(t));
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = ((kk >> 2) * CHB + (kk & 3) * 32) >> 4;
+          mma_f16_ss_u(tS, q_lo + off, kDescHiSw128, b0 + off, kDescHiSw128, IDESC_S, kk > 0);
         }
       }
+    };
+    auto issue_o_part = [&](int idx, int part, bool acc) {
+      const uint32_t b0 = v_lo + (idx % NS) * (STG >> 4);
+#pragma unroll
+      for (int kk = 2 * part; kk < 2 * part + 2; ++kk)
+        mma_f16_ts_u(tO, tS + kk * 8, b0 + kk * (2048 >> 4), kDescHiSw128, IDESC_O, (acc || kk > 0) ? 1u : 0u);
+    };
+    auto wait_full = [&](int idx) { mbar_wait(kv_full(idx % NS), (idx / NS) & 1); };
+    int kvbase = 0, qc = 0, pc = 0;                // ring index at the start of the item; items / KV steps done by this tile
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const Item im = decode(w);
+      const int nt = im.nt, n = im.n;
+      if (n > 0 && t < nt) {
+        // a lone tile (ragged last query block) releases every ring stage for the absent one as well
+        auto release = [&](int idx) { tc_commit_u(kv_empty(idx % NS)); if (nt == 1) tc_commit_u(kv_empty(idx % NS)); };
+        unsigned long long* tr = nullptr;            // timeline of the first item of CTA 0: MFA_FWD_TRACE (debug builds of the launch only)
+        if (TR && p.trace && w == 0 && lane == 0) tr = p.trace + (size_t)t * 64 * 16;
+        mbar_wait(q_full(t), qc & 1);
+        wait_full(kvbase);
+        tc_fence_after();
+        issue_s(kvbase);
+        tc_commit_u(s_full(t));
+        release(kvbase);
+        if (n == 1) tc_commit_u(q_empty(t));
+        for (int it = 0; it < n; ++it) {
+          const int vi = kvbase + 2 * it + 1, ki = kvbase + 2 * it + 2;
+          wait_full(vi);
+          if (TR && tr && it < 64) tr[it * 16 + 13] = clock64();
+#pragma unroll
+          for (int part = 0; part < kParts; ++part) {
+            mbar_wait(p_part(t, part), pc & 1);
+            // first P V of an item overwrites O: the epilogue of the previous item must have read it out of TMEM
+            if (part == 0 && it == 0 && qc > 0) mbar_wait(o_empty(t), (qc - 1) & 1);
+            tc_fence_after();
+            if (TR && tr && it < 64) tr[it * 16 + 8 + part] = clock64();
+            issue_o_part(vi, part, it > 0);
+          }
+          release(vi);
+          if (it + 1 < n) {
+            wait_full(ki);
+            tc_fence_after();
+            if (TR && tr && it < 64) tr[it * 16 + 14] = clock64();
+            issue_s(ki);
+            tc_commit_u(s_full(t));
+            release(ki);
+            if (it + 2 == n) tc_commit_u(q_empty(t));          // last S of the item: Q_t may be reloaded for the next one
+            if (TR && tr && it < 64) tr[it * 16 + 12] = clock64();
+          } else {
+            tc_commit_u(o_full(t));
+          }
+          ++pc;
+        }
+        ++qc;
+      }
+      kvbase += 2 * n;
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------ softmax warpgroups
     reg_alloc<232>();
     const int t = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
-    const int r = r0 + t * 128 + row;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tS = tmem + lane_base + t * 128;
     const uint32_t tO = tmem + lane_base + 256 + t * D;
+    int pc = 0, qc = 0;                                    // KV steps / items done by this tile (barrier phases)
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+    const Item im = decode(w);
+    const int r0 = im.r0, h = im.h, b = im.b, hk = im.hk, nt = im.nt, n = im.n;
+    const int r = r0 + t * 128 + row;
     float m = -CUDART_INF_F, l = 0.f;                      // m in scaled log2 units (score * scale * log2 e)
     const int chi = p.causal ? min(p.Skv - 1, r) : p.Skv - 1;
     const int clo = p.window >= 0 ? max(0, r - p.window) : 0;
@@ -317,9 +376,10 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       // after S of the current step has been read), so the L2 / HBM latency of these loads never sits between the
       // s_full wait and the exp2 phase (it cost ~900 clk per step when the loads were issued at the top of the step).
       float ksn0 = p.ks1, ksn1 = p.ks1, vsn0 = 1.f, vsn1 = 1.f;
-      auto fetch_scales = [&](int it) {
+      int jt_next = n > 0 ? tile_of(im, 0) : 0;        // tile index of the coming step (read one step ahead)
+      auto fetch_scales = [&](int jt) {
         if constexpr (I8) {
-          const int c0 = (j_lo + it) * 128;
+          const int c0 = jt * 128;
           if (ksp) {
             ksn0 = __ldg(ksp + min(c0 / p.kbr, p.nbk - 1));
             ksn1 = __ldg(ksp + min((c0 + 64) / p.kbr, p.nbk - 1));
@@ -330,9 +390,9 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           }
         }
       };
-      if (n > 0) fetch_scales(0);
+      if (n > 0) fetch_scales(jt_next);
       for (int it = 0; it < n; ++it) {
-        const int c0 = (j_lo + it) * 128;
+        const int c0 = jt_next * 128;
         // multipliers of the two 64-key halves of this tile (int8: blocks are multiples of 64 keys)
         float a0 = qsc, a1 = qsc, lv0 = 0.f, lv1 = 0.f, iv0 = 1.f, iv1 = 1.f;
         if constexpr (I8) {
@@ -344,9 +404,10 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           }
         }
         unsigned long long* tr = nullptr;
-        if (TR && p.trace && blockIdx.x + blockIdx.y + blockIdx.z == 0 && (threadIdx.x & 127) == 0 && it < 64)
+        if (TR && p.trace && w == 0 && (threadIdx.x & 127) == 0 && it < 64)
           tr = p.trace + ((size_t)t * 64 + it) * 16;
-        mbar_wait(s_full(t), it & 1);
+        mbar_wait(s_full(t), pc & 1);
+        ++pc;
         tc_fence_after();
         if (TR && tr) tr[0] = clock64();
         uint32_t su[128];
@@ -357,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         tmem_wait_ld();
         float* s = reinterpret_cast<float*>(su);
         if (TR && tr) tr[1] = clock64();
-        if (it + 1 < n) fetch_scales(it + 1);
+        if (it + 1 < n) { jt_next = tile_of(im, it + 1); fetch_scales(jt_next); }
         if constexpr (I8) {
           // exact widening (|s| <= 2^21).  Measured alternatives (profiles/r01d_int8_notes.txt): I2FP here = 3553 clk per
           // KV step pair, integer add onto the bits of 1.5 * 2^23 + packed subtract = 3750; the bf16 kernel = 2757.  The
@@ -491,7 +552,8 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       }
       // ---------------------------------------------------------------- epilogue: O / l, L = m + log2(l)
       if (n > 0) {
-        mbar_wait(o_full(t), 0);
+        mbar_wait(o_full(t), qc & 1);
+        ++qc;
         tc_fence_after();
       }
       float inv = (l > 0.f ? 1.f / l : 0.f) * ((I8 && !v_blocks) ? p.vs1 : 1.f);
@@ -506,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       const bool tma_out = p.o_tma && !acc_mode && !p.debug_skip_store;
       if (tma_out) {
         // the staging area reuses the operand memory: wait until the other tile has retired its last MMA too
-        if (n > 0 && nt == 2) { mbar_wait(o_full(t ^ 1), 0); tc_fence_after(); }
+        if (n > 0 && nt == 2) { mbar_wait(o_full(t ^ 1), 0); tc_fence_after(); }      // (o_tma is off in persistent mode)
       }
       if (acc_mode && live) {
         const float l_old = p.lse[lrow];
@@ -520,15 +582,22 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         }
       }
 #pragma unroll
-      for (int ch = 0; ch < D / 32; ++ch) {
-        uint32_t ou[32];
-        if (n > 0) {
-          tmem_ld_x32(tO + ch * 32, ou);
-          tmem_wait_ld();
-        } else {
+      uint32_t oall[D];
+      if (n > 0) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) ou[i] = 0u;
-        }
+        for (int ch = 0; ch < D / 32; ++ch) tmem_ld_x32(tO + ch * 32, oall + ch * 32);
+        tmem_wait_ld();
+        // O has left TMEM: the MMA warp may overwrite it with the first P V of this CTA's next item
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty(t));
+      } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) oall[i] = 0u;
+      }
+#pragma unroll
+      for (int ch = 0; ch < D / 32; ++ch) {
+        const uint32_t* ou = oall + ch * 32;
         if (tma_out) {
           // 32 columns of this row -> one 128-byte line of the swizzled staging chunk (16-byte unit j lands at j ^ (row & 7):
           // the layout the fp32 output tensor map expects, and conflict-free for the 32 rows of a warp)
@@ -584,6 +653,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       }
       if (live && p.lse) p.lse[lrow] = l_out;
     }
+    }   // items
   }
   else {
     reg_dealloc<40>();      // idle warp of the third warpgroup (setmaxnreg is warpgroup-wide)
@@ -591,6 +661,61 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
+// ---- tile skipping under an external mask (north_star item 3): a two-kernel pre-pass reads the mask once and leaves, per
+// (mask batch, mask head, query block of 256 rows), the compacted list of KV tiles that hold at least one visible element
+// (bool: non-zero byte; additive: value > -inf) inside the block's causal / window range.
+struct MaskTileParams {
+  const void* mask;
+  int kind, scalar;
+  long long sb, sh, sq;
+  int Sq, Skv, causal, window, nqb, nkt, MH;
+  int* tiles;
+  int* counts;
+};
+
+// one CTA per (KV tile, query block, mask batch x head): flag = the tile lies in the causal / window range of the block and
+// holds at least one visible element.  Warp = 32 rows, lane = column (4 coalesced loads per row), all loads independent.
+__global__ void __launch_bounds__(256) mask_flags_kernel(const MaskTileParams q, uint8_t* __restrict__ flags) {
+  const int j = blockIdx.x, qb = blockIdx.y, mbh = blockIdx.z;
+  const int mb = mbh / q.MH, mh = mbh % q.MH;
+  const int r0 = qb * 256, rows = min(256, q.Sq - r0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int klo, khi;
+  visible_key_range(q.causal, q.window, q.Skv, r0, min(r0 + 256, q.Sq), klo, khi);
+  const int j_lo = klo >> 7, j_hi = khi > klo ? (khi + 127) >> 7 : j_lo;
+  int any = 0;
+  if (j >= j_lo && j < j_hi) {
+    const int c0 = j * 128, ncol = min(128, q.Skv - c0);
+    const int nrows = q.sq ? rows : 1;                     // a mask broadcast over the rows: one row decides
+    for (int rr = warp; rr < nrows; rr += 8) {
+      const long long off = (long long)mb * q.sb + (long long)mh * q.sh + (long long)(r0 + rr) * q.sq + c0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = lane + 32 * k;
+        if (c < ncol) {
+          if (q.kind == kMaskBool) any |= reinterpret_cast<const uint8_t*>(q.mask)[off + c] != 0;
+          else if (q.scalar == kMaskF32) any |= reinterpret_cast<const float*>(q.mask)[off + c] > -CUDART_INF_F;
+          else if (q.scalar == kMaskBF16) any |= __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(q.mask)[off + c] << 16) > -CUDART_INF_F;
+          else any |= __half2float(reinterpret_cast<const __half*>(q.mask)[off + c]) > -CUDART_INF_F;
+        }
+      }
+    }
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) flags[((size_t)mbh * q.nqb + qb) * q.nkt + j] = any ? 1 : 0;
+}
+
+// one thread per list: compacts the flagged tile indices in ascending order
+__global__ void mask_compact_kernel(const uint8_t* __restrict__ flags, int* __restrict__ tiles, int* __restrict__ counts,
+                                    int lists, int nkt) {
+  const int lid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lid >= lists) return;
+  int cnt = 0;
+  for (int j = 0; j < nkt; ++j)
+    if (flags[(size_t)lid * nkt + j]) tiles[(size_t)lid * nkt + cnt++] = j;
+  counts[lid] = cnt;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -690,8 +815,35 @@ cudaError_t launch(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
 
 }  // namespace
 
-cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm, int D, int mode, cudaStream_t st, int B) {
-  dim3 grid((prm.Sq + 255) / 256, prm.H, B);
+namespace {
+int sm_count() {
+  static int v = 0;
+  if (!v) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+  }
+  return v;
+}
+int persist_setting() {
+  static int v = -1;
+  // measured (profiles/r01f_persist_notes.txt): at the 1 kW power cap the persistent grid does not beat one CTA per item
+  // with the TMA-store epilogue (FLUX 0.2199 vs 0.2161 ms), so it is opt-in
+  if (v < 0) { const char* e = getenv("MFA_FWD_PERSIST"); v = e ? atoi(e) : 0; }
+  return v;
+}
+}  // namespace
+
+cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm_in, int D, int mode, cudaStream_t st, int B) {
+  FwdTcParams prm = prm_in;
+  prm.nbatch = B;
+  const long long items = (long long)((prm.Sq + 255) / 256) * prm.H * B;
+  if (items <= 0 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
+  // Persistent grid (one CTA per SM striding over the items) when every item costs the same -- no causal / window
+  // imbalance that the hardware's dynamic CTA dispatch handles better -- and there is more than one item per SM.
+  const bool persist = persist_setting() && !prm.causal && prm.window < 0 && items > sm_count() && !prm.trace;
+  if (persist) prm.o_tma = 0;                    // the staging tile of the TMA-store epilogue aliases the operand ring
+  dim3 grid((unsigned)(persist ? sm_count() : items), 1, 1);
   if (mode == kFwdI8) return D == 128 ? launch<128, kFwdI8>(prm, grid, st) : cudaErrorInvalidValue;
   if (D == 128) return mode == kFwdBF16 ? launch<128, kFwdBF16>(prm, grid, st) : launch<128, kFwdF16>(prm, grid, st);
   if (D == 64) return mode == kFwdBF16 ? launch<64, kFwdBF16>(prm, grid, st) : launch<64, kFwdF16>(prm, grid, st);
@@ -709,6 +861,43 @@ void fwd_tc_set_mask(FwdTcParams& prm, const AttnParams& p) {
   if (p.mask_kind == kMaskNone || !p.mask) return;
   prm.mask = p.mask; prm.mask_kind = p.mask_kind; prm.mask_scalar = p.mask_scalar;
   prm.mask_sb = p.mask_sb; prm.mask_sh = p.mask_sh; prm.mask_sq = p.mask_sq;
+}
+
+namespace {
+struct MaskLists { long long lists; int nqb, nkt, MB, MH; };
+MaskLists mask_lists(const AttnParams& p) {
+  MaskLists m;
+  m.nqb = (p.Sq + 255) / 256; m.nkt = (p.Skv + 127) / 128;
+  m.MB = p.mask_sb ? p.B : 1; m.MH = p.mask_sh ? p.H : 1;
+  m.lists = (long long)m.MB * m.MH * m.nqb;
+  return m;
+}
+}  // namespace
+
+size_t fwd_tc_mask_scratch_bytes(const AttnParams& p) {
+  if (p.mask_kind == kMaskNone || !p.mask || getenv("MFA_DISABLE_MASK_SKIP")) return 0;
+  const MaskLists m = mask_lists(p);
+  return (size_t)m.lists * (m.nkt + 1) * sizeof(int) + (size_t)m.lists * m.nkt + 16;      // counts, lists, flags
+}
+
+// Builds the visible-tile lists into p.mask_tile_scratch (when given) and points the kernel parameters at them.
+cudaError_t fwd_tc_build_mask_tiles(FwdTcParams& prm, const AttnParams& p, cudaStream_t st) {
+  prm.mtiles = nullptr; prm.mcounts = nullptr; prm.m_nkt = 0;
+  if (!prm.mask || !p.mask_tile_scratch || fwd_tc_mask_scratch_bytes(p) == 0) return cudaSuccess;
+  const MaskLists m = mask_lists(p);
+  if (m.lists > 0x3fffffffLL || m.MB * (long long)m.MH > 65535 || m.nqb > 65535) return cudaSuccess;   // visit every tile
+  MaskTileParams q;
+  q.mask = p.mask; q.kind = p.mask_kind; q.scalar = p.mask_scalar;
+  q.sb = p.mask_sb; q.sh = p.mask_sh; q.sq = p.mask_sq;
+  q.Sq = p.Sq; q.Skv = p.Skv; q.causal = p.causal; q.window = p.window; q.nqb = m.nqb; q.nkt = m.nkt; q.MH = m.MH;
+  q.counts = p.mask_tile_scratch;
+  q.tiles = p.mask_tile_scratch + m.lists;
+  uint8_t* flags = reinterpret_cast<uint8_t*>(q.tiles + m.lists * m.nkt);
+  mask_flags_kernel<<<dim3((unsigned)m.nkt, (unsigned)m.nqb, (unsigned)(m.MB * m.MH)), 256, 0, st>>>(q, flags);
+  mask_compact_kernel<<<(unsigned)((m.lists + 127) / 128), 128, 0, st>>>(flags, q.tiles, q.counts, (int)m.lists, m.nkt);
+  g_launch_count += 2;
+  prm.mtiles = q.tiles; prm.mcounts = q.counts; prm.m_nkt = m.nkt;
+  return cudaGetLastError();
 }
 
 // fp32 O goes out through TMA bulk stores from a swizzled staging tile (coalesced, asynchronous) when the view allows a
@@ -753,6 +942,7 @@ cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st) {
   prm.debug_skip_store = getenv("MFA_DEBUG_SKIP_STORE") ? 1 : 0;       // timing experiment only: O / L are not written
   fwd_tc_set_out_map(prm, p);
   fwd_tc_set_mask(prm, p);
+  if (cudaError_t me = fwd_tc_build_mask_tiles(prm, p, st); me != cudaSuccess) return me;
   const bool bf = p.in_dtype == kBF16;
   cudaError_t e = launch_fwd_tc_kernel(prm, p.D, bf ? kFwdBF16 : kFwdF16, st, p.B);
   if (p.D == 128) g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d128_mask" : "fwd_tc_fp16_d128_mask") : (bf ? "fwd_tc_bf16_d128" : "fwd_tc_fp16_d128");

@@ -158,6 +158,7 @@ cudaError_t launch_fwd_tcq(const AttnParams& p, void* scratch, cudaStream_t st) 
   prm.causal = p.causal; prm.window = p.window;
   prm.pingpong = fwd_tc_pingpong();
   fwd_tc_set_mask(prm, p);
+  if ((e = fwd_tc_build_mask_tiles(prm, p, st)) != cudaSuccess) return e;
   fwd_tc_set_out_map(prm, p);
   auto setq = [](const QuantView& q, int S, const float*& arr, float& one, int& br, int& nb, int& stride) {
     arr = q.scales; one = q.scale;

@@ -51,6 +51,9 @@ struct AttnParams {
   const void* mask;
   int mask_kind, mask_scalar;
   int64_t mask_sb, mask_sh, mask_sq, mask_sk;
+  // tensor-core forward: device scratch for the per-query-block lists of KV tiles the mask leaves visible (tile skipping);
+  // null = every tile in the causal / window range is visited.  Size: fwd_tc_mask_scratch_bytes(p).
+  int* mask_tile_scratch;
   int in_dtype, o_dtype, do_dtype;
   QuantView qq, qk, qv;     // used when in_dtype is kI8 / kI4
 };
@@ -79,6 +82,7 @@ cudaError_t launch_bwd_dkv_only(const AttnParams& p, cudaStream_t st);      // d
 
 // tcgen05 forward (bf16/fp16, D in {64,128}); returns cudaErrorNotSupported when the problem is not eligible.
 bool fwd_tc_eligible(const AttnParams& p);
+size_t fwd_tc_mask_scratch_bytes(const AttnParams& p);     // 0 when there is no external mask
 cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st);
 
 // tcgen05 backward (bf16/fp16, D in {64,128}); needs p.dterm filled by launch_dterm first.

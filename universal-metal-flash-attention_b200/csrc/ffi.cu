@@ -56,7 +56,7 @@ struct Context {
   double last_latency = 0.0;
   int refs = 0;
   std::mutex mu;
-  enum { kMask, kLse, kDterm, kQCodes, kKCodes, kVCodes, kQScales, kKScales, kVScales, kTmpO, kQTmp, kNumScratch };
+  enum { kMask, kLse, kDterm, kQCodes, kKCodes, kVCodes, kQScales, kKScales, kVScales, kTmpO, kQTmp, kMaskTiles, kNumScratch };
   Scratch scratch[kNumScratch];
   std::vector<float> row_scales[3];
   const char* last_kernel = "none";
@@ -364,6 +364,8 @@ mfa_error_t forward_core(Context* ctx, const FwdArgs& a) {
   mfa_error_t me = setup_mask(ctx, st, a.mask, p);
   if (me != MFA_SUCCESS) return me;
 
+  if (const size_t mb = fwd_tc_mask_scratch_bytes(p))
+    p.mask_tile_scratch = reinterpret_cast<int*>(ctx->scratch[Context::kMaskTiles].get(mb));     // null = no tile skipping
   Timer tm(ctx, st, !a.async);
   if (fwd_tc_eligible(p)) {
     e = launch_fwd_tc(p, st);
@@ -572,6 +574,8 @@ mfa_error_t qforward_core(Context* ctx, const QFwdArgs& a) {
     p.mask = a.mask_buf->dev; p.mask_kind = kMaskAdditive; p.mask_scalar = kMaskF32;
     p.mask_sk = 1; p.mask_sq = a.Skv; p.mask_sh = (int64_t)a.Sq * a.Skv; p.mask_sb = (int64_t)a.H * a.Sq * a.Skv;
   }
+  if (const size_t mb = fwd_tc_mask_scratch_bytes(p))
+    p.mask_tile_scratch = reinterpret_cast<int*>(ctx->scratch[Context::kMaskTiles].get(mb));
   if (fwd_tcq_eligible(p)) {
     void* tmp = ctx->scratch[Context::kQTmp].get(fwd_tcq_scratch_bytes(p));
     if (!tmp) return MFA_ERROR_MEMORY_ALLOCATION;

@@ -21,6 +21,7 @@ struct FwdTcParams {
   int accumulate;          // merge this launch's partial (O, L) with what lse / o already hold (fp32 O, lse required)
   int o_dtype;
   int H, Hkv, Sq, Skv;
+  int nbatch;              // set by launch_fwd_tc_kernel (work items = query blocks x H x nbatch)
   float c;                 // softmax_scale * log2(e)
   int causal, window;
   // kFwdI8 only: symmetric scales of the int8 codes (value = code * scale)
@@ -34,6 +35,11 @@ struct FwdTcParams {
   const void* mask;
   int mask_kind, mask_scalar;
   long long mask_sb, mask_sh, mask_sq;
+  // tile skipping under an external mask: per (mask batch, mask head, query block) a compacted list of the KV tiles that
+  // hold at least one visible element (built by mask_tiles_kernel right before the launch), or null
+  const int* mtiles;       // [lists][m_nkt]
+  const int* mcounts;      // [lists]
+  int m_nkt;
   int debug_skip_store;                                 // MFA_DEBUG_SKIP_STORE: epilogue writes nothing (timing experiments)
   int pingpong;                                         // exp2 turn-taking between the two tiles (MFA_FWD_PINGPONG, default 1)
   unsigned long long* trace;                            // debug timeline buffer (MFA_FWD_TRACE), normally null
@@ -42,6 +48,7 @@ struct FwdTcParams {
 int fwd_tc_pingpong();
 bool fwd_tc_mask_ok(const AttnParams& p);
 void fwd_tc_set_mask(FwdTcParams& prm, const AttnParams& p);
+cudaError_t fwd_tc_build_mask_tiles(FwdTcParams& prm, const AttnParams& p, cudaStream_t st);
 void fwd_tc_set_out_map(FwdTcParams& prm, const AttnParams& p);
 
 // grid = (ceil(Sq / 256), H, B).  mode kFwdI8 needs D == 128 (Q / K tiles are int8, V tiles bf16).
