@@ -85,3 +85,71 @@ def test_bwd_tc_long_window_property(ctx):
     restricted to one head (oracle on one head only to keep the CPU cost bounded)."""
     errs = run_case(ctx, 1, 1, 2048, 2048, 128, "bf16", causal=True, window=512, seed=5)
     assert max(errs.values()) < 2e-2
+
+
+# ---- external masks in the tensor-core backward -----------------------------------------------------------------------
+def _mask_for(kind, rng, B, H, Sq, Skv):
+    kw = {}
+    if kind == "bool_bcast_heads":
+        m = rng.random((B, 1, Sq, Skv)) > 0.4
+        m[..., 0] = True
+        return m, m, kw
+    if kind == "bool_key_padding":
+        m = np.ones((B, 1, 1, Skv), dtype=bool)
+        for b in range(B):
+            m[b, 0, 0, Skv - 5 - 13 * (b + 1):] = False
+        return m, m, kw
+    if kind == "bool_rows_empty":
+        m = rng.random((B, H, Sq, Skv)) > 0.5
+        m[0, H - 1, 3, :] = False
+        return m, m, kw
+    base = (1.5 * rng.standard_normal((B, H, Sq, Skv))).astype(np.float32)
+    if kind == "add_neg_inf":
+        base[rng.random(base.shape) > 0.7] = -np.inf
+        base[..., 0] = 0.25
+        return base, base, kw
+    if kind == "add_fp16":
+        m = base.astype(np.float16)
+        return m, m.astype(np.float32), kw
+    if kind == "add_bf16":
+        om, bits = O.round_bf16(base)
+        kw["mask_precision"] = "bf16"
+        return bits, om, kw
+    return base, base, kw
+
+
+@pytest.mark.parametrize("kind", ["bool_bcast_heads", "bool_key_padding", "bool_rows_empty", "add_fp32", "add_fp16", "add_bf16", "add_neg_inf"])
+@pytest.mark.parametrize("shape", [(2, 2, 256, 384, 128, "bf16"), (1, 3, 300, 333, 64, "fp16")])
+def test_bwd_tc_external_masks(ctx, kind, shape):
+    import umfa
+    B, H, Sq, Skv, D, dtype = shape
+    rng = np.random.default_rng(31)
+    q, k, v, g = (rng.standard_normal(s).astype(np.float32) for s in
+                  ((B, H, Sq, D), (B, H, Skv, D), (B, H, Skv, D), (B, H, Sq, D)))
+    (qa, qf), (ka, kf), (va, vf), (ga, gf) = (to_dtype(x, dtype) for x in (q, k, v, g))
+    m, om, kw = _mask_for(kind, rng, B, H, Sq, Skv)
+    o_ref, l_ref = O.attention_forward(qf, kf, vf, mask=om)
+    dq, dk, dv, dt = umfa.flash_attention_backward(ctx, ga, qa, ka, va, o_ref, l_ref, input_precision=dtype, attn_mask=m, **kw)
+    assert ctx.last_kernel.startswith("bwd_tc_") and ctx.last_kernel.endswith("_mask"), ctx.last_kernel
+    rq, rk, rv, rt = O.attention_backward(qf, kf, vf, gf, mask=om)
+    errs = {}
+    for name, got, ref in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+        assert np.isfinite(got).all(), name
+        errs[name] = rel_max(got, ref)
+    assert max(errs.values()) < 2e-2, errs
+
+
+def test_bwd_tc_mask_with_causal_gqa_free(ctx):
+    """mask + causal together, gradients against the oracle"""
+    import umfa
+    B, H, S, D = 1, 2, 512, 128
+    rng = np.random.default_rng(32)
+    q, k, v, g = (rng.standard_normal((B, H, S, D)).astype(np.float32) for _ in range(4))
+    (qa, qf), (ka, kf), (va, vf), (ga, gf) = (to_dtype(x, "bf16") for x in (q, k, v, g))
+    m = rng.random((S, S)) > 0.3
+    m[:, 0] = True
+    o_ref, l_ref = O.attention_forward(qf, kf, vf, mask=m, causal=True)
+    dq, dk, dv, _ = umfa.flash_attention_backward(ctx, ga, qa, ka, va, o_ref, l_ref, input_precision="bf16", attn_mask=m, causal=True)
+    assert ctx.last_kernel.endswith("_mask")
+    rq, rk, rv, _ = O.attention_backward(qf, kf, vf, gf, mask=m, causal=True)
+    assert max(rel_max(dq, rq), rel_max(dk, rk), rel_max(dv, rv)) < 2e-2

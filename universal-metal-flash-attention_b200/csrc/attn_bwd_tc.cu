@@ -22,6 +22,7 @@
 // Tiles fully hidden by the causal / sliding-window rule are skipped before they are loaded.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 #include "common.h"
@@ -47,7 +48,34 @@ struct BwdTcParams {
   int H, Hkv, Sq, Skv;
   float c, scale;
   int causal, window;
+  // external mask (MASKED kernels): bool bytes (non-zero = attend) or additive values, element strides over [B,H,Sq,Skv]
+  // with broadcast dims = 0 and unit key stride; P = exp2(S c + mask log2 e - L)
+  const void* mask;
+  int mask_kind, mask_scalar;
+  long long mask_sb, mask_sh, mask_sq;
 };
+
+// 32 mask terms in log2 units (-inf = hidden) for elements off0 + i * stride, i < nvalid (the rest: 0, they belong to dead
+// rows / columns whose P is zeroed elsewhere).  The type switch sits outside the unrolled loops.
+__device__ __forceinline__ void mask_terms32(const BwdTcParams& p, long long off0, long long stride, int nvalid, float* mt) {
+  if (p.mask_kind == kMaskBool) {
+    const uint8_t* m = reinterpret_cast<const uint8_t*>(p.mask) + off0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mt[i] = (i < nvalid && __ldg(m + i * stride) == 0) ? -CUDART_INF_F : 0.f;
+  } else if (p.mask_scalar == kMaskF32) {
+    const float* m = reinterpret_cast<const float*>(p.mask) + off0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mt[i] = i < nvalid ? __ldg(m + i * stride) * kLog2e : 0.f;
+  } else if (p.mask_scalar == kMaskBF16) {
+    const uint16_t* m = reinterpret_cast<const uint16_t*>(p.mask) + off0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mt[i] = i < nvalid ? __uint_as_float((uint32_t)__ldg(m + i * stride) << 16) * kLog2e : 0.f;
+  } else {
+    const __half* m = reinterpret_cast<const __half*>(p.mask) + off0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mt[i] = i < nvalid ? __half2float(m[i * stride]) * kLog2e : 0.f;
+  }
+}
 
 template <int D>
 struct BCfg {
@@ -66,7 +94,7 @@ __device__ __forceinline__ void load_tile_4d(uint32_t dst, const CUtensorMap* m,
 }
 
 // ================================================================================================ dK / dV
-template <int D, bool BF16>
+template <int D, bool BF16, bool MASKED = false>
 __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_constant__ BwdTcParams p) {
   using C = BCfg<D>;
   constexpr int TILE = C::kTile, CHB = C::kChunkBytes;
@@ -243,14 +271,21 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
       for (int ch = 0; ch < 2; ++ch) {
         uint32_t su[32];
         tmem_ld_x32(tS + ch * 32, su);
+        float mt[32];
+        if constexpr (MASKED) {
+          // mask[q][key] for the 32 queries of this chunk: consecutive lanes = consecutive keys, so every load is coalesced
+          const int head = hk * group + it / nq, qa = q0 + ch * 32;
+          const long long off = (long long)b * p.mask_sb + (long long)head * p.mask_sh + (long long)qa * p.mask_sq + min(key, p.Skv - 1);
+          mask_terms32(p, off, p.mask_sq, key < p.Skv ? min(32, p.Sq - qa) : 0, mt);
+        }
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 L4 = *reinterpret_cast<const float4*>(sL + ch * 32 + i);
-          pv[ch * 32 + i + 0] = ex2(fmaf(__uint_as_float(su[i + 0]), c, -L4.x));
-          pv[ch * 32 + i + 1] = ex2(fmaf(__uint_as_float(su[i + 1]), c, -L4.y));
-          pv[ch * 32 + i + 2] = ex2(fmaf(__uint_as_float(su[i + 2]), c, -L4.z));
-          pv[ch * 32 + i + 3] = ex2(fmaf(__uint_as_float(su[i + 3]), c, -L4.w));
+          const float Ls[4] = {L4.x, L4.y, L4.z, L4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            pv[ch * 32 + i + k] = ex2(fmaf(__uint_as_float(su[i + k]), c, MASKED ? mt[i + k] - Ls[k] : -Ls[k]));
         }
         if (any_mask) {
 #pragma unroll
@@ -329,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
 }
 
 // ================================================================================================ dQ
-template <int D, bool BF16>
+template <int D, bool BF16, bool MASKED = false>
 __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_constant__ BwdTcParams p) {
   using C = BCfg<D>;
   constexpr int TILE = C::kTile, CHB = C::kChunkBytes;
@@ -471,9 +506,15 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
       for (int ch = 0; ch < 2; ++ch) {
         uint32_t su[32];
         tmem_ld_x32(tS + ch * 32, su);
+        float mt[32];
+        if constexpr (MASKED) {
+          const int ka = k0 + ch * 32;
+          const long long off = (long long)b * p.mask_sb + (long long)h * p.mask_sh + (long long)min(r, p.Sq - 1) * p.mask_sq + ka;
+          mask_terms32(p, off, 1, r < p.Sq ? min(32, p.Skv - ka) : 0, mt);
+        }
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) pv[ch * 32 + i] = ex2(fmaf(__uint_as_float(su[i]), c, -L));
+        for (int i = 0; i < 32; ++i) pv[ch * 32 + i] = ex2(fmaf(__uint_as_float(su[i]), c, MASKED ? mt[i] - L : -L));
         if (any_mask) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) pv[ch * 32 + i] = (ch * 32 + i < lo_i || ch * 32 + i > hi_i) ? 0.f : pv[ch * 32 + i];
@@ -539,25 +580,31 @@ cudaError_t ensure_smem(K kern, int bytes, bool& done) {
   return e;
 }
 
-template <int D, bool BF16>
-cudaError_t launch_bwd(const BwdTcParams& prm, int B, bool want_dq, bool want_dkv, cudaStream_t st) {
+template <int D, bool BF16, bool MASKED>
+cudaError_t launch_bwd_m(const BwdTcParams& prm, int B, bool want_dq, bool want_dkv, cudaStream_t st) {
   static bool a_set = false, b_set = false;
   cudaError_t e;
   if (want_dkv) {
-    if ((e = ensure_smem(bwd_dkv_tc_kernel<D, BF16>, BCfg<D>::kSmem, a_set)) != cudaSuccess) return e;
+    if ((e = ensure_smem(bwd_dkv_tc_kernel<D, BF16, MASKED>, BCfg<D>::kSmem, a_set)) != cudaSuccess) return e;
     dim3 grid((prm.Skv + 127) / 128, prm.Hkv, B);
-    bwd_dkv_tc_kernel<D, BF16><<<grid, kThreads, BCfg<D>::kSmem, st>>>(prm);
+    bwd_dkv_tc_kernel<D, BF16, MASKED><<<grid, kThreads, BCfg<D>::kSmem, st>>>(prm);
     ++g_launch_count;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   if (want_dq) {
-    if ((e = ensure_smem(bwd_dq_tc_kernel<D, BF16>, BCfg<D>::kSmem, b_set)) != cudaSuccess) return e;
+    if ((e = ensure_smem(bwd_dq_tc_kernel<D, BF16, MASKED>, BCfg<D>::kSmem, b_set)) != cudaSuccess) return e;
     dim3 grid((prm.Sq + 127) / 128, prm.H, B);
-    bwd_dq_tc_kernel<D, BF16><<<grid, kThreads, BCfg<D>::kSmem, st>>>(prm);
+    bwd_dq_tc_kernel<D, BF16, MASKED><<<grid, kThreads, BCfg<D>::kSmem, st>>>(prm);
     ++g_launch_count;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   return cudaSuccess;
+}
+
+template <int D, bool BF16>
+cudaError_t launch_bwd(const BwdTcParams& prm, int B, bool want_dq, bool want_dkv, cudaStream_t st) {
+  return prm.mask ? launch_bwd_m<D, BF16, true>(prm, B, want_dq, want_dkv, st)
+                  : launch_bwd_m<D, BF16, false>(prm, B, want_dq, want_dkv, st);
 }
 
 }  // namespace
@@ -567,7 +614,7 @@ bool bwd_tc_eligible(const AttnParams& p) {
   if (p.in_dtype != kBF16 && p.in_dtype != kF16) return false;
   if (p.do_dtype != p.in_dtype) return false;
   if (p.D != 64 && p.D != 128) return false;
-  if (p.mask_kind != kMaskNone) return false;
+  if (p.mask_kind != kMaskNone && p.mask && (p.mask_sk != 1 || getenv("MFA_DISABLE_TC_MASK"))) return false;
   if (p.Sq <= 0 || p.Skv <= 0 || p.B <= 0 || p.H <= 0 || p.Hkv <= 0 || p.H % p.Hkv) return false;
   if (p.B > 65535 || p.H > 65535) return false;
   if (!tc::view_ok(p.q, p.H, p.B) || !tc::view_ok(p.k, p.Hkv, p.B) || !tc::view_ok(p.v, p.Hkv, p.B) ||
@@ -592,12 +639,18 @@ cudaError_t launch_bwd_tc(const AttnParams& p, cudaStream_t st) {
   prm.H = p.H; prm.Hkv = p.Hkv; prm.Sq = p.Sq; prm.Skv = p.Skv;
   prm.c = p.scale * kLog2e; prm.scale = p.scale;
   prm.causal = p.causal; prm.window = p.window;
+  prm.mask = nullptr; prm.mask_kind = kMaskNone; prm.mask_scalar = 0; prm.mask_sb = prm.mask_sh = prm.mask_sq = 0;
+  if (p.mask_kind != kMaskNone && p.mask) {
+    prm.mask = p.mask; prm.mask_kind = p.mask_kind; prm.mask_scalar = p.mask_scalar;
+    prm.mask_sb = p.mask_sb; prm.mask_sh = p.mask_sh; prm.mask_sq = p.mask_sq;
+  }
   const bool want_dq = p.dq != nullptr, want_dkv = p.dk != nullptr && p.dv != nullptr;
   const bool bf = p.in_dtype == kBF16;
   cudaError_t e;
   if (p.D == 128) e = bf ? launch_bwd<128, true>(prm, p.B, want_dq, want_dkv, st) : launch_bwd<128, false>(prm, p.B, want_dq, want_dkv, st);
   else e = bf ? launch_bwd<64, true>(prm, p.B, want_dq, want_dkv, st) : launch_bwd<64, false>(prm, p.B, want_dq, want_dkv, st);
-  g_last_kernel = p.D == 128 ? (bf ? "bwd_tc_bf16_d128" : "bwd_tc_fp16_d128") : (bf ? "bwd_tc_bf16_d64" : "bwd_tc_fp16_d64");
+  if (prm.mask) g_last_kernel = p.D == 128 ? (bf ? "bwd_tc_bf16_d128_mask" : "bwd_tc_fp16_d128_mask") : (bf ? "bwd_tc_bf16_d64_mask" : "bwd_tc_fp16_d64_mask");
+  else g_last_kernel = p.D == 128 ? (bf ? "bwd_tc_bf16_d128" : "bwd_tc_fp16_d128") : (bf ? "bwd_tc_bf16_d64" : "bwd_tc_fp16_d64");
   return e;
 }
 
