@@ -268,7 +268,8 @@ def test_tc_mask_tile_skipping_matches_oracle(ctx, kind, monkeypatch):
     monkeypatch.setenv("MFA_DISABLE_MASK_SKIP", "1")
     out2, lse2 = umfa.flash_attention_forward(ctx, qa, ka, va, input_precision="bf16", output_precision="fp32", layout="bhsd",
                                               attn_mask=m, return_lse=True)
-    assert rel_max(out, out2) < 1e-6 and np.array_equal(np.isfinite(lse), np.isfinite(lse2))
+    # (tiles on which the mask is a no-op take the polynomial exp2 share when lists exist, plain ex2 otherwise: ~1e-3)
+    assert rel_max(out, out2) < 5e-3 and np.array_equal(np.isfinite(lse), np.isfinite(lse2))
 
 
 def test_tc_mask_tile_skipping_saves_time(ctx, monkeypatch):

@@ -50,6 +50,7 @@ using namespace ptx;
 constexpr int kThreads = 384;           // warpgroups: softmax 0, softmax 1, {MMA 0, TMA, MMA 1, idle}
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.f;     // log2 units
+constexpr int kTileNoMask = 1 << 30;          // flag bit in a visible-tile list entry
 constexpr int kParts = 4;                    // P hand-off granularity: 32 keys = 16 packed TMEM columns
 
 template <int D, int MODE>
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         load_qk(sQ, &p.tq, q_full(0), r0, h);
         ++qc[0];
         for (int it = 0; it < n; ++it) {
-          const int row = tile_of(im, it) * 128;
+          const int row = (tile_of(im, it) & (kTileNoMask - 1)) * 128;
           int s = kvi % NS;
           mbar_wait(kv_empty(s), ((kvi / NS) & 1) ^ 1);
           load_qk(sKV + s * STG, &p.tk, kv_full(s), row, hk);
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       int jt_next = n > 0 ? tile_of(im, 0) : 0;        // tile index of the coming step (read one step ahead)
       auto fetch_scales = [&](int jt) {
         if constexpr (I8) {
-          const int c0 = jt * 128;
+          const int c0 = (jt & (kTileNoMask - 1)) * 128;
           if (ksp) {
             ksn0 = __ldg(ksp + min(c0 / p.kbr, p.nbk - 1));
             ksn1 = __ldg(ksp + min((c0 + 64) / p.kbr, p.nbk - 1));
@@ -392,7 +393,8 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       };
       if (n > 0) fetch_scales(jt_next);
       for (int it = 0; it < n; ++it) {
-        const int c0 = jt_next * 128;
+        const int c0 = (jt_next & (kTileNoMask - 1)) * 128;
+        const bool mask_noop = (jt_next & kTileNoMask) != 0;
         // multipliers of the two 64-key halves of this tile (int8: blocks are multiples of 64 keys)
         float a0 = qsc, a1 = qsc, lv0 = 0.f, lv1 = 0.f, iv0 = 1.f, iv1 = 1.f;
         if constexpr (I8) {
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           for (int i = 0; i < 128; ++i) s[i] = __int2float_rn((int)su[i]);
         }
         if (TR && tr) tr[15] = clock64();
-        if constexpr (MASKED) {
+        if (MASKED && !mask_noop) {
           const int rq = min(r, p.Sq - 1);
           const long long eoff = (long long)b * p.mask_sb + (long long)h * p.mask_sh + (long long)rq * p.mask_sq + c0;
           const int ncol = min(128, p.Skv - c0);
@@ -542,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           else named_bar_sync(3, 256);
         }
         if (TR && tr) tr[2] = clock64();
-        if (POLY > 0 && !any_mask) exp_phase<PBF16, POLY, TR>(s, a0, a1, nk0, nk1, tS, p_part(t, 0), lane, sum_lo, sum_hi, tr);
+        if (POLY > 0 && !any_mask && (!MASKED || mask_noop)) exp_phase<PBF16, POLY, TR>(s, a0, a1, nk0, nk1, tS, p_part(t, 0), lane, sum_lo, sum_hi, tr);
         else exp_phase<PBF16, 0, TR>(s, a0, a1, nk0, nk1, tS, p_part(t, 0), lane, sum_lo, sum_hi, tr);
         if (pingpong) {
           if (t == 0) named_bar_arrive(3, 256);
@@ -685,7 +687,7 @@ __global__ void __launch_bounds__(256) mask_flags_kernel(const MaskTileParams q,
   int klo, khi;
   visible_key_range(q.causal, q.window, q.Skv, r0, min(r0 + 256, q.Sq), klo, khi);
   const int j_lo = klo >> 7, j_hi = khi > klo ? (khi + 127) >> 7 : j_lo;
-  int any = 0;
+  int any = 0, all = 1;         // any element visible / every element a no-op (bool: set; additive: exactly 0)
   if (j >= j_lo && j < j_hi) {
     const int c0 = j * 128, ncol = min(128, q.Skv - c0);
     const int nrows = q.sq ? rows : 1;                     // a mask broadcast over the rows: one row decides
@@ -695,26 +697,31 @@ __global__ void __launch_bounds__(256) mask_flags_kernel(const MaskTileParams q,
       for (int k = 0; k < 4; ++k) {
         const int c = lane + 32 * k;
         if (c < ncol) {
-          if (q.kind == kMaskBool) any |= reinterpret_cast<const uint8_t*>(q.mask)[off + c] != 0;
-          else if (q.scalar == kMaskF32) any |= reinterpret_cast<const float*>(q.mask)[off + c] > -CUDART_INF_F;
-          else if (q.scalar == kMaskBF16) any |= __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(q.mask)[off + c] << 16) > -CUDART_INF_F;
-          else any |= __half2float(reinterpret_cast<const __half*>(q.mask)[off + c]) > -CUDART_INF_F;
+          float val;
+          if (q.kind == kMaskBool) val = reinterpret_cast<const uint8_t*>(q.mask)[off + c] != 0 ? 0.f : -CUDART_INF_F;
+          else if (q.scalar == kMaskF32) val = reinterpret_cast<const float*>(q.mask)[off + c];
+          else if (q.scalar == kMaskBF16) val = __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(q.mask)[off + c] << 16);
+          else val = __half2float(reinterpret_cast<const __half*>(q.mask)[off + c]);
+          any |= val > -CUDART_INF_F;
+          all &= val == 0.f;
         }
       }
     }
   }
   any = __syncthreads_or(any);
-  if (threadIdx.x == 0) flags[((size_t)mbh * q.nqb + qb) * q.nkt + j] = any ? 1 : 0;
+  all = __syncthreads_and(all);
+  if (threadIdx.x == 0) flags[((size_t)mbh * q.nqb + qb) * q.nkt + j] = any ? (all ? 2 : 1) : 0;
 }
 
-// one thread per list: compacts the flagged tile indices in ascending order
+// one thread per list: compacts the flagged tile indices in ascending order; kTileNoMask marks tiles on which the mask is a
+// no-op (all attend / all zero), so the attention kernel neither loads nor applies it there
 __global__ void mask_compact_kernel(const uint8_t* __restrict__ flags, int* __restrict__ tiles, int* __restrict__ counts,
                                     int lists, int nkt) {
   const int lid = blockIdx.x * blockDim.x + threadIdx.x;
   if (lid >= lists) return;
   int cnt = 0;
   for (int j = 0; j < nkt; ++j)
-    if (flags[(size_t)lid * nkt + j]) tiles[(size_t)lid * nkt + cnt++] = j;
+    if (const int f = flags[(size_t)lid * nkt + j]) tiles[(size_t)lid * nkt + cnt++] = j | (f == 2 ? kTileNoMask : 0);
   counts[lid] = cnt;
 }
 
@@ -784,10 +791,10 @@ cudaError_t launch_traced(FwdTcParams prm, dim3 grid, cudaStream_t st, const cha
   return e;
 }
 
-template <int D, int MODE>
-cudaError_t launch_masked(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
+template <int D, int MODE, int POLY>
+cudaError_t launch_masked_k(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = fwd_tc_kernel<D, MODE, 0, false, true>;
+  auto kern = fwd_tc_kernel<D, MODE, POLY, false, true>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D, MODE>::kSmem);
     if (e != cudaSuccess) return e;
@@ -795,6 +802,12 @@ cudaError_t launch_masked(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
   }
   kern<<<grid, kThreads, Cfg<D, MODE>::kSmem, st>>>(prm);
   return cudaGetLastError();
+}
+
+// masked kernels come in two exp2 flavours only: all MUFU, or the default polynomial share on tiles the mask leaves alone
+template <int D, int MODE>
+cudaError_t launch_masked(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
+  return poly_setting() > 0 ? launch_masked_k<D, MODE, 3>(prm, grid, st) : launch_masked_k<D, MODE, 0>(prm, grid, st);
 }
 
 template <int D, int MODE>
