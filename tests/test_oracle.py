@@ -178,3 +178,32 @@ def test_bf16_rounding_rne():
     t = torch.from_numpy(x).to(torch.bfloat16)
     assert (t.float().numpy() == y).all()
     assert (t.view(torch.int16).numpy().view(np.uint16) == bits).all()
+
+
+def test_slice_property_used_by_full_size_gpu_tests():
+    """tests/test_gpu_fullsize.py checks full BASELINE sizes on slices: a row's O / L / dQ from (row, visible key span),
+    a key's dK / dV from the queries that see it.  Here the oracle confirms the slices reproduce the full problem exactly."""
+    rng = np.random.default_rng(0)
+    B, H, N, D, W = 1, 2, 768, 32, 96
+    q, k, v, g = (rng.standard_normal((B, H, N, D)).astype(np.float32) for _ in range(4))
+    of, lf = O.attention_forward(q, k, v, causal=True, window=W)
+    dq, dk, dv, _ = O.attention_backward(q, k, v, g, causal=True, window=W)
+
+    def vis(rows, keys):
+        r, c = np.asarray(rows)[:, None], np.asarray(keys)[None, :]
+        return (c <= r) & (r <= c + W)
+    for r0 in (0, W - 20, 400, N - 48):
+        rows = np.arange(r0, r0 + 48)
+        keys = np.arange(max(0, r0 - W), r0 + 48)
+        m = vis(rows, keys)
+        o, l = O.attention_forward(q[:, :, rows], k[:, :, keys], v[:, :, keys], mask=m)
+        rq, _, _, _ = O.attention_backward(q[:, :, rows], k[:, :, keys], v[:, :, keys], g[:, :, rows], mask=m)
+        assert np.abs(o - of[:, :, rows]).max() < 1e-6 and np.abs(l - lf[:, :, rows]).max() < 1e-5
+        assert np.abs(rq - dq[:, :, rows]).max() < 1e-6
+    for j0 in (5, 300, N - 16):
+        kk = np.arange(j0, j0 + 16)
+        rows = np.arange(j0, min(N, j0 + 16 + W))
+        keys = np.arange(max(0, rows[0] - W), rows[-1] + 1)
+        _, rk, rv, _ = O.attention_backward(q[:, :, rows], k[:, :, keys], v[:, :, keys], g[:, :, rows], mask=vis(rows, keys))
+        off = kk - keys[0]
+        assert np.abs(rk[:, :, off] - dk[:, :, kk]).max() < 1e-6 and np.abs(rv[:, :, off] - dv[:, :, kk]).max() < 1e-6
