@@ -42,6 +42,10 @@ WORKLOADS = {
                         label="FLUX shape, causal"),
     "long_window": dict(B=1, H=32, Sq=32768, Skv=32768, D=128, causal=True, window=4096, dtype="bf16",
                         label="causal + sliding window 4096, bf16 B=1 H=32 N=32768 D=128 forward"),
+    "long_dense": dict(B=1, H=32, Sq=32768, Skv=32768, D=128, causal=False, window=-1, dtype="bf16",
+                       label="dense bf16 B=1 H=32 N=32768 D=128 forward (256 KV steps per CTA)"),
+    "long_causal": dict(B=1, H=32, Sq=32768, Skv=32768, D=128, causal=True, window=-1, dtype="bf16",
+                        label="causal bf16 B=1 H=32 N=32768 D=128 forward"),
     "small": dict(B=1, H=4, Sq=1024, Skv=1024, D=128, causal=False, window=-1, dtype="bf16", label="small"),
     # config 5: total sequence fixed, split over the ranks (strong scaling); K/V blocks travel over NVLink (umfa/ring.py)
     "ring128k": dict(B=1, H=32, Sq=131072, Skv=131072, D=128, causal=True, window=-1, dtype="bf16", ring=True,

@@ -98,3 +98,25 @@ def test_tcq_outlier_channels_block_scales_help(ctx):
 def test_tcq_bf16_inputs(ctx):
     err, cs, rl2 = run_case(ctx, 1, 2, 384, 384, "int8", 2, seed=6, in_prec="bf16")
     assert cs >= 0.99
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("kind", ["dense", "neg_inf_blocks"])
+def test_tcq_int8_with_additive_mask(ctx, mode, kind):
+    """mfa_quantized_forward_with_lse's fp32 additive mask [B,H,Sq,Skv] (MFABridge+Quantized.swift:227) on the int8
+    tensor-core kernel: mask read in place by the softmax warps, hidden KV tiles skipped."""
+    import umfa
+    B, H, Sq, Skv, D = 1, 2, 384, 640, 128
+    rng = np.random.default_rng(9)
+    q, k, v = (rng.standard_normal(s).astype(np.float32) for s in ((B, H, Sq, D), (B, H, Skv, D), (B, H, Skv, D)))
+    m = (1.5 * rng.standard_normal((B, H, Sq, Skv))).astype(np.float32)
+    if kind == "neg_inf_blocks":
+        m[:, :, :, 256:512] = -np.inf            # two whole KV tiles hidden from every row
+        m[:, :, 100:130, :64] = -np.inf
+    out, lse = umfa.runtime_quantized_attention(ctx, q, k, v, target_precision="int8", quant_mode=mode, mask=m)
+    assert ctx.last_kernel.startswith("fwd_tcq_"), ctx.last_kernel
+    qd, kd, vd = (fake_quant(x, 8, mode, D) for x in (q, k, v))
+    o_ref, l_ref = O.attention_forward(qd, kd, vd, mask=m)
+    assert np.isfinite(out).all()
+    assert float(np.abs(out - o_ref).max() / np.abs(o_ref).max()) < 2e-2
+    assert np.abs(lse - l_ref).max() < 2e-2
