@@ -148,7 +148,7 @@ __device__ __forceinline__ void exp_phase(const float* s, float a0, float a1, fl
 // so masked elements always get an exact zero weight).
 // MASKED: an external mask (bool or additive, SURVEY A4 with the PyTorch placement softmax(scale * QK^T + mask)) is read by
 // the softmax warps straight from global memory -- each thread owns one row, so it reads the 128 mask values of its row
-// and tile with 16-byte loads; no dense fp32 expansion pass like the reference's mfa_prepare_mask (MFABridge.swift:153-243).
+// and tile with 32-byte (one sector) loads; no dense fp32 expansion pass like the reference's mfa_prepare_mask (MFABridge.swift:153-243).
 template <int D, int MODE, int POLY, bool TR = false, bool MASKED = false>
 __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_constant__ FwdTcParams p) {
   using C = Cfg<D, MODE>;
@@ -436,14 +436,14 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           const int ncol = min(128, p.Skv - c0);
           if (p.mask_kind == kMaskBool) {
             const uint8_t* mp = reinterpret_cast<const uint8_t*>(p.mask) + eoff;
-            if (ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 15) == 0) {
+            if (ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 31) == 0) {
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(mp) + c);
-                const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+              for (int c = 0; c < 4; ++c) {                       // 32 bytes = one sector per request
+                uint32_t w[8];
+                ldg256(mp + 32 * c, w);
 #pragma unroll
-                for (int k = 0; k < 16; ++k)
-                  if (((w[k >> 2] >> (8 * (k & 3))) & 0xffu) == 0) s[16 * c + k] = -CUDART_INF_F;
+                for (int k = 0; k < 32; ++k)
+                  if (((w[k >> 2] >> (8 * (k & 3))) & 0xffu) == 0) s[32 * c + k] = -CUDART_INF_F;
               }
             } else {
 #pragma unroll
@@ -454,13 +454,14 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
             // additive: fold the scale now (s <- s a_h + mask log2 e), the multipliers become 1 for the rest of the step
             if (p.mask_scalar == kMaskF32) {
               const float* mp = reinterpret_cast<const float*>(p.mask) + eoff;
-              if (ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 15) == 0) {
+              if (ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 31) == 0) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                  const float4 w = __ldg(reinterpret_cast<const float4*>(mp) + c);
-                  const float ah = c < 16 ? a0 : a1;
-                  s[4 * c] = fmaf(s[4 * c], ah, w.x * kLog2e); s[4 * c + 1] = fmaf(s[4 * c + 1], ah, w.y * kLog2e);
-                  s[4 * c + 2] = fmaf(s[4 * c + 2], ah, w.z * kLog2e); s[4 * c + 3] = fmaf(s[4 * c + 3], ah, w.w * kLog2e);
+                for (int c = 0; c < 16; ++c) {                    // 32 bytes = one sector per request
+                  uint32_t w[8];
+                  ldg256(mp + 8 * c, w);
+                  const float ah = c < 8 ? a0 : a1;
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) s[8 * c + k] = fmaf(s[8 * c + k], ah, __uint_as_float(w[k]) * kLog2e);
                 }
               } else {
 #pragma unroll
@@ -473,16 +474,16 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
               auto widen = [&](uint32_t bits) {
                 return bf ? __uint_as_float(bits << 16) : __half2float(__ushort_as_half((unsigned short)bits));
               };
-              if (ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 15) == 0) {
+              if (ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 31) == 0) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                  const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(mp) + c);
-                  const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-                  const float ah = c < 8 ? a0 : a1;
+                for (int c = 0; c < 8; ++c) {                     // 32 bytes = one sector per request
+                  uint32_t w[8];
+                  ldg256(mp + 16 * c, w);
+                  const float ah = c < 4 ? a0 : a1;
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    s[8 * c + 2 * k] = fmaf(s[8 * c + 2 * k], ah, widen(w[k] & 0xffffu) * kLog2e);
-                    s[8 * c + 2 * k + 1] = fmaf(s[8 * c + 2 * k + 1], ah, widen(w[k] >> 16) * kLog2e);
+                  for (int k = 0; k < 8; ++k) {
+                    s[16 * c + 2 * k] = fmaf(s[16 * c + 2 * k], ah, widen(w[k] & 0xffffu) * kLog2e);
+                    s[16 * c + 2 * k + 1] = fmaf(s[16 * c + 2 * k + 1], ah, widen(w[k] >> 16) * kLog2e);
                   }
                 }
               } else {
@@ -691,6 +692,8 @@ __global__ void __launch_bounds__(256) mask_flags_kernel(const MaskTileParams q,
   if (j >= j_lo && j < j_hi) {
     const int c0 = j * 128, ncol = min(128, q.Skv - c0);
     const int nrows = q.sq ? rows : 1;                     // a mask broadcast over the rows: one row decides
+    // a warp stops as soon as its rows prove the tile "partial" (something visible and something that is not a no-op):
+    // a dense bias costs one row per warp, only uniform-looking tiles are read in full
     for (int rr = warp; rr < nrows; rr += 8) {
       const long long off = (long long)mb * q.sb + (long long)mh * q.sh + (long long)(r0 + rr) * q.sq + c0;
 #pragma unroll
@@ -706,6 +709,7 @@ __global__ void __launch_bounds__(256) mask_flags_kernel(const MaskTileParams q,
           all &= val == 0.f;
         }
       }
+      if (__any_sync(0xffffffffu, any) && !__all_sync(0xffffffffu, all)) break;
     }
   }
   any = __syncthreads_or(any);
