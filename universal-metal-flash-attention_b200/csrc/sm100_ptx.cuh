@@ -79,6 +79,17 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
                : "l"(p));
 }
 
+// 256-bit coherent global load / store (read-modify-write epilogues)
+__device__ __forceinline__ void ld_global_v8(const float* p, float* r) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_global_v8(float* p, const float* r) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]) : "memory");
+}
+
 // Named barriers (ids 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
