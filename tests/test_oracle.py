@@ -207,3 +207,25 @@ def test_slice_property_used_by_full_size_gpu_tests():
         _, rk, rv, _ = O.attention_backward(q[:, :, rows], k[:, :, keys], v[:, :, keys], g[:, :, rows], mask=vis(rows, keys))
         off = kk - keys[0]
         assert np.abs(rk[:, :, off] - dk[:, :, kk]).max() < 1e-6 and np.abs(rv[:, :, off] - dv[:, :, kk]).max() < 1e-6
+
+
+def test_division_free_code_rule_is_bit_exact():
+    """csrc/quant.cu quant_code_fast(): round(x * (1/scale)) with an exact-division fallback within 1e-4 of a half-integer
+    must give the reference's codes round(x / scale) (GEMMQuantization.swift:487-521) for every input, including values that
+    sit exactly on (or one ulp beside) the rounding boundaries.  Emulated here in IEEE fp32 with numpy."""
+    rng = np.random.default_rng(0)
+    half_away = lambda q: np.sign(q) * np.floor(np.abs(q) + np.float32(0.5))
+    for trial in range(12):
+        sc = np.float32(abs(rng.standard_normal()) * 10 ** rng.uniform(-4, 2) / 127)
+        x = (rng.standard_normal(300_000) * sc * 60).astype(np.float32)
+        edge = ((rng.integers(-130, 130, 50_000).astype(np.float32) + np.float32(0.5)) * sc).astype(np.float32)
+        x = np.concatenate([x, edge, np.nextafter(edge, np.float32(0)), np.nextafter(edge, np.float32(1e9))])
+        qd = (x / sc).astype(np.float32)
+        exact = np.clip(half_away(qd), -128, 127)
+        inv = (np.float32(1) / sc).astype(np.float32)
+        t = (x * inv).astype(np.float32)
+        fr = np.abs(t - np.trunc(t)).astype(np.float32)
+        r = np.trunc((t + np.copysign(np.float32(0.5), t)).astype(np.float32))
+        near = (np.abs(fr - np.float32(0.5)) < np.float32(1e-4)) | ~(np.abs(t) < 1024)
+        r = np.clip(np.where(near, half_away(qd), r), -128, 127)
+        assert np.array_equal(r, exact), trial
