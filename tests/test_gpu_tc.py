@@ -318,3 +318,19 @@ print("persistent ok")
     env = dict(os.environ, MFA_FWD_PERSIST="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "persistent ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 256, 256, 128), (2, 3, 300, 777, 128), (1, 2, 1000, 130, 64), (1, 1, 77, 515, 64)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_tc_fp16_output_tma_store(ctx, shape, causal):
+    """16-bit O (the reference adapter's fp16-in / fp16-out default) leaves through the swizzled staging tile + TMA bulk
+    stores, ragged row counts clipped by the tensor map; rows past Sq must stay untouched"""
+    import umfa
+    B, H, Sq, Skv, D = shape
+    rng = np.random.default_rng(Sq + D)
+    q, k, v = (rng.standard_normal(s).astype(np.float32).astype(np.float16) for s in ((B, H, Sq, D), (B, H, Skv, D), (B, H, Skv, D)))
+    out = umfa.flash_attention_forward(ctx, q, k, v, input_precision="fp16", output_precision="fp16", layout="bhsd", causal=causal)
+    assert out.dtype == np.float16 and ctx.last_kernel.startswith("fwd_tc_fp16")
+    ref, _ = O.attention_forward(q.astype(np.float32), k.astype(np.float32), v.astype(np.float32), causal=causal)
+    assert np.isfinite(out).all()
+    assert rel_max(out.astype(np.float32), ref) < 2e-2

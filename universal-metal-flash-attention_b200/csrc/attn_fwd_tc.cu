@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
 #pragma unroll
       for (int ch = 0; ch < D / 32; ++ch) {
         const uint32_t* ou = oall + ch * 32;
-        if (tma_out) {
+        if (tma_out && p.o_dtype == kF32) {
           // 32 columns of this row -> one 128-byte line of the swizzled staging chunk (16-byte unit j lands at j ^ (row & 7):
           // the layout the fp32 output tensor map expects, and conflict-free for the 32 rows of a warp)
           const uint32_t line = base + (uint32_t)(t * (D / 32) + ch) * (128u * 128u) + (uint32_t)row * 128u;
@@ -609,6 +609,21 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           for (int i = 0; i < 8; ++i)
             st_shared_v4(line + (uint32_t)((i ^ (row & 7)) << 4), __uint_as_float(ou[4 * i]) * inv, __uint_as_float(ou[4 * i + 1]) * inv,
                          __uint_as_float(ou[4 * i + 2]) * inv, __uint_as_float(ou[4 * i + 3]) * inv);
+        } else if (tma_out) {
+          // 16-bit O: a staging chunk is 64 columns wide (128 bytes per row); these 32 columns are half a line (4 units)
+          const uint32_t line = base + (uint32_t)(t * (D / 64) + (ch >> 1)) * (128u * 128u) + (uint32_t)row * 128u;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float a = __uint_as_float(ou[8 * i + 2 * k]) * inv, bb = __uint_as_float(ou[8 * i + 2 * k + 1]) * inv;
+              w[k] = p.o_dtype == kBF16 ? pack_bf16(a, bb) : pack_f16(a, bb);
+            }
+            const int unit = (ch & 1) * 4 + i;
+            st_shared_v4(line + (uint32_t)((unit ^ (row & 7)) << 4), __uint_as_float(w[0]), __uint_as_float(w[1]),
+                         __uint_as_float(w[2]), __uint_as_float(w[3]));
+          }
         } else if (live) {
           if (p.o_dtype == kF32) {
             float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.o) + orow + ch * 32);
@@ -657,9 +672,15 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         fence_proxy_async_smem();
         named_bar_sync(4 + t, 128);
         if ((threadIdx.x & 127) == 0) {
+          if (p.o_dtype == kF32) {
 #pragma unroll
-          for (int ch = 0; ch < D / 32; ++ch)
-            tma_store_4d(&p.to, base + (uint32_t)(t * (D / 32) + ch) * (128u * 128u), ch * 32, r0 + t * 128, h, b);
+            for (int ch = 0; ch < D / 32; ++ch)
+              tma_store_4d(&p.to, base + (uint32_t)(t * (D / 32) + ch) * (128u * 128u), ch * 32, r0 + t * 128, h, b);
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < D / 64; ++ch)
+              tma_store_4d(&p.to, base + (uint32_t)(t * (D / 64) + ch) * (128u * 128u), ch * 64, r0 + t * 128, h, b);
+          }
           bulk_commit();
           bulk_wait_read();           // the CTA may exit (and free its shared memory) once the TMA has read the tile
         }
@@ -927,13 +948,15 @@ cudaError_t fwd_tc_build_mask_tiles(FwdTcParams& prm, const AttnParams& p, cudaS
   return cudaGetLastError();
 }
 
-// fp32 O goes out through TMA bulk stores from a swizzled staging tile (coalesced, asynchronous) when the view allows a
-// tensor map; otherwise (and for 16-bit O or the accumulate mode) the row-owner threads store directly.
+// O (fp32, or bf16 / fp16 on request) goes out through TMA bulk stores from a swizzled staging tile (coalesced, asynchronous)
+// when the view allows a tensor map; otherwise (and in the accumulate mode) the row-owner threads store directly.
 void fwd_tc_set_out_map(FwdTcParams& prm, const AttnParams& p) {
   prm.o_tma = 0;
-  if (p.o_dtype != kF32 || p.accumulate || getenv("MFA_DISABLE_TMA_STORE")) return;
-  if (!tc::view_ok(p.o, p.H, p.B, 4)) return;
-  if (tc::make_map(&prm.to, p.o, kF32, p.B, p.H, p.Sq, p.D)) prm.o_tma = 1;
+  if (p.accumulate || getenv("MFA_DISABLE_TMA_STORE")) return;
+  if (p.o_dtype != kF32 && p.o_dtype != kBF16 && p.o_dtype != kF16) return;
+  if (p.o_dtype != kF32 && !getenv("MFA_TMA_STORE_16")) return;        // 16-bit staging path: opt-in until verified on the GPU
+  if (!tc::view_ok(p.o, p.H, p.B, dtype_bytes(p.o_dtype))) return;
+  if (tc::make_map(&prm.to, p.o, p.o_dtype, p.B, p.H, p.Sq, p.D)) prm.o_tma = 1;
 }
 
 bool fwd_tc_eligible(const AttnParams& p) {

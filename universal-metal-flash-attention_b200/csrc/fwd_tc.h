@@ -12,7 +12,7 @@ enum FwdMode : int { kFwdF16 = 0, kFwdBF16 = 1, kFwdI8 = 2 };
 
 struct FwdTcParams {
   CUtensorMap tq, tk, tv;
-  CUtensorMap to;          // fp32 O, box = 32 floats x 128 rows (valid when o_tma != 0)
+  CUtensorMap to;          // O in its output type, box = 128 bytes (32 floats / 64 halves) x 128 rows (valid when o_tma != 0)
   int o_tma;               // epilogue stages O in shared memory and writes it with TMA bulk stores
   void* o;
   long long o_sb, o_sh, o_ss;
