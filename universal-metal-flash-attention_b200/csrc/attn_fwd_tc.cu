@@ -954,7 +954,6 @@ void fwd_tc_set_out_map(FwdTcParams& prm, const AttnParams& p) {
   prm.o_tma = 0;
   if (p.accumulate || getenv("MFA_DISABLE_TMA_STORE")) return;
   if (p.o_dtype != kF32 && p.o_dtype != kBF16 && p.o_dtype != kF16) return;
-  if (p.o_dtype != kF32 && !getenv("MFA_TMA_STORE_16")) return;        // 16-bit staging path: opt-in until verified on the GPU
   if (!tc::view_ok(p.o, p.H, p.B, dtype_bytes(p.o_dtype))) return;
   if (tc::make_map(&prm.to, p.o, p.o_dtype, p.B, p.H, p.Sq, p.D)) prm.o_tma = 1;
 }
