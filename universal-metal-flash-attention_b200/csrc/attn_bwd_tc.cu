@@ -349,11 +349,16 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
           for (int i = 0; i < 32; ++i) ou[i] = 0u;
         }
         if (live && dst_base) {
-          float4* dst = reinterpret_cast<float4*>(dst_base + orow + ch * 32);
+          float* dst = dst_base + orow + ch * 32;
+          if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {       // one 32-byte sector per store: half the LSU requests
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            dst[i] = make_float4(__uint_as_float(ou[4 * i]), __uint_as_float(ou[4 * i + 1]), __uint_as_float(ou[4 * i + 2]),
-                                 __uint_as_float(ou[4 * i + 3]));
+            for (int i = 0; i < 4; ++i) st_global_v8(dst + 8 * i, reinterpret_cast<const float*>(ou) + 8 * i);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              reinterpret_cast<float4*>(dst)[i] = make_float4(__uint_as_float(ou[4 * i]), __uint_as_float(ou[4 * i + 1]),
+                                                              __uint_as_float(ou[4 * i + 2]), __uint_as_float(ou[4 * i + 3]));
+          }
         }
       }
     }
@@ -559,11 +564,16 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
         for (int i = 0; i < 32; ++i) ou[i] = 0u;
       }
       if (live) {
-        float4* dst = reinterpret_cast<float4*>(p.dq + orow + ch * 32);
+        float* dst = p.dq + orow + ch * 32;
+        if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          dst[i] = make_float4(__uint_as_float(ou[4 * i]), __uint_as_float(ou[4 * i + 1]), __uint_as_float(ou[4 * i + 2]),
-                               __uint_as_float(ou[4 * i + 3]));
+          for (int i = 0; i < 4; ++i) st_global_v8(dst + 8 * i, reinterpret_cast<const float*>(ou) + 8 * i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            reinterpret_cast<float4*>(dst)[i] = make_float4(__uint_as_float(ou[4 * i]), __uint_as_float(ou[4 * i + 1]),
+                                                            __uint_as_float(ou[4 * i + 2]), __uint_as_float(ou[4 * i + 3]));
+        }
       }
     }
   }
