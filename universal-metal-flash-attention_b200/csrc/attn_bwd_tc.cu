@@ -40,6 +40,8 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 struct BwdTcParams {
   CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tdq, tdk, tdv;   // fp32 gradients, box = 32 floats x 128 rows (valid when g_tma != 0)
+  int g_tma;                   // epilogues stage the gradients in shared memory and write them with TMA bulk stores
   const float* lse;
   const float* dterm;
   float* dq;
@@ -348,7 +350,14 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
 #pragma unroll
           for (int i = 0; i < 32; ++i) ou[i] = 0u;
         }
-        if (live && dst_base) {
+        if (p.g_tma && dst_base) {
+          // swizzled staging chunk in the operand memory (every MMA has retired): 32 columns of this key row = one 128-byte line
+          const uint32_t line = base + (uint32_t)(which * (D / 32) + half * (D / 64) + ch) * (128u * 128u) + (uint32_t)row * 128u;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            st_shared_v4(line + (uint32_t)((i ^ (row & 7)) << 4), __uint_as_float(ou[4 * i]), __uint_as_float(ou[4 * i + 1]),
+                         __uint_as_float(ou[4 * i + 2]), __uint_as_float(ou[4 * i + 3]));
+        } else if (live && dst_base) {
           float* dst = dst_base + orow + ch * 32;
           if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {       // one 32-byte sector per store: half the LSU requests
 #pragma unroll
@@ -360,6 +369,22 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
                                                               __uint_as_float(ou[4 * i + 2]), __uint_as_float(ou[4 * i + 3]));
           }
         }
+      }
+    }
+    if (p.g_tma) {
+      fence_proxy_async_smem();
+      named_bar_sync(1 + half, 128);
+      if ((threadIdx.x & 127) == 0) {
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          if ((which == 0 ? p.dv : p.dk) == nullptr) continue;
+#pragma unroll
+          for (int ch = 0; ch < D / 64; ++ch)
+            tma_store_4d(which == 0 ? &p.tdv : &p.tdk, base + (uint32_t)(which * (D / 32) + half * (D / 64) + ch) * (128u * 128u),
+                         half * (D / 2) + ch * 32, c0, hk, b);
+        }
+        bulk_commit();
+        bulk_wait_read();
       }
     }
   }
@@ -563,7 +588,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
 #pragma unroll
         for (int i = 0; i < 32; ++i) ou[i] = 0u;
       }
-      if (live) {
+      if (p.g_tma) {
+        const uint32_t line = base + (uint32_t)(half * (D / 64) + ch) * (128u * 128u) + (uint32_t)row * 128u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          st_shared_v4(line + (uint32_t)((i ^ (row & 7)) << 4), __uint_as_float(ou[4 * i]), __uint_as_float(ou[4 * i + 1]),
+                       __uint_as_float(ou[4 * i + 2]), __uint_as_float(ou[4 * i + 3]));
+      } else if (live) {
         float* dst = p.dq + orow + ch * 32;
         if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
 #pragma unroll
@@ -574,6 +605,17 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
             reinterpret_cast<float4*>(dst)[i] = make_float4(__uint_as_float(ou[4 * i]), __uint_as_float(ou[4 * i + 1]),
                                                             __uint_as_float(ou[4 * i + 2]), __uint_as_float(ou[4 * i + 3]));
         }
+      }
+    }
+    if (p.g_tma) {
+      fence_proxy_async_smem();
+      named_bar_sync(1 + half, 128);
+      if ((threadIdx.x & 127) == 0) {
+#pragma unroll
+        for (int ch = 0; ch < D / 64; ++ch)
+          tma_store_4d(&p.tdq, base + (uint32_t)(half * (D / 64) + ch) * (128u * 128u), half * (D / 2) + ch * 32, r0, h, b);
+        bulk_commit();
+        bulk_wait_read();
       }
     }
   }
@@ -646,6 +688,16 @@ cudaError_t launch_bwd_tc(const AttnParams& p, cudaStream_t st) {
     return cudaErrorInvalidValue;
   prm.lse = p.lse; prm.dterm = p.dterm;
   prm.dq = p.dq; prm.dk = p.dk; prm.dv = p.dv;
+  // gradients leave through swizzled staging tiles + TMA bulk stores (contiguous fp32 BHSD by contract)
+  prm.g_tma = 0;
+  if (!getenv("MFA_DISABLE_TMA_STORE")) {
+    auto gview = [&](float* ptr, int Hn, int S) { return TensorView{ptr, (int64_t)Hn * S * p.D, (int64_t)S * p.D, (int64_t)p.D, 1}; };
+    bool ok = true;
+    if (p.dq) ok = ok && tc::make_map(&prm.tdq, gview(p.dq, p.H, p.Sq), kF32, p.B, p.H, p.Sq, p.D);
+    if (p.dk) ok = ok && tc::make_map(&prm.tdk, gview(p.dk, p.Hkv, p.Skv), kF32, p.B, p.Hkv, p.Skv, p.D);
+    if (p.dv) ok = ok && tc::make_map(&prm.tdv, gview(p.dv, p.Hkv, p.Skv), kF32, p.B, p.Hkv, p.Skv, p.D);
+    prm.g_tma = ok ? 1 : 0;
+  }
   prm.H = p.H; prm.Hkv = p.Hkv; prm.Sq = p.Sq; prm.Skv = p.Skv;
   prm.c = p.scale * kLog2e; prm.scale = p.scale;
   prm.causal = p.causal; prm.window = p.window;
