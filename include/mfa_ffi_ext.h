@@ -130,7 +130,10 @@ int mfa_rope_rotate_encode_mtl(
  * hidden from query i iff i > j + window_size (the reference kernel's rule, AttentionKernel+Softmax.swift:450,
  * which no mfa_* symbol reaches -- SURVEY A6).  Fully masked KV tiles are skipped before they are loaded.
  * stream: NULL = run on the context stream and block until done (like every reference entry point);
- * non-NULL = a cudaStream_t; the call only enqueues, and q/k/v/out/lse/mask must be device-resident. */
+ * non-NULL = a cudaStream_t; the call only enqueues, and q/k/v/out/lse/mask must be device-resident.
+ * External masks are read in place (bool bytes, fp16 / bf16 / fp32; any broadcast; unit key stride for the tensor-core
+ * kernels); a pre-pass leaves per-query-block lists of the KV tiles the mask keeps visible in context-owned scratch, so
+ * enqueue-only calls that carry a mask (or quantised operands) must stay on ONE stream per context at a time. */
 mfa_error_t mfa_attention_forward_ex(
     mfa_context_t context, mfa_buffer_t q, mfa_buffer_t k, mfa_buffer_t v, mfa_buffer_t out, mfa_buffer_t lse,
     uint32_t batch_size, uint32_t seq_len_q, uint32_t seq_len_kv, uint32_t num_heads, uint16_t head_dim,
