@@ -153,3 +153,32 @@ def test_bwd_tc_mask_with_causal_gqa_free(ctx):
     assert ctx.last_kernel.endswith("_mask")
     rq, rk, rv, _ = O.attention_backward(qf, kf, vf, gf, mask=m, causal=True)
     assert max(rel_max(dq, rq), rel_max(dk, rk), rel_max(dv, rv)) < 2e-2
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("kind", ["bool", "add_fp32"])
+def test_bwd_tc_mask_tile_skipping(ctx, kind, causal, monkeypatch):
+    """visible-tile lists in the backward (dQ: KV tiles per query block; dK/dV: query tiles per KV tile): a packing mask with
+    segments that do not line up with the tiles, some fully hidden rows; gradients against the oracle and against the
+    walk-every-tile path"""
+    import umfa
+    B, H, S, D = 2, 2, 900, 128
+    rng = np.random.default_rng(41)
+    q, k, v, g = (rng.standard_normal((B, H, S, D)).astype(np.float32) for _ in range(4))
+    (qa, qf), (ka, kf), (va, vf), (ga, gf) = (to_dtype(x, "bf16") for x in (q, k, v, g))
+    seg = np.repeat(np.arange(6), S // 6)
+    vis = np.broadcast_to((seg[:, None] == seg[None, :])[None, None], (B, 1, S, S)).copy()
+    vis[1, 0, 700:, :] = False
+    if causal:
+        vis[1, 0, 700:, 0] = True          # keep every row alive under the causal rule for a well-defined comparison
+    m = vis if kind == "bool" else np.where(vis, rng.standard_normal(vis.shape), -np.inf).astype(np.float32)
+    o_ref, l_ref = O.attention_forward(qf, kf, vf, mask=m, causal=causal)
+    rq, rk, rv, _ = O.attention_backward(qf, kf, vf, gf, mask=m, causal=causal)
+    dq, dk, dv, _ = umfa.flash_attention_backward(ctx, ga, qa, ka, va, o_ref, l_ref, input_precision="bf16", attn_mask=m, causal=causal)
+    assert ctx.last_kernel.endswith("_mask")
+    for name, got, ref in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+        assert np.isfinite(got).all(), name
+        assert rel_max(got, ref) < 2e-2, name
+    monkeypatch.setenv("MFA_DISABLE_MASK_SKIP", "1")
+    dq2, dk2, dv2, _ = umfa.flash_attention_backward(ctx, ga, qa, ka, va, o_ref, l_ref, input_precision="bf16", attn_mask=m, causal=causal)
+    assert rel_max(dq, dq2) < 1e-5 and rel_max(dk, dk2) < 1e-5 and rel_max(dv, dv2) < 1e-5

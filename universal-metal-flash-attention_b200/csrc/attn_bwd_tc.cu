@@ -55,7 +55,14 @@ struct BwdTcParams {
   const void* mask;
   int mask_kind, mask_scalar;
   long long mask_sb, mask_sh, mask_sq;
+  // visible-tile lists under an external mask (null = walk the whole causal / window range):
+  //   dQ kernel:  per (mask batch, mask head, 256-row query block) the KV tiles with a visible element   [lists][m_nkt]
+  //   dK/dV kernel (H == Hkv only): per (mask batch, mask head, KV tile) the 128-row query tiles           [listsT][2 m_nqb]
+  const int* ktiles; const int* kcounts;
+  const int* qtiles; const int* qcounts;
+  int m_nqb, m_nkt;
 };
+constexpr int kTileNoMask = 1 << 30;          // list entry flag: the mask is a no-op on this tile (no loads needed)
 
 // 32 mask terms in log2 units (-inf = hidden) for elements off0 + i * stride, i < nvalid (the rest: 0, they belong to dead
 // rows / columns whose P is zeroed elsewhere).  The type switch sits outside the unrolled loops.
@@ -127,8 +134,17 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
   int qlo, qhi;
   visible_query_range(p.causal, p.window, p.Sq, c0, min(c0 + 128, p.Skv), qlo, qhi);
   const int i_lo = qlo >> 7;
-  const int nq = qhi > qlo ? ((qhi + 127) >> 7) - i_lo : 0;
+  int nq = qhi > qlo ? ((qhi + 127) >> 7) - i_lo : 0;
+  const int* qlist = nullptr;                 // visible query tiles of this KV tile under the external mask
+  if constexpr (MASKED) {
+    if (p.qtiles) {
+      const int lid = ((p.mask_sb ? b : 0) * (p.mask_sh ? p.H : 1) + (p.mask_sh ? hk : 0)) * p.m_nkt + jt;
+      qlist = p.qtiles + (size_t)lid * (2 * p.m_nqb);
+      nq = __ldg(p.qcounts + lid);
+    }
+  }
   const int n_it = nq * group;
+  auto qtile_of = [&](int it) { return qlist ? (__ldg(qlist + it) & (kTileNoMask - 1)) : i_lo + it % nq; };
 
   if (threadIdx.x == 256) {
     mbar_init(kv_full, 1); mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 8); mbar_init(ds_full, 8);
@@ -158,7 +174,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
       load_tile_4d(sV, &p.tv, kv_full, c0, hk, b, C::kChunks, CHB);
       for (int it = 0; it < n_it; ++it) {
         const int sa = it % RA, sb = it % RB;
-        const int head = hk * group + it / nq, q0 = (i_lo + it % nq) * 128;
+        const int head = hk * group + it / nq, q0 = qtile_of(it) * 128;
         mbar_wait(q_empty(sa), ((it / RA) & 1) ^ 1);
         mbar_arrive_expect_tx(q_full(sa), TILE);
         load_tile_4d(sQ(sa), &p.tq, q_full(sa), q0, head, b, C::kChunks, CHB);
@@ -172,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
     const int tl = threadIdx.x - 320;
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1;
-      const int head = hk * group + it / nq, q0 = (i_lo + it % nq) * 128;
+      const int head = hk * group + it / nq, q0 = qtile_of(it) * 128;
       mbar_wait(stat_empty(s), ((it >> 1) & 1) ^ 1);
       const size_t rb = ((size_t)b * p.H + head) * p.Sq;
 #pragma unroll
@@ -259,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
     const int qhi_r = p.window >= 0 ? min(key + p.window, 1 << 30) : (1 << 30);
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1;
-      const int q0 = (i_lo + it % nq) * 128 + half * 64;
+      const int q0 = qtile_of(it) * 128 + half * 64;
       const float* sL = stat + (s * 2 + 0) * 128 + half * 64;
       const float* sD = stat + (s * 2 + 1) * 128 + half * 64;
       // queries visible to this key: [qlo_r, qhi_r]; rows past Sq carry L = +inf (P = 0)
@@ -422,7 +438,16 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
   int klo, khi;
   visible_key_range(p.causal, p.window, p.Skv, r0, min(r0 + 128, p.Sq), klo, khi);
   const int j_lo = klo >> 7;
-  const int n = khi > klo ? ((khi + 127) >> 7) - j_lo : 0;
+  int n = khi > klo ? ((khi + 127) >> 7) - j_lo : 0;
+  const int* klist = nullptr;                 // visible KV tiles of this tile's 256-row query block under the external mask
+  if constexpr (MASKED) {
+    if (p.ktiles) {
+      const int lid = ((p.mask_sb ? b : 0) * (p.mask_sh ? p.H : 1) + (p.mask_sh ? h : 0)) * p.m_nqb + (it_q >> 1);
+      klist = p.ktiles + (size_t)lid * p.m_nkt;
+      n = __ldg(p.kcounts + lid);
+    }
+  }
+  auto ktile_of = [&](int it) { return klist ? (__ldg(klist + it) & (kTileNoMask - 1)) : j_lo + it; };
 
   if (threadIdx.x == 256) {
     mbar_init(q_full, 1); mbar_init(dp_full, 1); mbar_init(ds_full, 8); mbar_init(acc_full, 1);
@@ -452,10 +477,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
         const int sa = it % RA, sb = it % RB;
         mbar_wait(k_empty(sa), ((it / RA) & 1) ^ 1);
         mbar_arrive_expect_tx(k_full(sa), TILE);
-        load_tile_4d(sK(sa), &p.tk, k_full(sa), (j_lo + it) * 128, hk, b, C::kChunks, CHB);
+        load_tile_4d(sK(sa), &p.tk, k_full(sa), ktile_of(it) * 128, hk, b, C::kChunks, CHB);
         mbar_wait(v_empty(sb), ((it / RB) & 1) ^ 1);
         mbar_arrive_expect_tx(v_full(sb), TILE);
-        load_tile_4d(sV(sb), &p.tv, v_full(sb), (j_lo + it) * 128, hk, b, C::kChunks, CHB);
+        load_tile_4d(sV(sb), &p.tv, v_full(sb), ktile_of(it) * 128, hk, b, C::kChunks, CHB);
       }
     }
   } else if (warp == 8) {
@@ -525,7 +550,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
     const int clo = p.window >= 0 ? max(0, r - p.window) : 0;
     for (int it = 0; it < n; ++it) {
       const int u = it & 1;
-      const int k0 = (j_lo + it) * 128 + half * 64;
+      const int k0 = ktile_of(it) * 128 + half * 64;
       const uint32_t tS = tmem + lane_base + u * 128 + half * 64;
       const bool any_mask = __any_sync(0xffffffffu, k0 < clo || k0 + 63 > chi);
       const int lo_i = clo - k0, hi_i = chi - k0;
@@ -624,6 +649,37 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
   if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
+// ---- visible-tile lists for the backward, from the forward's tile flags (launch_mask_flags)
+// dQ: same lists as the forward (KV tiles per 256-row query block).
+__global__ void bwd_compact_k_kernel(const uint8_t* __restrict__ flags, int* __restrict__ tiles, int* __restrict__ counts,
+                                     int lists, int nkt) {
+  const int lid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lid >= lists) return;
+  int cnt = 0;
+  for (int j = 0; j < nkt; ++j)
+    if (const int f = flags[(size_t)lid * nkt + j]) tiles[(size_t)lid * nkt + cnt++] = j | (f == 2 ? kTileNoMask : 0);
+  counts[lid] = cnt;
+}
+// dK/dV: per (mask batch x head, KV tile) the 128-row query tiles of every flagged 256-row block, clipped to the tile's own
+// causal / window query range.
+__global__ void bwd_compact_q_kernel(const uint8_t* __restrict__ flags, int* __restrict__ tiles, int* __restrict__ counts,
+                                     int mbh_n, int nqb, int nkt, int Sq, int Skv, int causal, int window) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= mbh_n * nkt) return;
+  const int mbh = idx / nkt, j = idx % nkt;
+  int qlo, qhi;
+  visible_query_range(causal, window, Sq, j * 128, min(j * 128 + 128, Skv), qlo, qhi);
+  const int i_lo = qlo >> 7, i_hi = qhi > qlo ? (qhi + 127) >> 7 : i_lo;
+  int cnt = 0;
+  for (int qb = 0; qb < nqb; ++qb) {
+    const int f = flags[((size_t)mbh * nqb + qb) * nkt + j];
+    if (!f) continue;
+    for (int t = 2 * qb; t < 2 * qb + 2; ++t)
+      if (t >= i_lo && t < i_hi && t * 128 < Sq) tiles[(size_t)idx * (2 * nqb) + cnt++] = t | (f == 2 ? kTileNoMask : 0);
+  }
+  counts[idx] = cnt;
+}
+
 template <typename K>
 cudaError_t ensure_smem(K kern, int bytes, bool& done) {
   if (done) return cudaSuccess;
@@ -678,6 +734,15 @@ bool bwd_tc_eligible(const AttnParams& p) {
   return tc::encode_fn() != nullptr;
 }
 
+size_t bwd_tc_mask_scratch_bytes(const AttnParams& p) {
+  if (p.mask_kind == kMaskNone || !p.mask || getenv("MFA_DISABLE_MASK_SKIP")) return 0;
+  int nqb, nkt, MB, MH;
+  mask_tile_dims(p, nqb, nkt, MB, MH);
+  const size_t lists = (size_t)MB * MH * nqb, listsT = (size_t)MB * MH * nkt;
+  if (lists > 0x3fffffffULL || listsT > 0x3fffffffULL) return 0;
+  return (lists * (nkt + 1) + listsT * (2 * (size_t)nqb + 1)) * sizeof(int) + lists * nkt + 16;
+}
+
 // dQ, dK, dV from Q, K, V, dO, L and D (= scale * rowsum(dO * O), launch_dterm).  Gradients are fp32 contiguous BHSD.
 cudaError_t launch_bwd_tc(const AttnParams& p, cudaStream_t st) {
   BwdTcParams prm;
@@ -706,9 +771,34 @@ cudaError_t launch_bwd_tc(const AttnParams& p, cudaStream_t st) {
     prm.mask = p.mask; prm.mask_kind = p.mask_kind; prm.mask_scalar = p.mask_scalar;
     prm.mask_sb = p.mask_sb; prm.mask_sh = p.mask_sh; prm.mask_sq = p.mask_sq;
   }
+  prm.ktiles = prm.kcounts = prm.qtiles = prm.qcounts = nullptr; prm.m_nqb = prm.m_nkt = 0;
+  cudaError_t e;
+  if (prm.mask && p.mask_tile_scratch && bwd_tc_mask_scratch_bytes(p)) {
+    int nqb, nkt, MB, MH;
+    mask_tile_dims(p, nqb, nkt, MB, MH);
+    const long long lists = (long long)MB * MH * nqb, listsT = (long long)MB * MH * nkt;
+    int* kcounts = p.mask_tile_scratch;
+    int* ktiles = kcounts + lists;
+    int* qcounts = ktiles + lists * nkt;
+    int* qtiles = qcounts + listsT;
+    uint8_t* flags = reinterpret_cast<uint8_t*>(qtiles + listsT * 2 * nqb);
+    if (launch_mask_flags(p, flags, st) == cudaSuccess) {
+      bwd_compact_k_kernel<<<(unsigned)((lists + 127) / 128), 128, 0, st>>>(flags, ktiles, kcounts, (int)lists, nkt);
+      prm.ktiles = ktiles; prm.kcounts = kcounts;
+      if (p.H == p.Hkv) {            // grouped heads may carry different masks per head of a group: walk the full range
+        bwd_compact_q_kernel<<<(unsigned)((listsT + 127) / 128), 128, 0, st>>>(flags, qtiles, qcounts, MB * MH, nqb, nkt, p.Sq,
+                                                                             p.Skv, p.causal, p.window);
+        prm.qtiles = qtiles; prm.qcounts = qcounts;
+      }
+      g_launch_count += 2;
+      prm.m_nqb = nqb; prm.m_nkt = nkt;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    } else {
+      cudaGetLastError();
+    }
+  }
   const bool want_dq = p.dq != nullptr, want_dkv = p.dk != nullptr && p.dv != nullptr;
   const bool bf = p.in_dtype == kBF16;
-  cudaError_t e;
   if (p.D == 128) e = bf ? launch_bwd<128, true>(prm, p.B, want_dq, want_dkv, st) : launch_bwd<128, false>(prm, p.B, want_dq, want_dkv, st);
   else e = bf ? launch_bwd<64, true>(prm, p.B, want_dq, want_dkv, st) : launch_bwd<64, false>(prm, p.B, want_dq, want_dkv, st);
   if (prm.mask) g_last_kernel = p.D == 128 ? (bf ? "bwd_tc_bf16_d128_mask" : "bwd_tc_fp16_d128_mask") : (bf ? "bwd_tc_bf16_d64_mask" : "bwd_tc_fp16_d64_mask");

@@ -928,6 +928,26 @@ size_t fwd_tc_mask_scratch_bytes(const AttnParams& p) {
   return (size_t)m.lists * (m.nkt + 1) * sizeof(int) + (size_t)m.lists * m.nkt + 16;      // counts, lists, flags
 }
 
+// Tile classification shared with the backward (attn_bwd_tc.cu): flags[((mb * MH + mh) * nqb + qb) * nkt + j] = 0 hidden,
+// 1 partial, 2 no-op for query block qb (256 rows) x KV tile j (128 keys).
+void mask_tile_dims(const AttnParams& p, int& nqb, int& nkt, int& MB, int& MH) {
+  const MaskLists m = mask_lists(p);
+  nqb = m.nqb; nkt = m.nkt; MB = m.MB; MH = m.MH;
+}
+
+cudaError_t launch_mask_flags(const AttnParams& p, uint8_t* flags, cudaStream_t st) {
+  const MaskLists m = mask_lists(p);
+  if (m.lists > 0x3fffffffLL || m.MB * (long long)m.MH > 65535 || m.nqb > 65535) return cudaErrorInvalidValue;
+  MaskTileParams q;
+  q.mask = p.mask; q.kind = p.mask_kind; q.scalar = p.mask_scalar;
+  q.sb = p.mask_sb; q.sh = p.mask_sh; q.sq = p.mask_sq;
+  q.Sq = p.Sq; q.Skv = p.Skv; q.causal = p.causal; q.window = p.window; q.nqb = m.nqb; q.nkt = m.nkt; q.MH = m.MH;
+  q.counts = nullptr; q.tiles = nullptr;
+  mask_flags_kernel<<<dim3((unsigned)m.nkt, (unsigned)m.nqb, (unsigned)(m.MB * m.MH)), 256, 0, st>>>(q, flags);
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
 // Builds the visible-tile lists into p.mask_tile_scratch (when given) and points the kernel parameters at them.
 cudaError_t fwd_tc_build_mask_tiles(FwdTcParams& prm, const AttnParams& p, cudaStream_t st) {
   prm.mtiles = nullptr; prm.mcounts = nullptr; prm.m_nkt = 0;

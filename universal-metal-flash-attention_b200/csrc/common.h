@@ -83,6 +83,9 @@ cudaError_t launch_bwd_dkv_only(const AttnParams& p, cudaStream_t st);      // d
 // tcgen05 forward (bf16/fp16, D in {64,128}); returns cudaErrorNotSupported when the problem is not eligible.
 bool fwd_tc_eligible(const AttnParams& p);
 size_t fwd_tc_mask_scratch_bytes(const AttnParams& p);     // 0 when there is no external mask
+size_t bwd_tc_mask_scratch_bytes(const AttnParams& p);     // same for the backward's two list sets
+void mask_tile_dims(const AttnParams& p, int& nqb, int& nkt, int& MB, int& MH);
+cudaError_t launch_mask_flags(const AttnParams& p, uint8_t* flags, cudaStream_t st);
 cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st);
 
 // tcgen05 backward (bf16/fp16, D in {64,128}); needs p.dterm filled by launch_dterm first.

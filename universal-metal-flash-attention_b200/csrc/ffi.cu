@@ -444,6 +444,8 @@ mfa_error_t backward_core(Context* ctx, const BwdArgs& a) {
   mfa_error_t me = setup_mask(ctx, st, a.mask, p);
   if (me != MFA_SUCCESS) return me;
 
+  if (const size_t mb = bwd_tc_mask_scratch_bytes(p))
+    p.mask_tile_scratch = reinterpret_cast<int*>(ctx->scratch[Context::kMaskTiles].get(mb));     // null = no tile skipping
   Timer tm(ctx, st, !a.async);
   cudaError_t e = cudaSuccess;
   if (bwd_tc_eligible(p)) {
