@@ -62,5 +62,32 @@ for name, (mask, mt, ms) in cases.items():
     res[name] = {"ms": t * 1e3, "kernel": ctx.last_kernel, "visible_fraction": vis,
                  "tflops_of_visible_pairs": 4.0 * B * H * S * S * D * vis / t / 1e12,
                  "mask_mb": 0 if mask is None else mask.numel() * mask.element_size() / 1e6}
+# backward under the same masks (dO random, O / L from the forward just run)
+do = torch.randn(B, H, S, D, device=dev, generator=g).to(torch.bfloat16)
+dq, dk, dv = (torch.empty(B, H, S, D, device=dev, dtype=torch.float32) for _ in range(3))
+dt = torch.empty(B, H, S, device=dev, dtype=torch.float32)
+gb = [umfa.MFABuffer(ctx, device_ptr=t.data_ptr(), size=t.numel() * t.element_size()) for t in (do, dq, dk, dv, dt)]
+
+
+def bwd(mask, mtype, mscalar):
+    margs = [None, 0, None, None, 0, 0, 0]
+    if mask is not None:
+        margs = [ctypes.c_void_p(mask.data_ptr()), mask.numel() * mask.element_size(), (i64 * mask.dim())(*mask.shape),
+                 (i64 * mask.dim())(*mask.stride()), mask.dim(), mtype, mscalar]
+    return lib.mfa_attention_backward_ex(ctx.handle, gb[0].handle, h[0], h[1], h[2], h[3], h[4], gb[1].handle, gb[2].handle,
+                                         gb[3].handle, gb[4].handle, B, S, S, H, D, scale, False, -1, 1, *margs, None)
+
+
+for name, (mask, mt, ms) in cases.items():
+    assert fwd(mask, mt, ms) == 0
+    ts = []
+    for i in range(steps + 2):
+        rc = bwd(mask, mt, ms)
+        assert rc == 0, (name, rc)
+        if i >= 2:
+            ts.append(ctx.gpu_latency)
+    t = float(np.median(ts))
+    res[name]["bwd_ms"] = t * 1e3
+    res[name]["bwd_kernel"] = ctx.last_kernel
 print(json.dumps({"workload": "FLUX.1-schnell shape B=1 H=24 N=4608 D=128 bf16 forward under external masks",
                   "timing": "mfa_get_gpu_latency, median of %d" % steps, **res}))

@@ -67,6 +67,48 @@ constexpr int kTileNoMask = 1 << 30;          // list entry flag: the mask is a 
 // 32 mask terms in log2 units (-inf = hidden) for elements off0 + i * stride, i < nvalid (the rest: 0, they belong to dead
 // rows / columns whose P is zeroed elsewhere).  The type switch sits outside the unrolled loops.
 __device__ __forceinline__ void mask_terms32(const BwdTcParams& p, long long off0, long long stride, int nvalid, float* mt) {
+  if (stride == 1 && nvalid == 32) {
+    // row-owner layout (dQ kernel): 32 consecutive elements of one row -> 32-byte sector loads when aligned
+    if (p.mask_kind == kMaskBool) {
+      const uint8_t* m = reinterpret_cast<const uint8_t*>(p.mask) + off0;
+      if ((reinterpret_cast<uintptr_t>(m) & 31) == 0) {
+        uint32_t w[8];
+        ldg256(m, w);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mt[i] = ((w[i >> 2] >> (8 * (i & 3))) & 0xffu) ? 0.f : -CUDART_INF_F;
+        return;
+      }
+    } else if (p.mask_scalar == kMaskF32) {
+      const float* m = reinterpret_cast<const float*>(p.mask) + off0;
+      if ((reinterpret_cast<uintptr_t>(m) & 31) == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t w[8];
+          ldg256(m + 8 * c, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) mt[8 * c + i] = __uint_as_float(w[i]) * kLog2e;
+        }
+        return;
+      }
+    } else {
+      const uint16_t* m = reinterpret_cast<const uint16_t*>(p.mask) + off0;
+      if ((reinterpret_cast<uintptr_t>(m) & 31) == 0) {
+        const bool bf = p.mask_scalar == kMaskBF16;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t w[8];
+          ldg256(m + 16 * c, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
+            mt[16 * c + 2 * i] = (bf ? __uint_as_float(lo << 16) : __half2float(__ushort_as_half((unsigned short)lo))) * kLog2e;
+            mt[16 * c + 2 * i + 1] = (bf ? __uint_as_float(hi << 16) : __half2float(__ushort_as_half((unsigned short)hi))) * kLog2e;
+          }
+        }
+        return;
+      }
+    }
+  }
   if (p.mask_kind == kMaskBool) {
     const uint8_t* m = reinterpret_cast<const uint8_t*>(p.mask) + off0;
 #pragma unroll
@@ -291,10 +333,15 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
         tmem_ld_x32(tS + ch * 32, su);
         float mt[32];
         if constexpr (MASKED) {
-          // mask[q][key] for the 32 queries of this chunk: consecutive lanes = consecutive keys, so every load is coalesced
-          const int head = hk * group + it / nq, qa = q0 + ch * 32;
-          const long long off = (long long)b * p.mask_sb + (long long)head * p.mask_sh + (long long)qa * p.mask_sq + min(key, p.Skv - 1);
-          mask_terms32(p, off, p.mask_sq, key < p.Skv ? min(32, p.Sq - qa) : 0, mt);
+          if (qlist && (__ldg(qlist + it) & kTileNoMask)) {          // the mask is a no-op on this tile: nothing to load
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mt[i] = 0.f;
+          } else {
+            // mask[q][key] for the 32 queries of this chunk: consecutive lanes = consecutive keys, so every load is coalesced
+            const int head = hk * group + it / nq, qa = q0 + ch * 32;
+            const long long off = (long long)b * p.mask_sb + (long long)head * p.mask_sh + (long long)qa * p.mask_sq + min(key, p.Skv - 1);
+            mask_terms32(p, off, p.mask_sq, key < p.Skv ? min(32, p.Sq - qa) : 0, mt);
+          }
         }
         tmem_wait_ld();
 #pragma unroll
@@ -563,9 +610,14 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
         tmem_ld_x32(tS + ch * 32, su);
         float mt[32];
         if constexpr (MASKED) {
-          const int ka = k0 + ch * 32;
-          const long long off = (long long)b * p.mask_sb + (long long)h * p.mask_sh + (long long)min(r, p.Sq - 1) * p.mask_sq + ka;
-          mask_terms32(p, off, 1, r < p.Sq ? min(32, p.Skv - ka) : 0, mt);
+          if (klist && (__ldg(klist + it) & kTileNoMask)) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mt[i] = 0.f;
+          } else {
+            const int ka = k0 + ch * 32;
+            const long long off = (long long)b * p.mask_sb + (long long)h * p.mask_sh + (long long)min(r, p.Sq - 1) * p.mask_sq + ka;
+            mask_terms32(p, off, 1, r < p.Sq ? min(32, p.Skv - ka) : 0, mt);
+          }
         }
         tmem_wait_ld();
 #pragma unroll
