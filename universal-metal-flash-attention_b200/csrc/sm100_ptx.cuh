@@ -72,9 +72,11 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, fl
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// 256-bit read-only global load (LDG.E.256 on sm_100): one full 32-byte sector per thread per request
+// 256-bit read-only global load (LDG.E.256 on sm_100): one full 32-byte sector per thread per request.  L1::no_allocate: the
+// attention kernels carve ~225 KB of the 228 KB L1 / shared array out as shared memory, and the few KB of L1 left cap the
+// lines in flight -- streaming mask rows past it took the dense fp32 mask forward from 0.76 to 0.56 ms at the FLUX shape
 __device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
-  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "l"(p));
 }
