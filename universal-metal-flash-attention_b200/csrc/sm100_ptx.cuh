@@ -83,7 +83,7 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
 
 // 256-bit coherent global load / store (read-modify-write epilogues)
 __device__ __forceinline__ void ld_global_v8(const float* p, float* r) {
-  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+  asm volatile("ld.global.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
                : "l"(p) : "memory");
 }
