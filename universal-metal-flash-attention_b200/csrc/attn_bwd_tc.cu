@@ -324,6 +324,23 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
       const bool any_mask = __any_sync(0xffffffffu, q0 < qlo_r || q0 + 63 > qhi_r);
       const int lo_i = qlo_r - q0, hi_i = qhi_r - q0;
       float pv[64];
+      if constexpr (MASKED) {
+        // the mask terms of this (query tile, key) pair do not depend on S: they are requested before the wait for S and land
+        // in the registers that will hold P (free at this point), so their latency hides under the MMA
+        if (qlist && (__ldg(qlist + it) & kTileNoMask)) {          // the mask is a no-op on this tile: nothing to load
+#pragma unroll
+          for (int i = 0; i < 64; ++i) pv[i] = 0.f;
+        } else {
+          const int head = hk * group + it / nq;
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            // mask[q][key] for 32 queries: consecutive lanes = consecutive keys, so every load is coalesced
+            const int qa = q0 + ch * 32;
+            const long long off = (long long)b * p.mask_sb + (long long)head * p.mask_sh + (long long)qa * p.mask_sq + min(key, p.Skv - 1);
+            mask_terms32(p, off, p.mask_sq, key < p.Skv ? min(32, p.Sq - qa) : 0, pv + ch * 32);
+          }
+        }
+      }
       mbar_wait(stat_full(s), (it >> 1) & 1);
       mbar_wait(s_full, it & 1);
       tc_fence_after();
@@ -331,18 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
       for (int ch = 0; ch < 2; ++ch) {
         uint32_t su[32];
         tmem_ld_x32(tS + ch * 32, su);
-        float mt[32];
-        if constexpr (MASKED) {
-          if (qlist && (__ldg(qlist + it) & kTileNoMask)) {          // the mask is a no-op on this tile: nothing to load
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mt[i] = 0.f;
-          } else {
-            // mask[q][key] for the 32 queries of this chunk: consecutive lanes = consecutive keys, so every load is coalesced
-            const int head = hk * group + it / nq, qa = q0 + ch * 32;
-            const long long off = (long long)b * p.mask_sb + (long long)head * p.mask_sh + (long long)qa * p.mask_sq + min(key, p.Skv - 1);
-            mask_terms32(p, off, p.mask_sq, key < p.Skv ? min(32, p.Sq - qa) : 0, mt);
-          }
-        }
+        const float* mt = pv + ch * 32;           // MASKED: mask terms loaded above; overwritten by P below
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -602,23 +608,26 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
       const bool any_mask = __any_sync(0xffffffffu, k0 < clo || k0 + 63 > chi);
       const int lo_i = clo - k0, hi_i = chi - k0;
       float pv[64];
+      if constexpr (MASKED) {
+        if (klist && (__ldg(klist + it) & kTileNoMask)) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) pv[i] = 0.f;
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            const int ka = k0 + ch * 32;
+            const long long off = (long long)b * p.mask_sb + (long long)h * p.mask_sh + (long long)min(r, p.Sq - 1) * p.mask_sq + ka;
+            mask_terms32(p, off, 1, r < p.Sq ? min(32, p.Skv - ka) : 0, pv + ch * 32);
+          }
+        }
+      }
       mbar_wait(s_full(u), (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         uint32_t su[32];
         tmem_ld_x32(tS + ch * 32, su);
-        float mt[32];
-        if constexpr (MASKED) {
-          if (klist && (__ldg(klist + it) & kTileNoMask)) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mt[i] = 0.f;
-          } else {
-            const int ka = k0 + ch * 32;
-            const long long off = (long long)b * p.mask_sb + (long long)h * p.mask_sh + (long long)min(r, p.Sq - 1) * p.mask_sq + ka;
-            mask_terms32(p, off, 1, r < p.Sq ? min(32, p.Skv - ka) : 0, mt);
-          }
-        }
+        const float* mt = pv + ch * 32;           // MASKED: mask terms loaded above; overwritten by P below
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) pv[ch * 32 + i] = ex2(fmaf(__uint_as_float(su[i]), c, MASKED ? mt[i] - L : -L));
