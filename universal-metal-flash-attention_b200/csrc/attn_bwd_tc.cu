@@ -109,22 +109,31 @@ __device__ __forceinline__ void mask_terms32(const BwdTcParams& p, long long off
       }
     }
   }
+  // strided path (dK/dV kernel: one element per query row): two passes over the same registers -- first nothing but the 32
+  // loads (raw bits parked in mt[]), then the conversions -- so all requests are in flight together.  (Fused into one loop the
+  // compiler issued load, convert, load, convert ...: 64 serialised L2 round trips per step; profiles/r01n_ncu_full_dkv_masked.txt)
   if (p.mask_kind == kMaskBool) {
     const uint8_t* m = reinterpret_cast<const uint8_t*>(p.mask) + off0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) mt[i] = (i < nvalid && __ldg(m + i * stride) == 0) ? -CUDART_INF_F : 0.f;
+    for (int i = 0; i < 32; ++i) mt[i] = __uint_as_float(ldg_pred_u8(m + i * stride, i < nvalid, 1u));
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mt[i] = __float_as_uint(mt[i]) == 0u ? -CUDART_INF_F : 0.f;
   } else if (p.mask_scalar == kMaskF32) {
     const float* m = reinterpret_cast<const float*>(p.mask) + off0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) mt[i] = i < nvalid ? __ldg(m + i * stride) * kLog2e : 0.f;
-  } else if (p.mask_scalar == kMaskBF16) {
-    const uint16_t* m = reinterpret_cast<const uint16_t*>(p.mask) + off0;
+    for (int i = 0; i < 32; ++i) mt[i] = __uint_as_float(ldg_pred_b32(m + i * stride, i < nvalid, 0u));
 #pragma unroll
-    for (int i = 0; i < 32; ++i) mt[i] = i < nvalid ? __uint_as_float((uint32_t)__ldg(m + i * stride) << 16) * kLog2e : 0.f;
+    for (int i = 0; i < 32; ++i) mt[i] *= kLog2e;
   } else {
-    const __half* m = reinterpret_cast<const __half*>(p.mask) + off0;
+    const uint16_t* m = reinterpret_cast<const uint16_t*>(p.mask) + off0;
+    const bool bf = p.mask_scalar == kMaskBF16;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) mt[i] = i < nvalid ? __half2float(m[i * stride]) * kLog2e : 0.f;
+    for (int i = 0; i < 32; ++i) mt[i] = __uint_as_float(ldg_pred_u16(m + i * stride, i < nvalid, 0u));
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const uint32_t raw = __float_as_uint(mt[i]);
+      mt[i] = (bf ? __uint_as_float(raw << 16) : __half2float(__ushort_as_half((unsigned short)raw))) * kLog2e;
+    }
   }
 }
 

@@ -81,6 +81,24 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
                : "l"(p));
 }
 
+// predicated read-only scalar loads as volatile asm: a run of them stays a run of loads (the compiler otherwise re-fuses
+// "load all, then convert all" into load-4 / convert-4 groups and the requests never overlap)
+__device__ __forceinline__ uint32_t ldg_pred_b32(const void* p, bool pred, uint32_t dflt) {
+  uint32_t v = dflt;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.b32 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"((int)pred));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_pred_u16(const void* p, bool pred, uint32_t dflt) {
+  unsigned short v = (unsigned short)dflt;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.u16 %0, [%1];\n\t}" : "+h"(v) : "l"(p), "r"((int)pred));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_pred_u8(const void* p, bool pred, uint32_t dflt) {
+  uint32_t v = dflt;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.u8 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"((int)pred));
+  return v;
+}
+
 // 256-bit coherent global load / store (read-modify-write epilogues)
 __device__ __forceinline__ void ld_global_v8(const float* p, float* r) {
   asm volatile("ld.global.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
