@@ -476,14 +476,19 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
               };
               if (ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 31) == 0) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {                     // 32 bytes = one sector per request
-                  uint32_t w[8];
-                  ldg256(mp + 16 * c, w);
-                  const float ah = c < 4 ? a0 : a1;
+                for (int g = 0; g < 2; ++g) {                     // 4 requests of 32 bytes in flight, then their 64 terms
+                  uint32_t w[4][8];
 #pragma unroll
-                  for (int k = 0; k < 8; ++k) {
-                    s[16 * c + 2 * k] = fmaf(s[16 * c + 2 * k], ah, widen(w[k] & 0xffffu) * kLog2e);
-                    s[16 * c + 2 * k + 1] = fmaf(s[16 * c + 2 * k + 1], ah, widen(w[k] >> 16) * kLog2e);
+                  for (int k4 = 0; k4 < 4; ++k4) ldg256(mp + 16 * (4 * g + k4), w[k4]);
+                  const float ah = g == 0 ? a0 : a1;
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4) {
+                    const int c = 4 * g + k4;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                      s[16 * c + 2 * k] = fmaf(s[16 * c + 2 * k], ah, widen(w[k4][k] & 0xffffu) * kLog2e);
+                      s[16 * c + 2 * k + 1] = fmaf(s[16 * c + 2 * k + 1], ah, widen(w[k4][k] >> 16) * kLog2e);
+                    }
                   }
                 }
               } else {
