@@ -41,3 +41,18 @@ def test_visible_pairs_brute_force():
         if window >= 0:
             vis &= r <= c + window
         assert b.visible_pairs(Sq, Skv, causal, window) == int(vis.sum()), (Sq, Skv, causal, window)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference needs no GPU: it times the CPU oracle and prints one JSON line with the contract keys"""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "small",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "TFLOP/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
