@@ -180,3 +180,46 @@ def test_python_adapter_argument_validation():
     assert m.mask_type == 1 and m.ndim == 2 and list(m.shape) == [5, 7] and list(m.strides) == [7, 1]
     with pytest.raises(ValueError):
         core._prepare_mask_metadata(np.ones((4, 7), bool), (2, 3, 5, 7))
+
+
+def test_c_program_links_by_library_name_and_runs(tmp_path):
+    """A plain C consumer, the way the reference's Rust / ObjC examples link (-lMFAFFI, examples/rust-ffi/build.rs:45;
+    extern calls as in examples/objc/simple_bridge.m:23-35): version, error string ownership (free), and a context request
+    that either succeeds (GPU present) or reports MFA_ERROR_DEVICE_NOT_SUPPORTED -- never a crash, never a CPU fallback."""
+    lib_dir = os.path.join(ROOT, "universal-metal-flash-attention_b200", "lib")
+    src = tmp_path / "consumer.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "mfa_ffi.h"
+int main(void) {
+  int major = -1, minor = -1, patch = -1;
+  mfa_get_version(&major, &minor, &patch);
+  if (major != 1 || minor != 0 || patch != 0) return 10;
+  char* s = (char*)mfa_error_string(MFA_ERROR_INVALID_ARGS);
+  if (!s || strcmp(s, "Invalid arguments") != 0) return 11;
+  free(s);                                             /* strdup'd by the library: the caller frees */
+  mfa_context_t ctx = NULL;
+  mfa_error_t rc = mfa_create_context(&ctx);
+  if (mfa_is_device_supported()) {
+    if (rc != MFA_SUCCESS || !ctx) return 12;
+    mfa_buffer_t b = NULL;
+    if (mfa_create_buffer(ctx, 1024, &b) != MFA_SUCCESS || !mfa_buffer_contents(b)) return 13;
+    mfa_destroy_buffer(b);
+    mfa_destroy_context(ctx);
+  } else if (rc != MFA_ERROR_DEVICE_NOT_SUPPORTED) {
+    return 14;
+  }
+  if (mfa_attention_forward(NULL, NULL, NULL, NULL, NULL, 1, 1, 1, 1, 8, 1.0f, false, MFA_PRECISION_FP32, MFA_PRECISION_FP32,
+                            MFA_PRECISION_FP32, false, false, false, false, NULL, 0, NULL, NULL, 0, MFA_MASK_TYPE_NONE,
+                            MFA_MASK_SCALAR_BYTE) != MFA_ERROR_INVALID_ARGS) return 15;
+  puts("c consumer ok");
+  return 0;
+}
+''')
+    exe = tmp_path / "consumer"
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", INCLUDE, str(src), "-o", str(exe), "-L", lib_dir,
+                    "-lMFAFFI", "-Wl,-rpath," + lib_dir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "c consumer ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
