@@ -314,6 +314,17 @@ void oracle_round_bf16(const float* in, float* out, uint16_t* bits_out, long n) 
   }
 }
 
+/* bench.py --impl reference: torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm asks for all host
+ * cores explicitly so the CPU baseline is not a one-thread strawman. */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  extern void omp_set_num_threads(int);
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   extern int omp_get_max_threads(void);

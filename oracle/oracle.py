@@ -55,6 +55,8 @@ def lib():
         L.oracle_round_bf16.argtypes = [fp, fp, ctypes.POINTER(ctypes.c_uint16), l]
         L.oracle_round_bf16.restype = None
         L.oracle_num_threads.restype = i
+        L.oracle_set_num_threads.argtypes = [i]
+        L.oracle_set_num_threads.restype = None
         _lib = L
     return _lib
 
@@ -69,6 +71,12 @@ def _f32c(a):
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP thread count of the oracle (bench.py's reference arm: all host cores, whatever OMP_NUM_THREADS says)."""
+    lib().oracle_set_num_threads(int(n))
+    return num_threads()
 
 
 def attention_forward(q, k, v, *, scale=None, causal=False, window=-1, mask=None, mask_mode=0):

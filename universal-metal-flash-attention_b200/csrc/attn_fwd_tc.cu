@@ -170,6 +170,9 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
   auto o_empty = [&](int t) { return sBar + 112 + 16 * NS + 32 + 8 * t; };   // softmax warps: O_t left TMEM (epilogue read it)
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
+  // MFA_FWD_CTATRACE (debug build of the launch only): per-CTA wall-clock stamps written by thread 0
+  unsigned long long* ct = nullptr;
+  if constexpr (TR) { if (p.cta_trace && threadIdx.x == 0) { ct = p.cta_trace + (size_t)blockIdx.x * 16; ct[0] = globaltimer_ns(); ct[7] = clock64(); ct[6] = smid(); } }
   // Work items = (batch, head, 256-row query block), x fastest so the CTAs of one head run together (K/V stay in L2).
   // The grid is either one CTA per item or -- persistent mode, uniform-cost problems -- one CTA per SM striding over the
   // items: the producer then prefetches the next item's Q/K/V and the MMA warps start its first S while the softmax warps
@@ -223,6 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw)), 0);
+  if (TR && ct) ct[1] = globaltimer_ns();
 
   if (warp == 9) {
     // ------------------------------------------------------------------ TMA producer
@@ -412,6 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         ++pc;
         tc_fence_after();
         if (TR && tr) tr[0] = clock64();
+        if (TR && ct && it == 0 && w == (int)blockIdx.x) ct[2] = globaltimer_ns();
         uint32_t su[128];
         tmem_ld_x32(tS, su);
         tmem_ld_x32(tS + 32, su + 32);
@@ -559,11 +564,13 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         l += sum_lo * iv0 + sum_hi * iv1;
       }
       // ---------------------------------------------------------------- epilogue: O / l, L = m + log2(l)
+      if (TR && ct && w == (int)blockIdx.x) ct[3] = globaltimer_ns();
       if (n > 0) {
         mbar_wait(o_full(t), qc & 1);
         ++qc;
         tc_fence_after();
       }
+      if (TR && ct && w == (int)blockIdx.x) ct[4] = globaltimer_ns();
       float inv = (l > 0.f ? 1.f / l : 0.f) * ((I8 && !v_blocks) ? p.vs1 : 1.f);
       const bool live = r < p.Sq && !p.debug_skip_store;
       const size_t orow = (size_t)b * p.o_sb + (size_t)h * p.o_sh + (size_t)r * p.o_ss;
@@ -691,6 +698,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         }
       }
       if (live && p.lse) p.lse[lrow] = l_out;
+      if (TR && ct && w == (int)blockIdx.x) { ct[5] = globaltimer_ns(); ct[8] = clock64(); }
     }
     }   // items
   }
@@ -699,6 +707,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (TR && ct) ct[9] = globaltimer_ns();
   if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
@@ -803,6 +812,34 @@ cudaError_t launch_k(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
 // MFA_FWD_TRACE=<file>: run the instrumented build of the D=128 kernel and dump the clock64 timeline of CTA (0,0,0)
 // (rows: tile, step; 16 stamps: 0 S ready, 1 S in registers, 2 max done, 3-6 P part published, 8-11 part seen by the
 // MMA warp, 12 next S issued, 13 V tile landed, 14 K tile landed).  Debug aid; synchronises the stream.
+// MFA_FWD_CTATRACE=<file>: same instrumented build, per-CTA stamps (globaltimer ns: 0 entry, 1 set-up done, 2 first S seen,
+// 3 main loop done, 4 last P V retired, 5 epilogue done, 9 CTA end; 6 = SM id; 7 / 8 = clock64 at entry / epilogue end).
+template <int MODE, int POLY>
+cudaError_t launch_cta_traced(FwdTcParams prm, dim3 grid, cudaStream_t st, const char* path) {
+  const size_t words = (size_t)grid.x * 16;
+  unsigned long long* dev = nullptr;
+  if (cudaMalloc(&dev, words * 8) != cudaSuccess) return cudaErrorMemoryAllocation;
+  cudaMemsetAsync(dev, 0, words * 8, st);
+  prm.cta_trace = dev;
+  auto kern = fwd_tc_kernel<128, MODE, POLY, true>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128, MODE>::kSmem);
+  kern<<<grid, kThreads, Cfg<128, MODE>::kSmem, st>>>(prm);
+  cudaError_t e = cudaStreamSynchronize(st);
+  unsigned long long* host = (unsigned long long*)malloc(words * 8);
+  cudaMemcpy(host, dev, words * 8, cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (FILE* f = fopen(path, "w")) {
+    for (unsigned c = 0; c < grid.x; ++c) {
+      fprintf(f, "%u", c);
+      for (int k = 0; k < 10; ++k) fprintf(f, " %llu", host[(size_t)c * 16 + k]);
+      fprintf(f, "\n");
+    }
+    fclose(f);
+  }
+  free(host);
+  return e;
+}
+
 template <int MODE, int POLY>
 cudaError_t launch_traced(FwdTcParams prm, dim3 grid, cudaStream_t st, const char* path) {
   constexpr size_t kWords = 2 * 64 * 16;
@@ -856,6 +893,8 @@ cudaError_t launch(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
   if constexpr (D == 128 && MODE != kFwdF16) {
     if (const char* path = getenv("MFA_FWD_TRACE"))
       return poly_setting() == 2 ? launch_traced<MODE, 2>(prm, grid, st, path) : launch_traced<MODE, 0>(prm, grid, st, path);
+    if (const char* path = getenv("MFA_FWD_CTATRACE"))
+      return poly_setting() == 3 ? launch_cta_traced<MODE, 3>(prm, grid, st, path) : launch_cta_traced<MODE, 0>(prm, grid, st, path);
   }
   switch (poly_setting()) {
     case 1: return launch_k<D, MODE, 1>(prm, grid, st);

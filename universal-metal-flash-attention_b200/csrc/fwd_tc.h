@@ -43,6 +43,7 @@ struct FwdTcParams {
   int debug_skip_store;                                 // MFA_DEBUG_SKIP_STORE: epilogue writes nothing (timing experiments)
   int pingpong;                                         // exp2 turn-taking between the two tiles (MFA_FWD_PINGPONG, default 1)
   unsigned long long* trace;                            // debug timeline buffer (MFA_FWD_TRACE), normally null
+  unsigned long long* cta_trace;                        // debug per-CTA wall-clock stamps (MFA_FWD_CTATRACE), normally null
 };
 
 int fwd_tc_pingpong();

@@ -286,3 +286,36 @@ class CudaBackend:
 
     def finish(self):
         pass
+
+
+# ------------------------------------------------------------------------------------------------ runners (bench / adapters)
+class PythonRingRunner:
+    """Ring forward driven from Python: `ring_attention_forward` over `CudaBackend` (torch.distributed P2P for the hops)."""
+    kind = "python driver (umfa/ring.py) over mfa_attention_forward_accumulate"
+    transport = "NCCL send/recv (torch.distributed.batch_isend_irecv)"
+
+    def __init__(self, ctx, dist, device, dtype, rank, world):
+        self.be = CudaBackend(ctx, dist if world > 1 else None, device, dtype)
+        self.rank, self.world = rank, world
+
+    @property
+    def launches(self):
+        return self.be.launches
+
+    def forward(self, q_pair, k_pair, v_pair, scale):
+        return ring_attention_forward(self.be, q_pair, k_pair, v_pair, self.rank, self.world, scale)
+
+    def close(self):
+        pass
+
+
+def make_runner(ctx, dist, device, dtype, rank, world, prefer_native=True):
+    """The ring driver bench.py and the adapters use: the native one (libMFAFFI's mfa_ring_* symbols: C++ step loop,
+    ncclSend / ncclRecv on a side stream) when the library has it and NCCL can be loaded, else the Python driver."""
+    if prefer_native:
+        try:
+            from .ring_native import NativeRingRunner
+            return NativeRingRunner(ctx, dist, device, dtype, rank, world)
+        except Exception:
+            pass
+    return PythonRingRunner(ctx, dist, device, dtype, rank, world)
