@@ -115,7 +115,8 @@ int32_t mfa_quantized_backward(
 int32_t mfa_hadamard_rotate(mfa_buffer_t data, uint32_t block_size, uint32_t num_blocks);
 
 /* bridge:2286 -- interleaved-pair RoPE encoded on a caller stream (command_buffer = cudaStream_t); buffers are
- * device pointers with byte offsets; strides in elements; cos/sin tables [S, D/2] fp32. */
+ * device pointers with byte offsets; strides in elements; cos/sin tables fp32, pair-duplicated [S, D] (or [B, S, D]):
+ * element b * table_batch_stride + s * D + 2 * pair is read, table_batch_stride = 0 or S * D (bridge:282,305). */
 int mfa_rope_rotate_encode_mtl(
     mfa_context_t context, void* command_buffer,
     void* src, int64_t src_offset, int64_t src_stride_b, int64_t src_stride_h, int64_t src_stride_s,

@@ -314,6 +314,27 @@ void oracle_round_bf16(const float* in, float* out, uint16_t* bits_out, long n) 
   }
 }
 
+/* Interleaved-pair rotary embedding (Sources/MFABridge/MFABridge.swift:269-319, ROPE_KERNEL): for every pair i of a row,
+ *   out[2i] = x[2i] c - x[2i+1] s,  out[2i+1] = x[2i+1] c + x[2i] s,  c / s = table[b * table_batch_stride + s * D + 2i]
+ * (pair-duplicated fp32 tables, only the even entry is read; table_batch_stride = 0 or S * D); negate_sin = the inverse
+ * rotation = the backward transform of dQ / dK.  src / dst contiguous [B, H, S, D] fp32. */
+void oracle_rope_rotate(const float* src, float* dst, const float* cos_t, const float* sin_t, long B, long H, long S, long D,
+                        long table_batch_stride, int negate_sin) {
+  for (long b = 0; b < B; ++b)
+    for (long h = 0; h < H; ++h)
+      for (long s = 0; s < S; ++s)
+        for (long pair = 0; pair < D / 2; ++pair) {
+          const long base = (((b * H + h) * S + s) * D) + 2 * pair;
+          const long t = b * table_batch_stride + s * D + 2 * pair;
+          const float c = cos_t[t];
+          float sn = sin_t[t];
+          if (negate_sin) sn = -sn;
+          const float x0 = src[base], x1 = src[base + 1];
+          dst[base] = x0 * c - x1 * sn;
+          dst[base + 1] = x1 * c + x0 * sn;
+        }
+}
+
 /* bench.py --impl reference: torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm asks for all host
  * cores explicitly so the CPU baseline is not a one-thread strawman. */
 void oracle_set_num_threads(int n) {

@@ -55,6 +55,8 @@ def lib():
         L.oracle_round_bf16.argtypes = [fp, fp, ctypes.POINTER(ctypes.c_uint16), l]
         L.oracle_round_bf16.restype = None
         L.oracle_num_threads.restype = i
+        L.oracle_rope_rotate.argtypes = [fp, fp, fp, fp, l, l, l, l, l, i]
+        L.oracle_rope_rotate.restype = None
         L.oracle_set_num_threads.argtypes = [i]
         L.oracle_set_num_threads.restype = None
         _lib = L
@@ -114,6 +116,17 @@ def attention_backward(q, k, v, d_o, *, scale=None, causal=False, window=-1, mas
                                          int(mask_mode))
     assert rc == 0
     return dq, dk, dv, dt
+
+
+def rope_rotate(x, cos_t, sin_t, negate_sin=False):
+    """Interleaved-pair RoPE of x [B,H,S,D] with pair-duplicated fp32 tables [S,D] or [B,S,D] (MFABridge.swift:269-319)."""
+    x = _f32c(x)
+    B, H, S, D = x.shape
+    cos_t, sin_t = _f32c(cos_t), _f32c(sin_t)
+    stride = S * D if cos_t.ndim == 3 and cos_t.shape[0] == B and B > 1 else 0
+    out = np.empty_like(x)
+    lib().oracle_rope_rotate(_fp(x), _fp(out), _fp(cos_t), _fp(sin_t), B, H, S, D, stride, int(negate_sin))
+    return out
 
 
 def attention_forward_f32(q, k, v):

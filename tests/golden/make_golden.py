@@ -39,10 +39,21 @@ def main():
         ("addmask_fp32", (2, 2, 40, 16), 56, torch.float32, False, "add", None, True),
         ("bf16_d128", (1, 2, 160, 128), 160, torch.bfloat16, False, None, None, False),
         ("fp16_causal_d64", (1, 2, 130, 64), 130, torch.float16, True, None, None, False),
+        # sliding window (kernel-source rule, AttentionKernel+Softmax.swift:445,450: hidden iff col > row or row > col + W),
+        # handed to torch as the equivalent banded bool mask: the independent cross-check of the window numerics that
+        # upstream's compile-only tests do not give.  meta[2] = W.
+        ("window_fp32", (1, 2, 200, 32), 200, torch.float32, True, ("window", 37), None, True),
+        ("window_bf16_d128", (1, 2, 300, 128), 300, torch.bfloat16, True, ("window", 130), None, False),
     ]
     for name, (B, H, Sq, D), Skv, dtype, causal, mkind, scale, want_grad in cases:
         q, k, v = make_inputs((B, H, Sq, D), (B, H, Skv, D), dtype)
         mask = None
+        window = -1
+        if isinstance(mkind, tuple):
+            window = mkind[1]
+            r, c = torch.arange(Sq)[:, None], torch.arange(Skv)[None, :]
+            mask = ((c <= r) & ~(r > c + window))[None, None]
+            causal = False                      # torch gets the whole rule as a mask; the oracle / kernel get (causal, window)
         if mkind == "bool":
             g = torch.Generator().manual_seed(7)
             mask = torch.rand((1, 1, Sq, Skv), generator=g) > 0.3
@@ -57,9 +68,12 @@ def main():
         out[f"{name}.k"] = k.detach().numpy()
         out[f"{name}.v"] = v.detach().numpy()
         out[f"{name}.o"] = o.detach().numpy()
-        out[f"{name}.meta"] = np.array([int(causal), -1.0 if scale is None else scale], np.float64)
-        if mask is not None:
-            out[f"{name}.mask"] = mask.numpy()
+        if window >= 0:
+            out[f"{name}.meta"] = np.array([1, -1.0 if scale is None else scale, window], np.float64)
+        else:
+            out[f"{name}.meta"] = np.array([int(causal), -1.0 if scale is None else scale], np.float64)
+            if mask is not None:
+                out[f"{name}.mask"] = mask.numpy()
         if want_grad:
             torch.manual_seed(43)
             d_o = torch.randn_like(o) * 0.1

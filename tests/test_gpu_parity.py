@@ -74,6 +74,28 @@ def test_golden_forward(ctx, golden, name):
         assert rel_max(out, ref) < TOL[dtype]
 
 
+@pytest.mark.parametrize("name", ["window_fp32", "window_bf16_d128"])
+def test_golden_sliding_window(ctx, golden, name):
+    """causal + sliding window through mfa_attention_forward_ex / _backward_ex against torch CPU SDPA's banded-mask result"""
+    import umfa
+    q, k, v, ref = (golden[f"{name}.{t}"] for t in "qkvo")
+    _, scale, window = golden[f"{name}.meta"]
+    dtype = "bf16" if "bf16" in name else "fp32"
+    (qa, _), (ka, _), (va, _) = (to_dtype(x, dtype) for x in (q, k, v))
+    out, lse = umfa.flash_attention_forward(ctx, qa, ka, va, input_precision=dtype, output_precision="fp32", layout="bhsd",
+                                            causal=True, window_size=int(window), return_lse=True)
+    if dtype == "fp32":
+        np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-6)
+        d_o = golden[f"{name}.do"]
+        dq, dk, dv, _ = umfa.flash_attention_backward(ctx, d_o, q, k, v, out, lse, input_precision="fp32", causal=True,
+                                                      window_size=int(window))
+        for got, key in ((dq, "dq"), (dk, "dk"), (dv, "dv")):
+            np.testing.assert_allclose(got, golden[f"{name}.{key}"], rtol=1e-4, atol=1e-6)
+    else:
+        assert ctx.last_kernel.startswith("fwd_tc_"), ctx.last_kernel
+        assert rel_max(out, ref) < TOL[dtype]
+
+
 # ---- the reference's 20 ragged (N, D) shapes (SquareAttentionTest.swift:6-25), all six quantities, fp32
 SHAPES = [(10, 3), (10, 80), (8, 2), (9, 2), (23, 2), (24, 2), (25, 2), (192, 77), (192, 80), (93, 32), (99, 35),
           (64, 32), (32, 64), (4, 1), (4, 2), (384, 95), (777, 199), (256, 128), (512, 256), (1, 1)]

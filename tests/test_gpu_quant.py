@@ -145,3 +145,36 @@ def test_hadamard_and_merge(ctx):
         x.close()
     ref, lref = O.attention_forward(q, k, v)
     assert np.abs(o1 - ref).max() < 2e-5 and np.abs(l1 - lref).max() < 1e-4
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("per_batch", [False, True])
+def test_rope_c_symbol_reference_table_contract(ctx, dtype, per_batch):
+    """mfa_rope_rotate_encode_mtl called the way a C / Rust / Swift consumer of the reference ABI calls it: pair-duplicated
+    fp32 [S, D] (or [B, S, D]) tables, table_batch_stride 0 (or S * D), strided source -- against the oracle's restatement of
+    rope_rotate_* (MFABridge.swift:269-319), forward and inverse (negate_sin) rotation."""
+    import ctypes
+    import torch
+    from umfa._ffi import _lib
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(21)
+    B, H, S, D = 2, 3, 50, 64
+    x = rng.standard_normal((B, S, H, D)).astype(np.float32)                 # BSHD storage, handed over with BHSD strides
+    ang = rng.uniform(0, 6.28, (B if per_batch else 1, S, D // 2)).astype(np.float32)
+    cos, sin = np.repeat(np.cos(ang), 2, -1), np.repeat(np.sin(ang), 2, -1)
+    tdt = torch.float32 if dtype == "fp32" else torch.bfloat16
+    xd = torch.from_numpy(x).to(dev).to(tdt)
+    cd, sd = torch.from_numpy(cos).to(dev).contiguous(), torch.from_numpy(sin).to(dev).contiguous()
+    dst = torch.empty(B, H, S, D, device=dev, dtype=tdt)
+    x_bhsd = xd.float().permute(0, 2, 1, 3).contiguous().cpu().numpy()
+    for neg in (False, True):
+        rc = _lib.mfa_rope_rotate_encode_mtl(ctx.handle, None, ctypes.c_void_p(xd.data_ptr()), 0, S * H * D, D, H * D,
+                                             ctypes.c_void_p(dst.data_ptr()), 0, ctypes.c_void_p(cd.data_ptr()), 0,
+                                             ctypes.c_void_p(sd.data_ptr()), 0, S * D if per_batch else 0, neg, B, H, S, D,
+                                             dtype.encode())
+        assert rc == 0
+        torch.cuda.synchronize()
+        ref = O.rope_rotate(x_bhsd, cos if per_batch else cos[0], sin if per_batch else sin[0], negate_sin=neg)
+        got = dst.float().cpu().numpy()
+        tol = 1e-6 if dtype == "fp32" else 1e-2
+        assert np.abs(got - ref).max() <= tol * max(1.0, np.abs(ref).max())

@@ -155,3 +155,31 @@ def test_ring_emulated_on_one_gpu(world):
             assert np.abs(o.cpu().numpy() - ref).max() / np.abs(ref).max() < 2e-2, (r, cid)
             assert np.abs(l.cpu().numpy() - l_ref[:, :, cid * c:(cid + 1) * c]).max() < 2e-2, (r, cid)
     ctx.close()
+
+
+def test_accumulate_many_items_per_cta():
+    """Accumulate mode with more work items than SMs: every persistent CTA merges several items in a row, so the epilogue
+    warpgroup's staging ring, the running-O TMA loads and the TMEM hand-back are exercised across item boundaries."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "universal-metal-flash-attention_b200"))
+    import umfa
+    from umfa import ring
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(5)
+    B, H, T, D, K1, K2, W0 = 1, 20, 4096 + 60, 128, 256, 320, 1024          # ragged last query block on purpose
+    q = rng.standard_normal((B, H, T, D)).astype(np.float32)
+    k = rng.standard_normal((B, H, K1 + K2, D)).astype(np.float32)
+    v = rng.standard_normal((B, H, K1 + K2, D)).astype(np.float32)
+    ctx = umfa.MFAContext()
+    be = ring.CudaBackend(ctx, None, dev, "bf16")
+    qd, kd, vd = (_bf16_dev(x, dev) for x in (q, k, v))
+    acc = be.attend(qd, kd[:, :, :K1], vd[:, :, :K1], False, 1.0 / np.sqrt(D))
+    be.attend_accumulate(acc, W0, qd[:, :, W0:], kd[:, :, K1:], vd[:, :, K1:], False, 1.0 / np.sqrt(D))
+    be.attend_accumulate(acc, 0, qd[:, :, :W0], kd[:, :, K1:], vd[:, :, K1:], False, 1.0 / np.sqrt(D))
+    torch.cuda.synchronize(dev)
+    o, l = acc[0].cpu().numpy(), acc[1].cpu().numpy()
+    o_ref, l_ref = O.attention_forward(*(O.round_bf16(x)[0] for x in (q, k, v)))
+    assert np.isfinite(o).all()
+    assert np.abs(o - o_ref).max() / np.abs(o_ref).max() < 2e-2
+    assert np.abs(l - l_ref).max() < 2e-2
+    ctx.close()

@@ -120,3 +120,66 @@ def test_tcq_int8_with_additive_mask(ctx, mode, kind):
     assert np.isfinite(out).all()
     assert float(np.abs(out - o_ref).max() / np.abs(o_ref).max()) < 2e-2
     assert np.abs(lse - l_ref).max() < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Config 3 of BASELINE.json at its own size: FLUX sequence length N = 4608, D = 128 (two heads keep the fp64 oracle at a
+# few seconds), through BOTH quantised entry points, against the oracle on the oracle's dequantised operands (2e-2) and
+# against the unquantised oracle (cosine >= 0.99 int8 / 0.95 int4, max-abs stated per case).
+C3_N = 4608
+
+
+def _c3_inputs(seed):
+    rng = np.random.default_rng(seed)
+    return tuple(rng.standard_normal((1, 2, C3_N, 128)).astype(np.float32) for _ in range(3))
+
+
+@pytest.mark.parametrize("target,mode,cos_min,maxabs", [("int8", 2, 0.99, 0.02), ("int8", 0, 0.99, 0.02), ("int4", 2, 0.95, 0.12)])
+def test_c3_flux_size_runtime_quantised(ctx, target, mode, cos_min, maxabs):
+    """mfa_quantized_forward_with_lse at N = 4608: runtime quantise (per tensor / blocks of 64 tokens) + tensor-core kernel."""
+    import umfa
+    q, k, v = _c3_inputs(11)
+    bits = 8 if target == "int8" else 4
+    out, lse = umfa.runtime_quantized_attention(ctx, q, k, v, target_precision=target, quant_mode=mode, input_precision="fp32")
+    assert ctx.last_kernel.startswith("fwd_tcq_"), ctx.last_kernel
+    qd, kd, vd = (fake_quant(x, bits, mode, 128) for x in (q, k, v))
+    o_ref, l_ref = O.attention_forward(qd, kd, vd)
+    assert np.isfinite(out).all()
+    err = float(np.abs(out - o_ref).max() / np.abs(o_ref).max())
+    assert err < 2e-2, f"vs the oracle on dequantised operands: {err}"
+    assert np.abs(lse - l_ref).max() < 2e-2
+    o_full, _ = O.attention_forward(q, k, v)
+    cs, ma = cosine(out, o_full), float(np.abs(out - o_full).max())
+    assert cs >= cos_min and ma < maxabs, (cs, ma)
+
+
+@pytest.mark.parametrize("bits", [8, 4])
+def test_c3_flux_size_prequantised_entry_point(ctx, bits):
+    """mfa_attention_forward_quantized at N = 4608: caller-supplied int8 / packed int4 codes, per-tensor scales."""
+    import umfa
+    from umfa._ffi import _lib, _check_error
+    q, k, v = _c3_inputs(12)
+    B, H, S, D = q.shape
+    prec = 3 if bits == 8 else 4
+    codes, scales, deq = [], [], []
+    for x in (q, k, v):
+        c, s = O.quantize(x.reshape(-1, D), bits=bits, clamp_scale_min=1e-8)
+        codes.append(np.ascontiguousarray(c))
+        scales.append(float(s[0]))
+        deq.append(O.dequantize(c, s, B * H * S, D, bits=bits).reshape(x.shape))
+    out = np.zeros((B, H, S, D), np.float32)
+    bufs = [umfa.MFABuffer(ctx, a) for a in codes] + [umfa.MFABuffer(ctx, out)]
+    try:
+        _check_error(_lib.mfa_attention_forward_quantized(
+            ctx.handle, *[b.handle for b in bufs], B, S, S, H, D, 1.0 / np.sqrt(D), False,
+            scales[0], 0, scales[1], 0, scales[2], 0, prec, prec, prec, 2, False, False, False, False))
+    finally:
+        for b in bufs:
+            b.close()
+    assert ctx.last_kernel.startswith("fwd_tcq_"), ctx.last_kernel
+    o_ref, _ = O.attention_forward(*deq)
+    assert np.isfinite(out).all()
+    assert float(np.abs(out - o_ref).max() / np.abs(o_ref).max()) < 2e-2
+    o_full, _ = O.attention_forward(q, k, v)
+    cs = cosine(out, o_full)
+    assert cs >= (0.99 if bits == 8 else 0.95), cs

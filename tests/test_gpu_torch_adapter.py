@@ -204,6 +204,41 @@ def test_rope_sdpa_and_hadamard(torch_mod, adapter):
     assert relmax(y2, x) < 1e-5 and abs(float(y.norm() / x.norm()) - 1.0) < 1e-5
 
 
+def test_rope_sdpa_gradients(torch_mod, adapter):
+    """rope_scaled_dot_product_attention under autograd: dQ / dK come back through the inverse rotation (negate_sin), dV
+    straight from the attention backward -- against torch autograd of the same formula, and dQ against the CPU oracle."""
+    from oracle import oracle as O
+    torch = torch_mod
+    p, ext = adapter
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, H, S, D = 2, 2, 96, 64
+    q, k, v = (torch.randn(B, H, S, D, device="cuda", generator=g).requires_grad_(True) for _ in range(3))
+    d_o = torch.randn(B, H, S, D, device="cuda", generator=g)
+    ang = torch.rand(B, S, D // 2, device="cuda", generator=g) * 6.28
+    cos, sin = ang.cos().repeat_interleave(2, -1), ang.sin().repeat_interleave(2, -1)      # per-batch pair-duplicated [B, S, D]
+
+    def rot(x):
+        x0, x1 = x[..., 0::2], x[..., 1::2]
+        c, s = ang.cos()[:, None], ang.sin()[:, None]
+        return torch.stack((x0 * c - x1 * s, x0 * s + x1 * c), -1).flatten(-2)
+    out = ext.rope_scaled_dot_product_attention(q, k, v, cos, sin, is_causal=True)
+    out.backward(d_o)
+    got = [t.grad.clone() for t in (q, k, v)]
+    for t in (q, k, v):
+        t.grad = None
+    ref = ref_sdpa(torch, rot(q), rot(k), v, causal=True)
+    ref.backward(d_o)
+    assert relmax(out, ref) < 1e-5
+    for a, t in zip(got, (q, k, v)):
+        assert relmax(a, t.grad) < 1e-4
+    # the oracle: rotate on the CPU, attention backward, inverse rotation of dQ
+    qn, kn, vn, dn = (t.detach().cpu().numpy() for t in (q, k, v, d_o))
+    cn, sn = cos.cpu().numpy(), sin.cpu().numpy()
+    rq, rk, _, _ = O.attention_backward(O.rope_rotate(qn, cn, sn), O.rope_rotate(kn, cn, sn), vn, dn, causal=True)
+    dq_ref = O.rope_rotate(rq, cn, sn, negate_sin=True)
+    assert float(np.abs(got[0].cpu().numpy() - dq_ref).max() / np.abs(dq_ref).max()) < 1e-4
+
+
 def test_unsupported_inputs_fall_back_or_raise(torch_mod, adapter):
     torch = torch_mod
     p, ext = adapter

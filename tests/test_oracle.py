@@ -120,6 +120,20 @@ def test_oracle_vs_golden_backward(golden, name):
         np.testing.assert_allclose(got, golden[f"{name}.{key}"], rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["window_fp32", "window_bf16_d128"])
+def test_oracle_sliding_window_vs_torch_golden(golden, name):
+    """causal + sliding window (AttentionKernel+Softmax.swift:445,450) against torch CPU SDPA fed the equivalent banded
+    bool mask (tests/golden/make_golden.py): pins the window numerics that upstream's own tests only compile."""
+    q, k, v, ref = (golden[f"{name}.{t}"] for t in "qkvo")
+    causal, scale, window = golden[f"{name}.meta"]
+    o, _ = O.attention_forward(q, k, v, causal=bool(causal), window=int(window))
+    np.testing.assert_allclose(o, ref, rtol=1e-5, atol=1e-6)
+    if f"{name}.do" in golden:
+        dq, dk, dv, _ = O.attention_backward(q, k, v, golden[f"{name}.do"], causal=bool(causal), window=int(window))
+        for got, key in ((dq, "dq"), (dk, "dk"), (dv, "dv")):
+            np.testing.assert_allclose(got, golden[f"{name}.{key}"], rtol=1e-4, atol=1e-6)
+
+
 def test_mask_rules_causal_window():
     # AttentionKernel+Softmax.swift:445,450: causal masks col > row; window masks row > col + W
     rng = np.random.default_rng(1)
@@ -229,3 +243,21 @@ def test_division_free_code_rule_is_bit_exact():
         near = (np.abs(fr - np.float32(0.5)) < np.float32(1e-4)) | ~(np.abs(t) < 1024)
         r = np.clip(np.where(near, half_away(qd), r), -128, 127)
         assert np.array_equal(r, exact), trial
+
+
+def test_rope_oracle_is_orthonormal_and_matches_formula():
+    """oracle_rope_rotate (MFABridge.swift:269-319): formula check, shared vs per-batch tables, inverse = negate_sin."""
+    rng = np.random.default_rng(0)
+    B, H, S, D = 2, 3, 7, 10
+    x = rng.standard_normal((B, H, S, D)).astype(np.float32)
+    ang = rng.uniform(0, 6.28, (B, S, D // 2)).astype(np.float32)
+    cos, sin = np.repeat(np.cos(ang), 2, -1), np.repeat(np.sin(ang), 2, -1)
+    y = O.rope_rotate(x, cos, sin)
+    x0, x1 = x[..., 0::2], x[..., 1::2]
+    c, s = np.cos(ang)[:, None], np.sin(ang)[:, None]
+    ref = np.stack((x0 * c - x1 * s, x0 * s + x1 * c), -1).reshape(x.shape)
+    np.testing.assert_allclose(y, ref, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(O.rope_rotate(y, cos, sin, negate_sin=True), x, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(np.linalg.norm(y, axis=-1), np.linalg.norm(x, axis=-1), rtol=1e-5)
+    y1 = O.rope_rotate(x, cos[0], sin[0])                  # one [S, D] table shared by the batch
+    np.testing.assert_allclose(y1[1], O.rope_rotate(x[1:], cos[0], sin[0])[0], rtol=0, atol=0)

@@ -27,8 +27,30 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _extra_flags(stamp):
+    """MFA_WATCHDOG=1 in the environment of the BUILD compiles the mbarrier wall-clock watchdog in (sm100_ptx.cuh: a
+    protocol bug traps instead of hanging the GPU); MFA_WATCHDOG=0 builds the release library, which spins without a
+    limit.  With the variable unset an existing library keeps the mode it was built in (no surprise rebuilds on the GPU
+    box); a fresh tree builds release."""
+    want = os.environ.get("MFA_WATCHDOG")
+    if want is None:
+        try:
+            return ["-DMFA_MBAR_WATCHDOG"] if "-DMFA_MBAR_WATCHDOG" in open(stamp).read() else []
+        except OSError:
+            return []
+    return ["-DMFA_MBAR_WATCHDOG"] if want not in ("", "0") else []
+
+
 def build(force=False, verbose=False):
     os.makedirs(OUT_DIR, exist_ok=True)
+    stamp = os.path.join(OUT_DIR, "build_flags.txt")
+    extra = _extra_flags(stamp)
+    want = " ".join(FLAGS + extra)
+    have = open(stamp).read() if os.path.exists(stamp) else None
+    if have is None and os.path.exists(LIB) and not extra:
+        have = want                      # a library built before the stamp existed: release flags
+    if have != want:
+        force = True
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers += [os.path.join(HERE, "..", "include", f) for f in ("mfa_ffi.h", "mfa_ffi_ext.h")]
     objs = []
@@ -38,7 +60,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
@@ -51,6 +73,8 @@ def build(force=False, verbose=False):
     if force or procs or _stale(LIB, objs + [os.path.join(CSRC, "exports.map")]):
         cmd = [NVCC, "-shared", "--cudart", "static", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs + ["-ldl", "-lpthread", "-lrt", "-Xlinker", "--version-script=" + os.path.join(CSRC, "exports.map")]
         subprocess.run(cmd, check=True)
+    with open(stamp, "w") as f:
+        f.write(want)
     return LIB
 
 

@@ -34,16 +34,24 @@ bool g_debug = false;
 struct Scratch {
   void* ptr = nullptr;
   size_t cap = 0;
+  // cross-stream ordering: the stream that used the block last and an event recorded behind that use (ScratchScope)
+  cudaEvent_t ev = nullptr;
+  cudaStream_t last = nullptr;
+  bool used = false;
   void* get(size_t bytes) {
     if (bytes <= cap) return ptr;
-    if (ptr) cudaFree(ptr);
-    ptr = nullptr; cap = 0;
+    if (ptr) cudaFree(ptr);            // implicitly waits for everything that may still read the old block
+    ptr = nullptr; cap = 0; used = false;
     size_t want = bytes + (bytes >> 2) + 256;
     if (cudaMalloc(&ptr, want) != cudaSuccess) { ptr = nullptr; cudaGetLastError(); return nullptr; }
     cap = want;
     return ptr;
   }
-  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    if (ev) cudaEventDestroy(ev);
+    ptr = nullptr; cap = 0; ev = nullptr; used = false;
+  }
 };
 
 struct Context {
@@ -55,7 +63,7 @@ struct Context {
   std::vector<cudaEvent_t> ev_in, ev_k0, ev_k1;
   double last_latency = 0.0;
   int refs = 0;
-  std::mutex mu;
+  std::recursive_mutex mu;          // recursive: mfa_quantized_backward holds it across quantise + backward_core
   enum { kMask, kLse, kDterm, kQCodes, kKCodes, kVCodes, kQScales, kKScales, kVScales, kTmpO, kQTmp, kMaskTiles, kNumScratch };
   Scratch scratch[kNumScratch];
   std::vector<float> row_scales[3];
@@ -63,10 +71,58 @@ struct Context {
 };
 
 std::mutex g_ctx_mu;
-Context* g_ctx = nullptr;          // retained singleton (MFABridge.swift:652-687)
+constexpr int kMaxDevices = 64;
+Context* g_ctxs[kMaxDevices] = {nullptr};   // one retained singleton per device (MFABridge.swift:652-687 keeps one per process:
+                                            // a single-process host selects the device of the next create with mfa_set_device)
 int g_device_request = -1;
 
+int requested_device() {
+  if (g_device_request >= 0) return g_device_request;
+  if (const char* e = getenv("MFA_CUDA_DEVICE")) return atoi(e);
+  return 0;
+}
+
+// Every entry point runs on its context's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Scratch blocks are shared by every call on a context.  Calls on different streams are ordered through an event recorded
+// behind each use: a later call on another stream waits for it before touching the block (a blocking call could
+// overwrite scratch an earlier async kernel was still reading).
+struct ScratchScope {
+  Context* ctx; cudaStream_t st;
+  std::vector<int> slots;
+  ScratchScope(Context* c, cudaStream_t s) : ctx(c), st(s) {}
+  void* take(int slot, size_t bytes);
+  ~ScratchScope();
+};
+
+void* ScratchScope::take(int slot, size_t bytes) {
+  Scratch& sc = ctx->scratch[slot];
+  void* p = sc.get(bytes);
+  if (!p) return nullptr;
+  if (sc.used && sc.last != st && sc.ev) cudaStreamWaitEvent(st, sc.ev, 0);
+  slots.push_back(slot);
+  return p;
+}
+ScratchScope::~ScratchScope() {
+  for (int slot : slots) {
+    Scratch& sc = ctx->scratch[slot];
+    if (!sc.ev && cudaEventCreateWithFlags(&sc.ev, cudaEventDisableTiming) != cudaSuccess) { sc.ev = nullptr; cudaGetLastError(); continue; }
+    cudaEventRecord(sc.ev, st);
+    sc.last = st; sc.used = true;
+  }
+}
+
 struct Buffer {
+  Context* owner = nullptr;
   void* host = nullptr;   // CPU-dereferenceable pointer (may be null for pure device views)
   void* dev = nullptr;    // device pointer used by kernels
   size_t bytes = 0;
@@ -76,19 +132,23 @@ struct Buffer {
   int64_t shape[4] = {0, 0, 0, 0}, strides[4] = {0, 0, 0, 0};
 };
 
-bool device_ok() {
-  static int cached = -1;
-  if (cached >= 0) return cached == 1;
-  int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); cached = 0; return false; }
-  int dev = g_device_request >= 0 ? g_device_request : 0;
-  if (const char* e = getenv("MFA_CUDA_DEVICE")) { if (g_device_request < 0) dev = atoi(e); }
-  if (dev >= n) { cached = 0; return false; }
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); cached = 0; return false; }
-  cached = (prop.major == 10) ? 1 : 0;   // kernels are built for sm_100a only
-  return cached == 1;
+bool device_ok(int dev) {
+  static int cached[kMaxDevices];        // 0 unknown, 1 yes, 2 no
+  static std::mutex mu;
+  if (dev < 0 || dev >= kMaxDevices) return false;
+  std::lock_guard<std::mutex> lock(mu);
+  if (cached[dev]) return cached[dev] == 1;
+  int n = 0, major = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || dev >= n ||
+      cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    cudaGetLastError();
+    cached[dev] = 2;
+    return false;
+  }
+  cached[dev] = (major == 10) ? 1 : 2;   // kernels are built for sm_100a only
+  return cached[dev] == 1;
 }
+bool device_ok() { return device_ok(requested_device()); }
 
 inline mfa_error_t cuda_fail(cudaError_t e, const char* what) {
   DBG("%s: %s", what, cudaGetErrorString(e));
@@ -147,13 +207,31 @@ TensorView view_of(Buffer* b, int64_t H, int64_t S, int64_t D, bool transposed) 
   return t;
 }
 
+// Does the handle cover a [B, H, S, D] operand of `esz`-byte elements?  Plain handles need B*H*S*D elements; handles made
+// *_with_strides must carry exactly that shape (3-D handles: [H, S, D], batch 1) and their furthest element must lie inside.
+bool view_fits(const Buffer* b, uint64_t B, uint64_t H, uint64_t S, uint64_t D, size_t esz) {
+  if (!b) return false;
+  if (b->ndim == 0) return b->bytes >= B * H * S * D * esz;
+  const uint64_t want4[4] = {B, H, S, D};
+  const uint64_t* want = b->ndim == 4 ? want4 : want4 + 1;
+  if (b->ndim != 4 && b->ndim != 3) return false;
+  if (b->ndim == 3 && B != 1) return false;
+  uint64_t last = 0;
+  for (int i = 0; i < b->ndim; ++i) {
+    if (b->shape[i] != (int64_t)want[i] || b->strides[i] < 0) return false;
+    if (want[i] == 0) return true;
+    last += (want[i] - 1) * (uint64_t)b->strides[i];
+  }
+  return (last + 1) * esz <= b->bytes;
+}
+
 struct MaskArgs {
   const void* ptr; size_t bytes; const int64_t* shape; const int64_t* strides; uint32_t ndim; int type; int scalar;
 };
 
 // Resolve mask metadata into broadcast strides over [B,H,Sq,Skv] (right-aligned, size-1 dims broadcast:
 // MFABridge.swift:186-198).  Host masks are copied into device scratch.  Returns 0 / error code.
-mfa_error_t setup_mask(Context* ctx, cudaStream_t st, const MaskArgs& m, AttnParams& p) {
+mfa_error_t setup_mask(ScratchScope& scope, cudaStream_t st, const MaskArgs& m, AttnParams& p) {
   p.mask = nullptr; p.mask_kind = kMaskNone; p.mask_scalar = kMaskU8;
   p.mask_sb = p.mask_sh = p.mask_sq = p.mask_sk = 0;
   if (m.type == MFA_MASK_TYPE_NONE || !m.ptr || m.bytes == 0 || m.ndim == 0) return MFA_SUCCESS;
@@ -183,7 +261,7 @@ mfa_error_t setup_mask(Context* ctx, cudaStream_t st, const MaskArgs& m, AttnPar
   cudaGetLastError();
   const void* dptr = m.ptr;
   if (!on_device) {
-    void* s = ctx->scratch[Context::kMask].get(m.bytes);
+    void* s = scope.take(Context::kMask, m.bytes);
     if (!s) return MFA_ERROR_MEMORY_ALLOCATION;
     if (cudaMemcpyAsync(s, m.ptr, m.bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return MFA_ERROR_EXECUTION_FAILED;
     dptr = s;
@@ -331,8 +409,9 @@ mfa_error_t forward_core(Context* ctx, const FwdArgs& a) {
   if (!device_ok()) return MFA_ERROR_DEVICE_NOT_SUPPORTED;
   const size_t nq = elems(a.B, a.H, a.Sq, a.D), nkv = elems(a.B, a.H, a.Skv, a.D);
   const size_t esz = dtype_bytes(a.in_dtype);
-  const bool strided = a.q->ndim || a.k->ndim || a.v->ndim;
-  if (!strided && (a.q->bytes < nq * esz || a.k->bytes < nkv * esz || a.v->bytes < nkv * esz)) return MFA_ERROR_INVALID_ARGS;
+  if (!view_fits(a.q, a.B, a.H, a.Sq, a.D, esz) || !view_fits(a.k, a.B, a.H, a.Skv, a.D, esz) ||
+      !view_fits(a.v, a.B, a.H, a.Skv, a.D, esz))
+    return MFA_ERROR_INVALID_ARGS;
   // O is fp32 (reference contract) unless the handle only fits the requested lower precision.
   int o_dtype = kF32;
   if (a.out->bytes < nq * 4) {
@@ -343,10 +422,22 @@ mfa_error_t forward_core(Context* ctx, const FwdArgs& a) {
   if (a.async && (a.q->mirrored || a.k->mirrored || a.v->mirrored || a.out->mirrored || (a.lse && a.lse->mirrored)))
     return MFA_ERROR_INVALID_ARGS;
 
-  std::lock_guard<std::mutex> lock(ctx->mu);
-  cudaSetDevice(ctx->device);
-  if (nq != 0 && nkv != 0 && forward_pipeline_ok(a, o_dtype)) return forward_pipelined(ctx, a, o_dtype);
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  DeviceGuard dg(ctx->device);
+  if (nq != 0 && nkv != 0 && forward_pipeline_ok(a, o_dtype)) {
+    // the pipeline only drives the tensor-core kernel: probe eligibility on one head's worth of the problem first and take
+    // the single-shot path (which may route to the exact SIMT kernel) when it does not apply
+    AttnParams probe;
+    init_params(probe, 1, 1, a.Sq, a.Skv, a.D, a.scale, a.causal, a.window);
+    probe.q = contiguous_view(a.q->dev, 1, a.Sq, a.D, false);
+    probe.k = contiguous_view(a.k->dev, 1, a.Skv, a.D, false);
+    probe.v = contiguous_view(a.v->dev, 1, a.Skv, a.D, false);
+    probe.o = contiguous_view(a.out->dev, 1, a.Sq, a.D, false);
+    probe.in_dtype = a.in_dtype; probe.o_dtype = o_dtype;
+    if (fwd_tc_eligible(probe)) return forward_pipelined(ctx, a, o_dtype);
+  }
   cudaStream_t st = a.async ? a.user_stream : ctx->stream;
+  ScratchScope scope(ctx, st);
   Sync sync{ctx, st, a.async, {}};
   cudaError_t e;
   if ((e = sync.in(a.q)) != cudaSuccess || (e = sync.in(a.k)) != cudaSuccess || (e = sync.in(a.v)) != cudaSuccess)
@@ -361,11 +452,11 @@ mfa_error_t forward_core(Context* ctx, const FwdArgs& a) {
   p.o = view_of(a.out, a.H, a.Sq, a.D, a.to);
   p.lse = a.lse ? reinterpret_cast<float*>(a.lse->dev) : nullptr;
   p.in_dtype = a.in_dtype; p.o_dtype = o_dtype;
-  mfa_error_t me = setup_mask(ctx, st, a.mask, p);
+  mfa_error_t me = setup_mask(scope, st, a.mask, p);
   if (me != MFA_SUCCESS) return me;
 
   if (const size_t mb = fwd_tc_mask_scratch_bytes(p))
-    p.mask_tile_scratch = reinterpret_cast<int*>(ctx->scratch[Context::kMaskTiles].get(mb));     // null = no tile skipping
+    p.mask_tile_scratch = reinterpret_cast<int*>(scope.take(Context::kMaskTiles, mb));     // null = no tile skipping
   Timer tm(ctx, st, !a.async);
   if (fwd_tc_eligible(p)) {
     e = launch_fwd_tc(p, st);
@@ -410,9 +501,10 @@ mfa_error_t backward_core(Context* ctx, const BwdArgs& a) {
     return MFA_ERROR_INVALID_ARGS;
   if (a.dbuf && a.dbuf->bytes < rows * 4) return MFA_ERROR_INVALID_ARGS;
 
-  std::lock_guard<std::mutex> lock(ctx->mu);
-  cudaSetDevice(ctx->device);
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  DeviceGuard dg(ctx->device);
   cudaStream_t st = a.async ? a.user_stream : ctx->stream;
+  ScratchScope scope(ctx, st);
   Sync sync{ctx, st, a.async, {}};
   Buffer* ins[] = {a.dout, a.q, a.k, a.v, a.out, a.lse};
   for (Buffer* b : ins) {
@@ -438,14 +530,14 @@ mfa_error_t backward_core(Context* ctx, const BwdArgs& a) {
   p.dv = a.want_dkv ? reinterpret_cast<float*>(a.dv->dev) : nullptr;
   if (a.dbuf) p.dterm = reinterpret_cast<float*>(a.dbuf->dev);
   else {
-    p.dterm = reinterpret_cast<float*>(ctx->scratch[Context::kDterm].get(rows * 4 + 4));
+    p.dterm = reinterpret_cast<float*>(scope.take(Context::kDterm, rows * 4 + 4));
     if (!p.dterm) return MFA_ERROR_MEMORY_ALLOCATION;
   }
-  mfa_error_t me = setup_mask(ctx, st, a.mask, p);
+  mfa_error_t me = setup_mask(scope, st, a.mask, p);
   if (me != MFA_SUCCESS) return me;
 
   if (const size_t mb = bwd_tc_mask_scratch_bytes(p))
-    p.mask_tile_scratch = reinterpret_cast<int*>(ctx->scratch[Context::kMaskTiles].get(mb));     // null = no tile skipping
+    p.mask_tile_scratch = reinterpret_cast<int*>(scope.take(Context::kMaskTiles, mb));     // null = no tile skipping
   Timer tm(ctx, st, !a.async);
   cudaError_t e = cudaSuccess;
   if (bwd_tc_eligible(p)) {
@@ -482,7 +574,7 @@ struct QFwdArgs {
   bool use_row_scales;
 };
 
-mfa_error_t quantise_operand(Context* ctx, cudaStream_t st, const QOperand& op, int which, uint32_t B, uint32_t H,
+mfa_error_t quantise_operand(ScratchScope& scope, cudaStream_t st, const QOperand& op, int which, uint32_t B, uint32_t H,
                              uint32_t S, uint32_t D, int target_dtype, TensorView& view, QuantView& qv, int& dtype_out) {
   const size_t n = elems(B, H, S, D);
   if (op.dtype == kI8 || op.dtype == kI4) {
@@ -504,8 +596,8 @@ mfa_error_t quantise_operand(Context* ctx, cudaStream_t st, const QOperand& op, 
   const uint64_t rows = (uint64_t)B * H * S;
   const uint32_t br = op.block_rows;                          // 0 = per tensor
   const uint64_t nb = br ? (uint64_t)B * H * ((S + br - 1) / br) : 1;
-  void* codes = ctx->scratch[Context::kQCodes + which].get(packed_bytes(n, target_dtype) + 16);
-  float* scales = reinterpret_cast<float*>(ctx->scratch[Context::kQScales + which].get(nb * 4 + 16));
+  void* codes = scope.take(Context::kQCodes + which, packed_bytes(n, target_dtype) + 16);
+  float* scales = reinterpret_cast<float*>(scope.take(Context::kQScales + which, nb * 4 + 16));
   if (!codes || !scales) return MFA_ERROR_MEMORY_ALLOCATION;
   cudaError_t e = launch_quantize_grouped(op.buf->dev, op.dtype, codes, scales, rows, D, br ? br : (uint32_t)0, D,
                                           br ? S : 0, bits, 1e-8f, st);
@@ -534,9 +626,10 @@ mfa_error_t qforward_core(Context* ctx, const QFwdArgs& a) {
   if (a.lse && a.lse->bytes < (size_t)a.B * a.H * a.Sq * 4) return MFA_ERROR_INVALID_ARGS;
   if (a.mask_buf && a.mask_buf->bytes < (size_t)a.B * a.H * a.Sq * a.Skv * 4) return MFA_ERROR_INVALID_ARGS;
 
-  std::lock_guard<std::mutex> lock(ctx->mu);
-  cudaSetDevice(ctx->device);
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  DeviceGuard dg(ctx->device);
   cudaStream_t st = ctx->stream;
+  ScratchScope scope(ctx, st);
   Sync sync{ctx, st, false, {}};
   cudaError_t e;
   if ((e = sync.in(a.q.buf)) != cudaSuccess || (e = sync.in(a.k.buf)) != cudaSuccess ||
@@ -549,9 +642,9 @@ mfa_error_t qforward_core(Context* ctx, const QFwdArgs& a) {
   Timer tm(ctx, st, true);
   int dq_, dk_, dv_;
   mfa_error_t me;
-  if ((me = quantise_operand(ctx, st, a.q, 0, a.B, a.H, a.Sq, a.D, a.target_dtype, p.q, p.qq, dq_)) != MFA_SUCCESS) return me;
-  if ((me = quantise_operand(ctx, st, a.k, 1, a.B, a.H, a.Skv, a.D, a.target_dtype, p.k, p.qk, dk_)) != MFA_SUCCESS) return me;
-  if ((me = quantise_operand(ctx, st, a.v, 2, a.B, a.H, a.Skv, a.D, a.target_dtype, p.v, p.qv, dv_)) != MFA_SUCCESS) return me;
+  if ((me = quantise_operand(scope, st, a.q, 0, a.B, a.H, a.Sq, a.D, a.target_dtype, p.q, p.qq, dq_)) != MFA_SUCCESS) return me;
+  if ((me = quantise_operand(scope, st, a.k, 1, a.B, a.H, a.Skv, a.D, a.target_dtype, p.k, p.qk, dk_)) != MFA_SUCCESS) return me;
+  if ((me = quantise_operand(scope, st, a.v, 2, a.B, a.H, a.Skv, a.D, a.target_dtype, p.v, p.qv, dv_)) != MFA_SUCCESS) return me;
   if (dq_ != dk_ || dk_ != dv_) return MFA_ERROR_INVALID_ARGS;   // callers normalise mixed operands first
   p.in_dtype = dq_;
   if (a.use_row_scales && (dq_ == kI8 || dq_ == kI4)) {
@@ -561,7 +654,7 @@ mfa_error_t qforward_core(Context* ctx, const QFwdArgs& a) {
     const QOperand* ops[3] = {&a.q, &a.k, &a.v};
     for (int i = 0; i < 3; ++i) {
       if ((ops[i]->dtype == kI8 || ops[i]->dtype == kI4) && ctx->row_scales[i].size() == want[i]) {
-        float* s = reinterpret_cast<float*>(ctx->scratch[Context::kQScales + i].get(want[i] * 4));
+        float* s = reinterpret_cast<float*>(scope.take(Context::kQScales + i, want[i] * 4));
         if (!s) return MFA_ERROR_MEMORY_ALLOCATION;
         if ((e = cudaMemcpyAsync(s, ctx->row_scales[i].data(), want[i] * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess)
           return cuda_fail(e, "row scales");
@@ -577,9 +670,9 @@ mfa_error_t qforward_core(Context* ctx, const QFwdArgs& a) {
     p.mask_sk = 1; p.mask_sq = a.Skv; p.mask_sh = (int64_t)a.Sq * a.Skv; p.mask_sb = (int64_t)a.H * a.Sq * a.Skv;
   }
   if (const size_t mb = fwd_tc_mask_scratch_bytes(p))
-    p.mask_tile_scratch = reinterpret_cast<int*>(ctx->scratch[Context::kMaskTiles].get(mb));
+    p.mask_tile_scratch = reinterpret_cast<int*>(scope.take(Context::kMaskTiles, mb));
   if (fwd_tcq_eligible(p)) {
-    void* tmp = ctx->scratch[Context::kQTmp].get(fwd_tcq_scratch_bytes(p));
+    void* tmp = scope.take(Context::kQTmp, fwd_tcq_scratch_bytes(p));
     if (!tmp) return MFA_ERROR_MEMORY_ALLOCATION;
     e = launch_fwd_tcq(p, tmp, st);
   } else {
@@ -600,13 +693,14 @@ mfa_error_t make_buffer(Context* ctx, void* ptr, size_t bytes, bool device_hint,
   if (ndim > 4 || (ndim && (!shape || !strides))) return MFA_ERROR_INVALID_ARGS;
   Buffer* b = new (std::nothrow) Buffer();
   if (!b) return MFA_ERROR_MEMORY_ALLOCATION;
+  b->owner = ctx;
   b->bytes = bytes;
   b->ndim = (int)ndim;
   for (uint32_t i = 0; i < ndim; ++i) { b->shape[i] = shape[i]; b->strides[i] = strides[i]; }
   bool on_device = device_hint;
   bool managed = false;
-  if (device_ok()) {
-    cudaSetDevice(ctx->device);
+  DeviceGuard dg(ctx->device);
+  if (device_ok(ctx->device)) {
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess) {
       if (attr.type == cudaMemoryTypeDevice) on_device = true;
@@ -624,8 +718,9 @@ mfa_error_t make_buffer(Context* ctx, void* ptr, size_t bytes, bool device_hint,
   } else {
     b->host = ptr;
     b->mirrored = true;
-    if (device_ok() && bytes) {
+    if (device_ok(ctx->device) && bytes) {
       if (cudaMalloc(&b->dev, bytes) != cudaSuccess) { cudaGetLastError(); delete b; return MFA_ERROR_MEMORY_ALLOCATION; }
+      cudaMemset(b->dev, 0, bytes);       // an output mirror is copied back whole: bytes a kernel never wrote must not be garbage
       b->owns_dev = true;
       // Pin the caller's pages so the per-call copies run at full PCIe rate; failure is harmless.
       if (bytes >= (1u << 16) && cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess) b->registered = true;
@@ -664,9 +759,13 @@ void mfa_get_quantized_capabilities(void* out_capabilities) {
 }
 
 mfa_error_t mfa_set_device(int32_t device_index) {
+  // Selects the device of the contexts created from now on.  Every device has its own retained context, so a single-process
+  // host drives several GPUs by alternating mfa_set_device(i) / mfa_create_context (heads or batches sharded over the contexts).
+  if (device_index < 0 || device_index >= kMaxDevices) return MFA_ERROR_INVALID_ARGS;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0 && device_index >= n) return MFA_ERROR_INVALID_ARGS;
+  cudaGetLastError();
   std::lock_guard<std::mutex> lock(g_ctx_mu);
-  if (g_ctx) return g_ctx->device == device_index ? MFA_SUCCESS : MFA_ERROR_INVALID_ARGS;
-  if (device_index < 0) return MFA_ERROR_INVALID_ARGS;
   g_device_request = device_index;
   return MFA_SUCCESS;
 }
@@ -682,36 +781,38 @@ mfa_error_t mfa_create_context(mfa_context_t* context) {
   *context = nullptr;
   if (const char* d = getenv("MFA_DEBUG")) g_debug = d[0] && d[0] != '0';
   std::lock_guard<std::mutex> lock(g_ctx_mu);
-  if (!g_ctx) {
-    if (!device_ok()) return MFA_ERROR_DEVICE_NOT_SUPPORTED;
+  const int dev = requested_device();
+  if (dev < 0 || dev >= kMaxDevices) return MFA_ERROR_INVALID_ARGS;
+  if (!g_ctxs[dev]) {
+    if (!device_ok(dev)) return MFA_ERROR_DEVICE_NOT_SUPPORTED;
     Context* c = new (std::nothrow) Context();
     if (!c) return MFA_ERROR_MEMORY_ALLOCATION;
-    c->device = g_device_request >= 0 ? g_device_request : 0;
-    if (g_device_request < 0) if (const char* e = getenv("MFA_CUDA_DEVICE")) c->device = atoi(e);
-    if (cudaSetDevice(c->device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    c->device = dev;
+    DeviceGuard dg(dev);
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
       cudaGetLastError();
       delete c;
       return MFA_ERROR_DEVICE_NOT_SUPPORTED;
     }
-    g_ctx = c;
+    g_ctxs[dev] = c;
   }
-  ++g_ctx->refs;
-  *context = g_ctx;
+  ++g_ctxs[dev]->refs;
+  *context = g_ctxs[dev];
   return MFA_SUCCESS;
 }
 
 void mfa_destroy_context(mfa_context_t context) {
   if (!context) return;
   std::lock_guard<std::mutex> lock(g_ctx_mu);
-  if (context != g_ctx || !g_ctx) return;
-  if (--g_ctx->refs > 0) return;
+  Context* c = nullptr;
+  for (int i = 0; i < kMaxDevices; ++i) if (g_ctxs[i] && g_ctxs[i] == context) { c = g_ctxs[i]; break; }
+  if (!c) return;
+  if (--c->refs > 0) return;
   // Last reference: release device resources.  (The reference keeps its singleton alive for the process;
   // releasing here keeps create/destroy loops leak-free and a later create simply rebuilds it.)
-  Context* c = g_ctx;
-  g_ctx = nullptr;
-  cudaSetDevice(c->device);
+  g_ctxs[c->device] = nullptr;
+  DeviceGuard dg(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& s : c->scratch) s.release();
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -728,14 +829,16 @@ mfa_error_t mfa_create_buffer(mfa_context_t context, size_t size_bytes, mfa_buff
   *buffer = nullptr;
   if (!device_ok()) return MFA_ERROR_DEVICE_NOT_SUPPORTED;
   Context* ctx = C_(context);
-  cudaSetDevice(ctx->device);
+  DeviceGuard dg(ctx->device);
   Buffer* b = new (std::nothrow) Buffer();
   if (!b) return MFA_ERROR_MEMORY_ALLOCATION;
+  b->owner = ctx;
   b->bytes = size_bytes;
   size_t alloc = size_bytes ? size_bytes : 1;
   if (cudaHostAlloc(&b->host, alloc, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); delete b; return MFA_ERROR_MEMORY_ALLOCATION; }
   if (cudaMalloc(&b->dev, alloc) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(b->host); delete b; return MFA_ERROR_MEMORY_ALLOCATION; }
   memset(b->host, 0, alloc);
+  cudaMemset(b->dev, 0, alloc);
   b->owns_host = b->owns_dev = true;
   b->mirrored = true;
   *buffer = b;
@@ -862,12 +965,15 @@ mfa_error_t mfa_attention_forward_accumulate(
   if (in_dtype != kBF16 && in_dtype != kF16) return MFA_ERROR_INVALID_ARGS;
   if ((uint64_t)acc_row_offset + seq_len_q > acc_rows) return MFA_ERROR_INVALID_ARGS;
   if (bq->mirrored || bk->mirrored || bv->mirrored || bo->mirrored || bl->mirrored) return MFA_ERROR_INVALID_ARGS;
+  if (!view_fits(bq, batch_size, num_heads, seq_len_q, head_dim, 2) || !view_fits(bk, batch_size, num_heads, seq_len_kv, head_dim, 2) ||
+      !view_fits(bv, batch_size, num_heads, seq_len_kv, head_dim, 2))
+    return MFA_ERROR_INVALID_ARGS;
   if (bo->bytes < elems(batch_size, num_heads, acc_rows, head_dim) * 4 || bl->bytes < (size_t)batch_size * num_heads * acc_rows * 4)
     return MFA_ERROR_INVALID_ARGS;
   if (!device_ok()) return MFA_ERROR_DEVICE_NOT_SUPPORTED;
   if (batch_size == 0 || num_heads == 0 || seq_len_q == 0 || seq_len_kv == 0) return MFA_SUCCESS;
-  std::lock_guard<std::mutex> lock(ctx->mu);
-  cudaSetDevice(ctx->device);
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  DeviceGuard dg(ctx->device);
   cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
   AttnParams p;
   init_params(p, batch_size, num_heads, seq_len_q, seq_len_kv, head_dim, softmax_scale, causal, window_size < 0 ? -1 : window_size);
@@ -1130,8 +1236,20 @@ static int32_t prequantised_backward(
     // dK/dV from the caller's D: run the kv kernel directly.
     if (!device_ok()) return MFA_ERROR_DEVICE_NOT_SUPPORTED;
     if (D == 0 || D > 256 || H == 0 || Hkv == 0 || H % Hkv) return MFA_ERROR_INVALID_ARGS;
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    cudaSetDevice(ctx->device);
+    {
+      const size_t nq = elems(B, H, Sq, D), nkv = elems(B, Hkv, Skv, D), rows = (size_t)B * H * Sq;
+      if (B_(q)->bytes < packed_bytes(nq, dt) || B_(k)->bytes < packed_bytes(nkv, dt) || B_(v)->bytes < packed_bytes(nkv, dt) ||
+          B_(grad_output)->bytes < nq * 4 || B_(logsumexp)->bytes < rows * 4 || B_(d_values)->bytes < rows * 4 ||
+          B_(grad_key)->bytes < nkv * 4 || B_(grad_value)->bytes < nkv * 4)
+        return MFA_ERROR_INVALID_ARGS;
+      auto scales_fit = [&](mfa_buffer_t bs, uint32_t blk, uint32_t Hn, uint32_t S) {
+        return !bs || !blk || B_(bs)->bytes >= (size_t)B * Hn * ((S + blk - 1) / blk) * 4;
+      };
+      if (!scales_fit(qbs, qblk, H, Sq) || !scales_fit(kbs, kblk, Hkv, Skv) || !scales_fit(vbs, vblk, Hkv, Skv))
+        return MFA_ERROR_INVALID_ARGS;
+    }
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->stream;
     Sync sync{ctx, st, false, {}};
     Buffer* ins[] = {B_(q), B_(k), B_(v), B_(grad_output), B_(logsumexp), B_(d_values), B_(qbs), B_(kbs), B_(vbs)};
@@ -1238,14 +1356,17 @@ int32_t mfa_quantized_backward(
   const uint32_t B = batch_size, H = num_heads, Sq = seq_len_q, Skv = seq_len_kv, D = head_dim;
   const uint32_t blk = quant_mode == 2 ? 64 : 0;
   if (mask && B_(mask)->bytes < (size_t)B * H * Sq * Skv * 4) return MFA_ERROR_INVALID_ARGS;
-  // Re-quantise Q, K, V exactly as the forward did (deterministic), then run the backward on the codes.
+  // Re-quantise Q, K, V exactly as the forward did (deterministic), then run the backward on the codes.  The context lock
+  // (recursive) and the scratch scope are held across BOTH phases: no other call can overwrite the codes or scales between
+  // the quantise kernels and the backward kernels that read them.
   QuantView qq, qk, qvv;
   TensorView tq, tk, tv;
   int d0, d1, d2;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  DeviceGuard dg(ctx->device);
+  cudaStream_t st = ctx->stream;
+  ScratchScope scope(ctx, st);
   {
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    cudaSetDevice(ctx->device);
-    cudaStream_t st = ctx->stream;
     Sync sync{ctx, st, false, {}};
     cudaError_t e;
     if ((e = sync.in(B_(q))) != cudaSuccess || (e = sync.in(B_(k))) != cudaSuccess || (e = sync.in(B_(v))) != cudaSuccess ||
@@ -1253,9 +1374,9 @@ int32_t mfa_quantized_backward(
       return cuda_fail(e, "h2d");
     mfa_error_t me;
     QOperand oq{B_(q), in_dt, 1.f, 0, blk}, ok{B_(k), in_dt, 1.f, 0, blk}, ov{B_(v), in_dt, 1.f, 0, blk};
-    if ((me = quantise_operand(ctx, st, oq, 0, B, H, Sq, D, target_precision, tq, qq, d0)) != MFA_SUCCESS) return me;
-    if ((me = quantise_operand(ctx, st, ok, 1, B, H, Skv, D, target_precision, tk, qk, d1)) != MFA_SUCCESS) return me;
-    if ((me = quantise_operand(ctx, st, ov, 2, B, H, Skv, D, target_precision, tv, qvv, d2)) != MFA_SUCCESS) return me;
+    if ((me = quantise_operand(scope, st, oq, 0, B, H, Sq, D, target_precision, tq, qq, d0)) != MFA_SUCCESS) return me;
+    if ((me = quantise_operand(scope, st, ok, 1, B, H, Skv, D, target_precision, tk, qk, d1)) != MFA_SUCCESS) return me;
+    if ((me = quantise_operand(scope, st, ov, 2, B, H, Skv, D, target_precision, tv, qvv, d2)) != MFA_SUCCESS) return me;
   }
   // Wrap the device-resident codes as transient buffers and reuse backward_core (stream order keeps the
   // quantise kernels ahead of the backward kernels).
@@ -1297,7 +1418,7 @@ mfa_error_t mfa_set_scale_arrays(mfa_context_t context, const float* q_scales, u
                                  uint32_t nk, const float* v_scales, uint32_t nv) {
   if (!context) return MFA_ERROR_INVALID_ARGS;
   Context* ctx = C_(context);
-  std::lock_guard<std::mutex> lock(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   const float* src[3] = {q_scales, k_scales, v_scales};
   const uint32_t n[3] = {nq, nk, nv};
   for (int i = 0; i < 3; ++i) {
@@ -1316,11 +1437,15 @@ int32_t mfa_hadamard_rotate(mfa_buffer_t data, uint32_t block_size, uint32_t num
   if (!device_ok()) return MFA_ERROR_DEVICE_NOT_SUPPORTED;
   Buffer* b = B_(data);
   if (b->bytes < (size_t)block_size * num_blocks * 4) return MFA_ERROR_INVALID_ARGS;
-  std::lock_guard<std::mutex> glock(g_ctx_mu);
-  if (!g_ctx) return MFA_ERROR_INVALID_ARGS;      // buffers only exist under a live context
-  Context* ctx = g_ctx;
-  std::lock_guard<std::mutex> lock(ctx->mu);
-  cudaSetDevice(ctx->device);
+  Context* ctx = b->owner;                         // no context argument in the reference ABI: the buffer knows its context
+  {
+    std::lock_guard<std::mutex> glock(g_ctx_mu);
+    bool alive = false;
+    for (int i = 0; i < kMaxDevices; ++i) alive |= g_ctxs[i] != nullptr && g_ctxs[i] == ctx;
+    if (!alive) return MFA_ERROR_INVALID_ARGS;      // buffers only exist under a live context
+  }
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  DeviceGuard dg(ctx->device);
   Sync sync{ctx, ctx->stream, false, {}};
   cudaError_t e = sync.in(b);
   if (e == cudaSuccess) e = launch_hadamard(reinterpret_cast<float*>(b->dev), block_size, num_blocks, ctx->stream);
@@ -1339,8 +1464,8 @@ int mfa_rope_rotate_encode_mtl(
   const int dt = parse_precision_str(precision);
   if (!valid_float_dtype(dt) || (D & 1)) return MFA_ERROR_INVALID_ARGS;
   Context* ctx = C_(context);
-  std::lock_guard<std::mutex> lock(ctx->mu);
-  cudaSetDevice(ctx->device);
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  DeviceGuard dg(ctx->device);
   cudaError_t e = launch_rope(reinterpret_cast<char*>(src) + src_offset, reinterpret_cast<char*>(dst) + dst_offset,
                               reinterpret_cast<const float*>(reinterpret_cast<char*>(cos_table) + cos_offset),
                               reinterpret_cast<const float*>(reinterpret_cast<char*>(sin_table) + sin_offset), sB, sH, sS,
@@ -1367,8 +1492,8 @@ mfa_error_t mfa_quantize(mfa_context_t context, mfa_buffer_t src, mfa_buffer_t c
   const bool async = stream != nullptr;
   if (async && (bs->mirrored || bcodes->mirrored || bsc->mirrored)) return MFA_ERROR_INVALID_ARGS;
   Context* ctx = C_(context);
-  std::lock_guard<std::mutex> lock(ctx->mu);
-  cudaSetDevice(ctx->device);
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  DeviceGuard dg(ctx->device);
   cudaStream_t st = async ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
   Sync sync{ctx, st, async, {}};
   cudaError_t e = sync.in(bs);
@@ -1396,11 +1521,17 @@ mfa_error_t mfa_dequantize(mfa_context_t context, mfa_buffer_t codes, mfa_buffer
   const uint64_t n = rows * cols;
   Buffer *bcodes = B_(codes), *bsc = B_(scales), *bo = B_(out);
   if (bcodes->bytes < (bits == 8 ? n : (n + 1) / 2) || bo->bytes < n * 4) return MFA_ERROR_INVALID_ARGS;
+  {
+    const uint64_t br = (block_rows == 0 || block_rows > rows) ? rows : block_rows;
+    const uint64_t bc = (block_cols == 0 || block_cols > cols) ? cols : block_cols;
+    const uint64_t nb = n ? ((rows + br - 1) / br) * ((cols + bc - 1) / bc) : 0;
+    if (bsc->bytes < nb * 4) return MFA_ERROR_INVALID_ARGS;
+  }
   const bool async = stream != nullptr;
   if (async && (bo->mirrored || bcodes->mirrored || bsc->mirrored)) return MFA_ERROR_INVALID_ARGS;
   Context* ctx = C_(context);
-  std::lock_guard<std::mutex> lock(ctx->mu);
-  cudaSetDevice(ctx->device);
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  DeviceGuard dg(ctx->device);
   cudaStream_t st = async ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
   Sync sync{ctx, st, async, {}};
   cudaError_t e;
@@ -1423,8 +1554,8 @@ mfa_error_t mfa_merge_partials(mfa_context_t context, mfa_buffer_t o_acc, mfa_bu
   const bool async = stream != nullptr;
   for (Buffer* b : bs) if (async && b->mirrored) return MFA_ERROR_INVALID_ARGS;
   Context* ctx = C_(context);
-  std::lock_guard<std::mutex> lock(ctx->mu);
-  cudaSetDevice(ctx->device);
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  DeviceGuard dg(ctx->device);
   cudaStream_t st = async ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
   Sync sync{ctx, st, async, {}};
   for (Buffer* b : bs) { cudaError_t e = sync.in(b); if (e != cudaSuccess) return cuda_fail(e, "h2d"); }

@@ -22,6 +22,10 @@ struct FwdTcParams {
   int o_dtype;
   int H, Hkv, Sq, Skv;
   int nbatch;              // set by launch_fwd_tc_kernel (work items = query blocks x H x nbatch)
+  // dynamic work scheduling (set by launch_fwd_tc_kernel): CTAs take their first item from blockIdx.x and every further one
+  // as gridDim.x + (atomicAdd(sched_counter, 1) - sched_base); null = static striding by gridDim.x
+  unsigned int* sched_counter;
+  unsigned int sched_base;
   float c;                 // softmax_scale * log2(e)
   int causal, window;
   // kFwdI8 only: symmetric scales of the int8 codes (value = code * scale)

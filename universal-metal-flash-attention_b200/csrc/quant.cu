@@ -311,7 +311,9 @@ __global__ void hadamard_kernel(float* __restrict__ data, uint32_t n, uint32_t n
   }
 }
 
-// ---- interleaved-pair RoPE (Sources/MFABridge/MFABridge.swift:269-319): (x0, x1) -> (x0 c - x1 s, x0 s + x1 c)
+// ---- interleaved-pair RoPE (Sources/MFABridge/MFABridge.swift:269-319): (x0, x1) -> (x0 c - x1 s, x0 s + x1 c).
+// Tables follow the reference contract exactly: pair-duplicated fp32 [S, D] (only the even entry of a pair is read),
+// element t = b * table_batch_stride + s * D + 2 * pair, table_batch_stride = 0 (shared) or S * D ([B, S, D]).
 template <typename T> __device__ __forceinline__ T from_f32(float x);
 template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
 template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return __float2half_rn(x); }
@@ -331,7 +333,7 @@ __global__ void rope_kernel(const T* __restrict__ src, T* __restrict__ dst, cons
     uint32_t b = (uint32_t)(t / H);
     const int64_t in = b * sB + h * sH + s * sS + 2 * j;
     const int64_t out = (((int64_t)b * H + h) * S + s) * D + 2 * j;     // dst is contiguous BHSD
-    const int64_t ti = b * table_batch_stride + (int64_t)s * half + j;
+    const int64_t ti = b * table_batch_stride + (int64_t)s * D + 2 * j;
     float c = cos_t[ti], sn = sin_t[ti];
     if (negate_sin) sn = -sn;
     float x0 = to_f32<T>(src[in]), x1 = to_f32<T>(src[in + 1]);

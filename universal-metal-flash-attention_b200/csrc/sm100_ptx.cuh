@@ -34,14 +34,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin until the phase with the given parity has completed.  A bounded watchdog turns a protocol bug into a
-// trap (=> CUDA error at the next sync) instead of a hung GPU.
+// Spin until the phase with the given parity has completed.  Builds with -DMFA_MBAR_WATCHDOG (build.py: MFA_DEBUG=1) add a
+// wall-clock watchdog that turns a protocol bug into a trap (=> CUDA error at the next sync) instead of a hung GPU: the limit
+// is 20 s of %globaltimer, checked every 4096 failed try_waits, so a slow wait under compute-sanitizer, a debugger or MPS
+// time-slicing does not trip it.  Release builds spin without a limit.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
+#ifdef MFA_MBAR_WATCHDOG
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) { asm volatile("trap;"); }
+    if ((++spins & 4095u) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) { asm volatile("trap;"); }
+    }
   }
+#else
+  while (!mbar_try_wait(bar, parity)) {}
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ TMA
@@ -66,10 +78,31 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src_
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk groups of this thread have finished READING their shared-memory source
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent one (a two-buffer staging ring: the buffer about to be refilled is free)
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// all committed bulk groups of this thread are complete (writes performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // generic-proxy shared-memory writes -> visible to the async proxy (TMA)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, float& a, float& b, float& c, float& d) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v2(uint32_t addr, float& a, float& b) {
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
 }
 
 // 256-bit read-only global load (LDG.E.256 on sm_100): one full 32-byte sector per thread per request.  L1::no_allocate: the

@@ -41,6 +41,10 @@ def _routable(query, key, value, dropout_p) -> bool:
         return False
     if query.dtype not in (torch.float16, torch.bfloat16, torch.float32):
         return False
+    if key.device != query.device or value.device != query.device:
+        return False                     # operands spread over devices: PyTorch's own path raises the proper error
+    if not _ext.device_supported(query.device):
+        return False                     # a GPU in this process the library has no kernels for (not sm_100)
     if key.dtype != query.dtype or value.dtype != query.dtype:
         return False
     if query.dim() < 2 or query.dim() > 4 or key.dim() != query.dim() or value.dim() != query.dim():

@@ -37,24 +37,39 @@ _MASK_SCALAR = {torch.float16: _ffi.MFA_MASK_SCALAR_FP16, torch.bfloat16: _ffi.M
 
 _state = threading.local()
 _lock = threading.Lock()
-_ctx: Optional[MFAContext] = None
+_ctx: Optional[MFAContext] = None            # the first context created (kept for introspection in tests)
+_ctxs = {}                                   # device index -> context
 _quant = {"precision": QUANT_NONE, "block_mode": QUANT_TENSOR_WISE}
 _STAT_KEYS = ("total", "quantized_autograd", "fp32_autograd", "direct", "mask_all_true_skipped", "fallback_native")
 _stats = {k: 0 for k in _STAT_KEYS}
 
 
 def _context(device: torch.device) -> MFAContext:
-    """The library context is a process singleton bound to one device (one process per GPU: mfa_ffi_ext.h)."""
+    """One retained library context per CUDA device (mfa_set_device selects the device of the next mfa_create_context), so
+    tensors on any GPU of the process are served by the context that lives on their device."""
     global _ctx
+    idx = device.index if device.index is not None else torch.cuda.current_device()
     with _lock:
-        if _ctx is None:
-            idx = device.index if device.index is not None else torch.cuda.current_device()
-            _lib.mfa_set_device(idx)
-            _ctx = MFAContext()
-            _ctx.device_index = idx
-        elif device.index is not None and device.index != _ctx.device_index:
-            raise RuntimeError(f"libMFAFFI context is bound to cuda:{_ctx.device_index}; got a tensor on {device}")
-        return _ctx
+        ctx = _ctxs.get(idx)
+        if ctx is None:
+            rc = _lib.mfa_set_device(idx)
+            if rc != 0:
+                raise RuntimeError(f"mfa_set_device({idx}) failed with code {rc}")
+            ctx = MFAContext()
+            ctx.device_index = idx
+            _ctxs[idx] = ctx
+            if _ctx is None:
+                _ctx = ctx
+        return ctx
+
+
+def device_supported(device: torch.device) -> bool:
+    """True when `device` is a GPU libMFAFFI.so has kernels for (compute capability 10.x)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    try:
+        return torch.cuda.get_device_capability(idx)[0] == 10
+    except Exception:
+        return False
 
 
 class _Bound:
@@ -371,21 +386,21 @@ def hadamard_rotate(tensor: torch.Tensor, block_size: int) -> torch.Tensor:
 
 
 def _rope_tables(table, B, S, D, device):
-    """pair-duplicated fp32 [S,D] / [1,S,D] / [B,S,D] -> ([b,S,D/2] contiguous fp32, table_batch_stride)."""
+    """pair-duplicated fp32 [S,D] / [1,S,D] / [B,S,D] -> (contiguous fp32 [b,S,D], table_batch_stride): the table contract of
+    mfa_rope_rotate_encode_mtl (MFABridge.swift:282,305: element b * stride + s * D + 2 * pair, stride 0 or S * D)."""
     t = table.to(device=device, dtype=torch.float32)
     if t.dim() == 2:
         t = t.unsqueeze(0)
     if t.dim() != 3 or t.size(1) != S or t.size(2) != D or t.size(0) not in (1, B):
         raise RuntimeError("rope tables must be [S,D], [1,S,D] or [B,S,D]")
-    half = t[..., 0::2].contiguous()
-    return half, (S * (D // 2) if t.size(0) == B and B > 1 else 0)
+    return t.contiguous(), (S * D if t.size(0) == B and B > 1 else 0)
 
 
 def _rope(x, cos_t, sin_t, negate_sin=False):
     ctx = _context(x.device)
     B, H, S, D = x.shape
-    cos_h, bstride = _rope_tables(cos_t, B, S, D, x.device)
-    sin_h, _ = _rope_tables(sin_t, B, S, D, x.device)
+    cos_f, bstride = _rope_tables(cos_t, B, S, D, x.device)
+    sin_f, _ = _rope_tables(sin_t, B, S, D, x.device)
     dst = torch.empty((B, H, S, D), device=x.device, dtype=x.dtype)
     prec = {torch.float16: b"fp16", torch.bfloat16: b"bf16", torch.float32: b"fp32"}[x.dtype]
     stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream or 0)
@@ -393,21 +408,37 @@ def _rope(x, cos_t, sin_t, negate_sin=False):
         x = x.contiguous()
     rc = _lib.mfa_rope_rotate_encode_mtl(ctx.handle, _stream_arg(stream, x), ctypes.c_void_p(x.data_ptr()), 0,
                                          x.stride(0), x.stride(1), x.stride(2), ctypes.c_void_p(dst.data_ptr()), 0,
-                                         ctypes.c_void_p(cos_h.data_ptr()), 0, ctypes.c_void_p(sin_h.data_ptr()), 0,
+                                         ctypes.c_void_p(cos_f.data_ptr()), 0, ctypes.c_void_p(sin_f.data_ptr()), 0,
                                          bstride, bool(negate_sin), B, H, S, D, prec)
     if rc != 0:
         raise RuntimeError(f"RoPE rotation failed with code {rc}")
     return dst
 
 
+class RopeRotateFn(torch.autograd.Function):
+    """Interleaved-pair rotary embedding with its exact backward: the rotation is orthonormal, so the gradient of the input
+    is the inverse rotation (negate_sin) of the gradient of the output -- the reference adapter's dQ / dK transform
+    (metal_sdpa_backend.cpp:2883-3122, MFABridge.swift:262-267)."""
+
+    @staticmethod
+    def forward(ctx, x, cos_t, sin_t):
+        ctx.save_for_backward(cos_t, sin_t)
+        return _rope(x, cos_t, sin_t)
+
+    @staticmethod
+    def backward(ctx, grad):
+        cos_t, sin_t = ctx.saved_tensors
+        return _rope(grad.contiguous(), cos_t, sin_t, negate_sin=True), None, None
+
+
 def rope_scaled_dot_product_attention(query, key, value, rope_cos, rope_sin, attn_mask=None, is_causal=False, scale=None):
-    """Interleaved-pair RoPE of Q and K on the device, then the SDPA entry (metal_sdpa_backend.cpp:1440-1560)."""
+    """Interleaved-pair RoPE of Q and K on the device, then the SDPA entry (metal_sdpa_backend.cpp:1440-1560); gradients
+    flow back through the attention backward and the inverse rotation of dQ / dK."""
     _check_inputs(query, key, value)
     if query.size(2) != key.size(2):
         raise RuntimeError("rope_scaled_dot_product_attention expects equal query / key sequence lengths")
-    with torch.no_grad():
-        q_r, k_r = _rope(query, rope_cos, rope_sin), _rope(key, rope_cos, rope_sin)
-        return metal_scaled_dot_product_attention(q_r, k_r, value, attn_mask, 0.0, is_causal, scale)
+    q_r, k_r = RopeRotateFn.apply(query, rope_cos, rope_sin), RopeRotateFn.apply(key, rope_cos, rope_sin)
+    return metal_scaled_dot_product_attention(q_r, k_r, value, attn_mask, 0.0, is_causal, scale)
 
 
 def is_metal_available() -> bool:
