@@ -150,7 +150,51 @@ bool device_ok(int dev) {
 }
 bool device_ok() { return device_ok(requested_device()); }
 
+}  // namespace
+
+namespace mfa {
+// Watchdog builds (-DMFA_MBAR_WATCHDOG): a host-mapped buffer the kernels' mbarrier watchdog writes stuck waits into; it is
+// ordinary pinned host memory, so it can still be read after the trap has killed the CUDA context.
+struct WatchdogLogHost { unsigned int count; unsigned int pad; unsigned int rec[1024][4]; };
+static WatchdogLogHost* g_wd_host = nullptr;
+void* watchdog_device_log() {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!g_wd_host) {
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, sizeof(WatchdogLogHost), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    memset(h, 0, sizeof(WatchdogLogHost));
+    g_wd_host = reinterpret_cast<WatchdogLogHost*>(h);
+  }
+  void* d = nullptr;
+  if (cudaHostGetDevicePointer(&d, g_wd_host, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return d;
+}
+static void watchdog_report() {
+  if (!g_wd_host || g_wd_host->count == 0) return;
+  const unsigned int n = g_wd_host->count < 1024 ? g_wd_host->count : 1024;
+  fprintf(stderr, "[mfa] mbarrier watchdog: %u stuck wait(s); unique (block, warp, barrier smem address, parity) x threads:\n", g_wd_host->count);
+  unsigned int shown = 0;
+  for (unsigned int i = 0; i < n && shown < 256; ++i) {
+    const unsigned int* r = g_wd_host->rec[i];
+    bool dup = false;
+    unsigned int same = 0;
+    for (unsigned int j = 0; j < n; ++j) {
+      const unsigned int* q = g_wd_host->rec[j];
+      if (q[0] == r[0] && q[1] / 32 == r[1] / 32 && q[2] == r[2] && q[3] == r[3]) { if (j < i) dup = true; ++same; }
+    }
+    if (dup) continue;
+    fprintf(stderr, "[mfa]   block %u warp %u bar 0x%x parity %u x%u\n", r[0], r[1] / 32, r[2], r[3], same);
+    ++shown;
+  }
+  g_wd_host->count = 0;
+}
+}  // namespace mfa
+
+namespace {
+
 inline mfa_error_t cuda_fail(cudaError_t e, const char* what) {
+  mfa::watchdog_report();
   DBG("%s: %s", what, cudaGetErrorString(e));
   cudaGetLastError();
   return e == cudaErrorMemoryAllocation ? MFA_ERROR_MEMORY_ALLOCATION : MFA_ERROR_EXECUTION_FAILED;

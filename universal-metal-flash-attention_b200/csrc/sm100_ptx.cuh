@@ -34,26 +34,76 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin until the phase with the given parity has completed.  Builds with -DMFA_MBAR_WATCHDOG (build.py: MFA_DEBUG=1) add a
-// wall-clock watchdog that turns a protocol bug into a trap (=> CUDA error at the next sync) instead of a hung GPU: the limit
-// is 20 s of %globaltimer, checked every 4096 failed try_waits, so a slow wait under compute-sanitizer, a debugger or MPS
-// time-slicing does not trip it.  Release builds spin without a limit.
+// Spin until the phase with the given parity has completed.  Builds with -DMFA_MBAR_WATCHDOG (MFA_WATCHDOG=1 at build time)
+// add a wall-clock watchdog that turns a protocol bug into a diagnosable trap instead of a hung GPU: after kWatchdogNs of
+// %globaltimer in ONE wait the thread writes (block, thread, barrier address, parity) into a host-mapped record buffer
+// (g_watchdog_log, set by the launcher; survives the dead context) and, after twice that time, traps.  The limit is seconds,
+// so compute-sanitizer, a debugger or MPS time-slicing do not trip it.  Release builds spin without a limit.
+#ifdef MFA_MBAR_WATCHDOG
+constexpr unsigned long long kWatchdogNs = 3000000000ull;
+struct WatchdogLog { unsigned int count; unsigned int pad; unsigned int rec[1024][4]; };
+static __device__ WatchdogLog* g_watchdog_log = nullptr;      // one per translation unit and device: watchdog_bind()
+// out of line on purpose: the hot wait loops (MMA issuer, softmax) must stay small in the instruction cache
+static __device__ __noinline__ void watchdog_tick(uint32_t bar, uint32_t parity, unsigned long long& t0, bool& logged) {
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  if (t0 == 0) { t0 = now; return; }
+  if (!logged && now - t0 > kWatchdogNs) {
+    logged = true;
+    if (WatchdogLog* lg = g_watchdog_log) {
+      const unsigned int i = atomicAdd(&lg->count, 1u);
+      if (i < 1024) {
+        lg->rec[i][0] = blockIdx.x; lg->rec[i][1] = threadIdx.x; lg->rec[i][2] = bar; lg->rec[i][3] = parity;
+        __threadfence_system();
+      }
+    }
+  }
+  if (now - t0 > 2 * kWatchdogNs) { asm volatile("trap;"); }
+}
+}  // namespace ptx
+void* watchdog_device_log();          // ffi.cu: host-mapped record buffer (device view), allocated on first use
+namespace ptx {
+// called by a launcher before its first launch on the current device: points this translation unit's log pointer at the buffer
+inline void watchdog_bind() {
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  void* d = watchdog_device_log();
+  if (d && cudaMemcpyToSymbol(g_watchdog_log, &d, sizeof(d)) == cudaSuccess) done[dev] = true;
+  else cudaGetLastError();
+}
+#else
+inline void watchdog_bind() {}
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
 #ifdef MFA_MBAR_WATCHDOG
   uint32_t spins = 0;
   unsigned long long t0 = 0;
+  bool logged = false;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 4095u) == 0) {
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 20000000000ull) { asm volatile("trap;"); }
-    }
+    if ((++spins & 4095u) == 0) watchdog_tick(bar, parity, t0, logged);
   }
 #else
   while (!mbar_try_wait(bar, parity)) {}
 #endif
+}
+
+// Long waits off the critical path (the epilogue warpgroup waiting a whole work item for its statistics): sleep between polls so
+// the waiting warp does not compete for issue slots with the warps doing the work.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+#ifdef MFA_MBAR_WATCHDOG
+  unsigned long long t0 = 0;
+  uint32_t spins = 0;
+  bool logged = false;
+#endif
+  while (!mbar_try_wait(bar, parity)) {
+    asm volatile("nanosleep.u32 256;" ::: "memory");
+#ifdef MFA_MBAR_WATCHDOG
+    if ((++spins & 1023u) == 0) watchdog_tick(bar, parity, t0, logged);
+#endif
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ TMA
@@ -141,6 +191,16 @@ __device__ __forceinline__ void ld_global_v8(const float* p, float* r) {
 __device__ __forceinline__ void st_global_v8(float* p, const float* r) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]) : "memory");
+}
+
+// 128-bit coherent global load / store (the forward's coalesced write-out / merge of O)
+__device__ __forceinline__ float4 ld_global_v4(const void* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_global_v4(void* p, float a, float b, float c, float d) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // Named barriers (ids 1..15; id 0 is __syncthreads)
