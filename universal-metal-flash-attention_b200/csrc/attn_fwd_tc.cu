@@ -74,8 +74,8 @@ struct Cfg {
   static constexpr int kQTile = kQChunks * kChunkBytes;
   static constexpr int kVTile = kVChunks * kChunkBytes;
   static constexpr int kStage = kVTile;                              // ring stage (K tiles may use part of it)
-  static constexpr int kStages = D == 128 ? 4 : 8;
-  static constexpr int kOutBytes = kChunkBytes;                      // epilogue staging: one 4 KB block (32 rows x 128 bytes) per warp
+  static constexpr int kStages = D == 128 ? 5 : 10;
+  static constexpr int kOutBytes = 0;                                // (no epilogue staging: the epilogue warpgroup stores straight from registers)
   static constexpr int kStatsBytes = 2 * 128 * 8;                    // (m, l) of every row of both tiles
   static constexpr int kFixedBars = 28;                              // see the barrier map in the kernel
   static constexpr int kBarBytes = 8 * (kFixedBars + 2 * kStages) + 16;      // + TMEM slot, two scheduler slots
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
   // Q/K/V are already in flight -- and its first S issued -- while the epilogue warpgroup is still writing the previous O.
   const int nqb = (p.Sq + 255) / 256;
   const int n_items = nqb * p.H * p.nbatch;
-  struct Item { int r0, h, b, hk, nt, j_lo, n, lid; };
+  struct Item { int r0, h, b, hk, nt, j_lo, n, lid, n0; };
   auto decode = [&](int w) {
     Item it;
     const int x = w % nqb, hb = w / nqb;
@@ -223,6 +223,14 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     it.j_lo = klo >> 7;
     it.n = khi > klo ? ((khi + 127) >> 7) - it.j_lo : 0;
     it.lid = 0;
+    it.n0 = it.n;
+    if (p.ring_world > 1) {
+      // single-launch ring attention (ring.cu): after the rank's own causal [low | high] pair (n0 steps) the item walks the
+      // visiting K/V pairs in arrival order, source rank (rank - s) mod world for s = 1 .. world-1: a lower rank shows every
+      // query row its low chunk only, a higher rank shows both of its chunks to the rank's high-chunk rows only (zig-zag)
+      const int l1 = p.ring_C >> 7, l2 = it.r0 >= p.ring_C ? (2 * p.ring_C) >> 7 : 0;
+      it.n = it.n0 + p.ring_rank * l1 + (p.ring_world - 1 - p.ring_rank) * l2;
+    }
     if constexpr (MASKED) {
       if (p.mtiles) {        // the list already folds in the causal / window range
         it.lid = ((p.mask_sb ? it.b : 0) * (p.mask_sh ? p.H : 1) + (p.mask_sh ? it.h : 0)) * nqb + qblk;
@@ -232,8 +240,17 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     return it;
   };
   // KV tile visited at step `it` of an item
+  // (ring mode: bits 20-27 = visiting slot s, 0 = the rank's own K/V)
   auto tile_of = [&](const Item& im, int it) {
     if constexpr (MASKED) { if (p.mtiles) return __ldg(p.mtiles + (size_t)im.lid * p.m_nkt + it); }
+    if (p.ring_world > 1 && it >= im.n0) {
+      int x = it - im.n0;
+      const int l1 = p.ring_C >> 7, a = p.ring_rank * l1;
+      if (x < a) return (x % l1) | ((1 + x / l1) << 20);
+      x -= a;
+      const int l2 = (2 * p.ring_C) >> 7;
+      return (x % l2) | ((p.ring_rank + 1 + x / l2) << 20);
+    }
     return im.j_lo + it;
   };
   // consumer side of the scheduler ring: item index of this CTA's k-th item (>= n_items: no more work)
@@ -274,6 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     reg_dealloc<kOtherRegs>();
     if (lane == 0) {
       int kvi = 0, qc[2] = {0, 0};                      // running ring index; items in which tile t took part
+      int slots_seen = 0;                               // ring mode: visiting slots known to have arrived (they arrive in order)
       int cur = blockIdx.x;
       for (int k = 0;; ++k) {
         const int sl = k & 1;
@@ -297,14 +315,29 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
 #pragma unroll
             for (int c = 0; c < C::kVChunks; ++c) tma_load_4d(dst + c * CHB, &p.tv, bar, c * 64, row, hk, b);
           };
+          // visiting K/V of ring slot s (s >= 1): 5-D maps over [slot][B][H][2C][D]
+          auto load_visit = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int row, int slot) {
+            mbar_arrive_expect_tx(bar, VT);
+#pragma unroll
+            for (int c = 0; c < C::kVChunks; ++c) tma_load_5d(dst + c * CHB, m, bar, c * 64, row, hk, b, slot - 1);
+          };
           if (qc[0] > 0) mbar_wait(q_empty(0), (qc[0] - 1) & 1);
           load_qk(sQ, &p.tq, q_full(0), r0, h);
           ++qc[0];
           for (int it = 0; it < n; ++it) {
-            const int row = (tile_of(im, it) & (kTileNoMask - 1)) * 128;
+            const int tile = tile_of(im, it);
+            const int row = (tile & 0xfffff) * 128;
+            const int slot = (tile >> 20) & 0xff;
+            if (slot > slots_seen) {
+              // the slot's K/V pair is written by the transport stream; its flag reaches this launch's epoch when it is complete
+              while ((int)(ld_acquire_gpu_u32(p.ring_flags + slot) - p.ring_epoch) < 0) nanosleep_ns(500);
+              fence_proxy_async_all();
+              slots_seen = slot;
+            }
             int s = kvi % NS;
             mbar_wait(kv_empty(s), ((kvi / NS) & 1) ^ 1);
-            load_qk(sKV + s * STG, &p.tk, kv_full(s), row, hk);
+            if (slot == 0) load_qk(sKV + s * STG, &p.tk, kv_full(s), row, hk);
+            else load_visit(sKV + s * STG, &p.tkr, kv_full(s), row, slot);
             ++kvi;
             if (it == 0 && nt == 2) {
               if (qc[1] > 0) mbar_wait(q_empty(1), (qc[1] - 1) & 1);
@@ -313,7 +346,8 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
             }
             s = kvi % NS;
             mbar_wait(kv_empty(s), ((kvi / NS) & 1) ^ 1);
-            load_v(sKV + s * STG, kv_full(s), row);
+            if (slot == 0) load_v(sKV + s * STG, kv_full(s), row);
+            else load_visit(sKV + s * STG, &p.tvr, kv_full(s), row, slot);
             ++kvi;
           }
         }
@@ -442,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       int jt_next = n > 0 ? tile_of(im, 0) : 0;        // tile index of the coming step (read one step ahead)
       auto fetch_scales = [&](int jt) {
         if constexpr (I8) {
-          const int c0 = (jt & (kTileNoMask - 1)) * 128;
+          const int c0 = (jt & 0xfffff) * 128;
           if (ksp) {
             ksn0 = __ldg(ksp + min(c0 / p.kbr, p.nbk - 1));
             ksn1 = __ldg(ksp + min((c0 + 64) / p.kbr, p.nbk - 1));
@@ -455,8 +489,9 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       };
       if (n > 0) fetch_scales(jt_next);
       for (int it = 0; it < n; ++it) {
-        const int c0 = (jt_next & (kTileNoMask - 1)) * 128;
+        const int c0 = (jt_next & 0xfffff) * 128;
         const bool mask_noop = (jt_next & kTileNoMask) != 0;
+        const bool visiting = ((jt_next >> 20) & 0xff) != 0;            // ring mode: keys of another rank, all visible
         // multipliers of the two 64-key halves of this tile (int8: blocks are multiples of 64 keys)
         float a0 = qsc, a1 = qsc, lv0 = 0.f, lv1 = 0.f, iv0 = 1.f, iv1 = 1.f;
         if constexpr (I8) {
@@ -563,7 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
             a0 = a1 = 1.f;
           }
         }
-        const bool need_mask = (c0 < clo) || (c0 + 127 > chi);
+        const bool need_mask = !visiting && ((c0 < clo) || (c0 + 127 > chi));
         const bool any_mask = __any_sync(0xffffffffu, need_mask);
         if (any_mask) {
           const int lo_i = clo - c0, hi_i = chi - c0;
@@ -638,23 +673,19 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
   } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
     // ------------------------------------------------------------------ epilogue warpgroup: O / l, L = m + log2(l)
     // Drains O_t from TMEM once the item's last P V has retired (o_full) while the other warps are already working on the
-    // CTA's next item.  Everything is warp-local: thread = row reads 32 fp32 columns (tcgen05.ld 32x32b), scales them and
-    // writes its 128-byte line into the warp's own 4 KB staging block (16-byte units XOR-swizzled with the row: conflict
-    // free); after a __syncwarp the warp reads the block back four rows per instruction and writes whole 128-byte lines to
-    // global memory (8 lanes x 16 bytes per row) -- coalesced, on the LSU path, so the stores never queue behind the
-    // producer's K/V loads in the TMA unit (a TMA-store staging ring needed ~0.6 us per 16 KB chunk there and held the next
-    // item's first P V back: profiles/r02/).  Accumulate mode (ring attention) merges with the running result on the way out,
-    //   L = log2(2^L_old + 2^L_new),  O = O_old 2^(L_old - L) + O_new 2^(L_new - L)      (fp32 O only)
-    // with the old lines loaded coalesced (all requests of a chunk in flight together) and the row's weight taken by shuffle.
+    // CTA's next item: thread = row reads 16 fp32 columns at a time (tcgen05.ld 32x32b), scales them and stores them as
+    // 32-byte pieces (one full sector per lane and request) -- fire and forget, so the TMEM hand-back (o_empty) is not held
+    // up by memory.  No shared-memory staging: the 16 KB it took (and the TMA-store variant's 32 KB) are worth more as the
+    // fifth K/V ring stage (steady state +4 %, profiles/r02/), and both staged variants -- TMA bulk stores queueing behind the
+    // producer's K/V loads, warp-local transposes -- needed 2.3 - 2.4 us per tile against ~1 us of issue time here.
+    // Accumulate mode (the step-by-step ring of umfa/ring.py; the native ring needs no merge) reads the running O the same
+    // way and merges in registers:  L = log2(2^L_old + 2^L_new),  O = O_old 2^(L_old - L) + O_new 2^(L_new - L)  (fp32 O).
     reg_dealloc<kEpiRegs>();
     const int ew = warp - kEpiWarp0;
     const int row = ew * 32 + lane;
     const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
     const bool stamp = threadIdx.x == kEpiWarp0 * 32;
     const bool acc_mode = p.accumulate && p.o_dtype == kF32;
-    const uint32_t wst = sOut + (uint32_t)ew * 4096u;                    // this warp's staging block: 32 rows x 128 bytes
-    const uint32_t my_line = wst + (uint32_t)lane * 128u;
-    const int sub = lane >> 3, unit = lane & 7;                          // read-back: row 4 j + sub, 16-byte unit `unit`
     const int oes = p.o_dtype == kF32 ? 4 : 2;
     int ec[2] = {0, 0}, oc[2] = {0, 0};                    // items in which tile t took part / of those, items with KV steps (barrier phases)
     for (int k = 0;; ++k) {
@@ -688,95 +719,58 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
             c_old = 1.f;                                   // nothing on either side: keep what is there
           }
         }
+        if (live && p.lse) p.lse[lrow] = l_out;
         if (n > 0) { mbar_wait(o_full(t), oc[t] & 1); ++oc[t]; tc_fence_after(); }
         ++ec[t];
         if (TR && ct && stamp && k == 0 && t == 0) ct[4] = globaltimer_ns();
-        if (live && p.lse) p.lse[lrow] = l_out;
-        // read-back geometry: lane (sub, unit) handles rows 4 j + sub of the warp's block, 16 bytes at unit * 16 of each line
-        const int wr0 = r0 + t * 128 + ew * 32 + sub;                              // global row of j = 0
-        const int nvalid = p.debug_skip_store ? 0 : p.Sq - wr0;                    // row 4 j + sub is stored iff 4 j < nvalid
-        const long long row_bytes = (long long)p.o_ss * oes;
-        char* gp = reinterpret_cast<char*>(p.o) + ((size_t)b * p.o_sb + (size_t)h * p.o_sh) * oes + (long long)wr0 * row_bytes + unit * 16;
-        // line of row 4 j + sub, unit (unit ^ (row & 7)) with (row & 7) = sub ^ (4 (j & 1)): rd + 512 j, bit 6 flipped for odd j
-        const uint32_t rd = wst + (uint32_t)sub * 128u + (uint32_t)((unit ^ sub) << 4);
-        const int n_chunks = p.o_dtype == kF32 ? D / 32 : D / 64;
+        char* orow = reinterpret_cast<char*>(p.o) + ((size_t)b * p.o_sb + (size_t)h * p.o_sh + (size_t)r * p.o_ss) * oes;
+        const bool wide = (reinterpret_cast<uintptr_t>(orow) & 31) == 0;      // 32-byte pieces need 32-byte aligned rows
 #pragma unroll 1
-        for (int ch = 0; ch < n_chunks; ++ch) {
-          // ---- TMEM -> registers -> this row's line of the staging block
-          if (p.o_dtype == kF32) {
+        for (int ch = 0; ch < D / 16; ++ch) {
+          uint32_t ou[16];
+          __syncwarp();                            // rows past the end skip the stores below: reconverge before the aligned TMEM read
+          if (n > 0) { tmem_ld_x16(tO + ch * 16, ou); tmem_wait_ld(); }
+          else {
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              uint32_t ou[16];
-              if (n > 0) { tmem_ld_x16(tO + ch * 32 + hf * 16, ou); tmem_wait_ld(); }
-              else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) ou[i] = 0u;
-              }
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                st_shared_v4(my_line + (uint32_t)(((hf * 4 + i) ^ (lane & 7)) << 4), __uint_as_float(ou[4 * i]) * inv,
-                             __uint_as_float(ou[4 * i + 1]) * inv, __uint_as_float(ou[4 * i + 2]) * inv, __uint_as_float(ou[4 * i + 3]) * inv);
-            }
-          } else {
-#pragma unroll
-            for (int qt = 0; qt < 4; ++qt) {
-              uint32_t ou[16];
-              if (n > 0) { tmem_ld_x16(tO + ch * 64 + qt * 16, ou); tmem_wait_ld(); }
-              else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) ou[i] = 0u;
-              }
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                uint32_t wv[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float a = __uint_as_float(ou[8 * i + 2 * q]) * inv, bb = __uint_as_float(ou[8 * i + 2 * q + 1]) * inv;
-                  wv[q] = p.o_dtype == kBF16 ? pack_bf16(a, bb) : pack_f16(a, bb);
-                }
-                st_shared_v4(my_line + (uint32_t)(((qt * 2 + i) ^ (lane & 7)) << 4), __uint_as_float(wv[0]), __uint_as_float(wv[1]),
-                             __uint_as_float(wv[2]), __uint_as_float(wv[3]));
-              }
-            }
+            for (int i = 0; i < 16; ++i) ou[i] = 0u;
           }
-          if (ch == n_chunks - 1 && n > 0) {       // O_t has left TMEM: the MMA warp may overwrite it (first P V of the next item)
+          if (ch == D / 16 - 1 && n > 0) {         // O_t has left TMEM: the MMA warp may overwrite it (first P V of the next item)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(o_empty(t));
           }
-          __syncwarp();
-          // ---- staging block -> global memory, four rows (4 x 128 bytes) per instruction
-          char* gc = gp + (size_t)ch * 128u;
-          if (acc_mode) {
+          if (!live) continue;
+          if (p.o_dtype == kF32) {
+            float* dst = reinterpret_cast<float*>(orow) + ch * 16;
+            float v[16];
 #pragma unroll
-            for (int g4 = 0; g4 < 2; ++g4) {           // two batches of four row groups: four old lines in flight per lane
-              float4 old[4];
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ou[i]) * inv;
+            if (acc_mode) {
+              float old[16];
+              if (wide) { ld_global_v8(dst, old); ld_global_v8(dst + 8, old + 8); }
+              else {
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int j = g4 * 4 + jj;
-                old[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (4 * j < nvalid) old[jj] = ld_global_v4(gc + (long long)(4 * j) * row_bytes);
+                for (int i = 0; i < 4; ++i) { const float4 q4 = ld_global_v4(dst + 4 * i); old[4 * i] = q4.x; old[4 * i + 1] = q4.y; old[4 * i + 2] = q4.z; old[4 * i + 3] = q4.w; }
               }
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int j = g4 * 4 + jj;
-                const float co = __shfl_sync(0xffffffffu, c_old, 4 * j + sub);
-                float v0, v1, v2, v3;
-                ld_shared_v4((rd + (uint32_t)j * 512u) ^ (uint32_t)((j & 1) << 6), v0, v1, v2, v3);
-                if (4 * j < nvalid)
-                  st_global_v4(gc + (long long)(4 * j) * row_bytes, fmaf(old[jj].x, co, v0), fmaf(old[jj].y, co, v1),
-                               fmaf(old[jj].z, co, v2), fmaf(old[jj].w, co, v3));
-              }
+              for (int i = 0; i < 16; ++i) v[i] = fmaf(old[i], c_old, v[i]);
+            }
+            if (wide) { st_global_v8(dst, v); st_global_v8(dst + 8, v + 8); }
+            else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) st_global_v4(dst + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
           } else {
+            float wv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float v0, v1, v2, v3;
-              ld_shared_v4((rd + (uint32_t)j * 512u) ^ (uint32_t)((j & 1) << 6), v0, v1, v2, v3);
-              if (4 * j < nvalid) st_global_v4(gc + (long long)(4 * j) * row_bytes, v0, v1, v2, v3);
+            for (int i = 0; i < 8; ++i) {
+              const float a = __uint_as_float(ou[2 * i]) * inv, bb = __uint_as_float(ou[2 * i + 1]) * inv;
+              wv[i] = __uint_as_float(p.o_dtype == kBF16 ? pack_bf16(a, bb) : pack_f16(a, bb));
             }
+            float* dst = reinterpret_cast<float*>(orow + (size_t)ch * 32);
+            if (wide) st_global_v8(dst, wv);
+            else { st_global_v4(dst, wv[0], wv[1], wv[2], wv[3]); st_global_v4(dst + 4, wv[4], wv[5], wv[6], wv[7]); }
           }
-          __syncwarp();                            // the block is rewritten by the next chunk
         }
         if (TR && ct && stamp && k == 0 && t == nt - 1) { ct[5] = globaltimer_ns(); ct[8] = clock64(); }
       }
@@ -1172,6 +1166,44 @@ cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st) {
   cudaError_t e = launch_fwd_tc_kernel(prm, p.D, bf ? kFwdBF16 : kFwdF16, st, p.B);
   if (p.D == 128) g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d128_mask" : "fwd_tc_fp16_d128_mask") : (bf ? "fwd_tc_bf16_d128" : "fwd_tc_fp16_d128");
   else g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d64_mask" : "fwd_tc_fp16_d64_mask") : (bf ? "fwd_tc_bf16_d64" : "fwd_tc_fp16_d64");
+  ++g_launch_count;
+  return e;
+}
+
+// Single-launch ring forward (ring.cu): the rank's own causal [low | high] problem plus the visiting K/V pairs of the other
+// ranks, consumed in arrival order by one persistent grid.  O never leaves TMEM between ring steps, so there is no partial
+// (O, L) merge and no per-step launch; the producer warps poll the slots' arrival flags before their first load of a slot.
+cudaError_t launch_fwd_tc_ring(const AttnParams& p, const RingLaunch& r, cudaStream_t st) {
+  if (!fwd_tc_eligible(p) || p.mask || !p.causal || p.window >= 0 || p.accumulate) return cudaErrorInvalidValue;
+  if (r.world < 1 || r.rank < 0 || r.rank >= r.world || r.world > 255) return cudaErrorInvalidValue;
+  if (p.Sq != 2 * r.chunk_rows || p.Skv != p.Sq || (r.chunk_rows % 256) != 0 || p.H != p.Hkv) return cudaErrorInvalidValue;
+  FwdTcParams prm = {};
+  if (!make_map(&prm.tq, p.q, p.in_dtype, p.B, p.H, p.Sq, p.D) || !make_map(&prm.tk, p.k, p.in_dtype, p.B, p.Hkv, p.Skv, p.D) ||
+      !make_map(&prm.tv, p.v, p.in_dtype, p.B, p.Hkv, p.Skv, p.D))
+    return cudaErrorInvalidValue;
+  if (r.world > 1) {
+    if (!r.k_visit || !r.v_visit || !r.flags) return cudaErrorInvalidValue;
+    if (!tc::make_map5(&prm.tkr, r.k_visit, p.in_dtype, r.world - 1, p.B, p.Hkv, p.Skv, p.D) ||
+        !tc::make_map5(&prm.tvr, r.v_visit, p.in_dtype, r.world - 1, p.B, p.Hkv, p.Skv, p.D))
+      return cudaErrorInvalidValue;
+    prm.ring_rank = r.rank; prm.ring_world = r.world; prm.ring_C = r.chunk_rows;
+    prm.ring_flags = r.flags; prm.ring_epoch = r.epoch;
+  }
+  prm.o = const_cast<void*>(p.o.ptr);
+  prm.o_sb = p.o.sb; prm.o_sh = p.o.sh; prm.o_ss = p.o.ss;
+  prm.lse = p.lse;
+  prm.lse_sh = p.lse_sh > 0 ? p.lse_sh : p.Sq;
+  prm.o_dtype = p.o_dtype;
+  prm.H = p.H; prm.Hkv = p.Hkv; prm.Sq = p.Sq; prm.Skv = p.Skv;
+  prm.c = p.scale * kLog2e;
+  prm.causal = 1; prm.window = -1;
+  prm.pingpong = fwd_tc_pingpong();
+  const bool bf = p.in_dtype == kBF16;
+  const int saved = t_sm_limit;
+  if (r.world > 1 && r.reserve_sms > 0) t_sm_limit = -r.reserve_sms;
+  cudaError_t e = launch_fwd_tc_kernel(prm, p.D, bf ? kFwdBF16 : kFwdF16, st, p.B);
+  t_sm_limit = saved;
+  g_last_kernel = p.D == 128 ? (bf ? "fwd_tc_ring_bf16_d128" : "fwd_tc_ring_fp16_d128") : (bf ? "fwd_tc_ring_bf16_d64" : "fwd_tc_ring_fp16_d64");
   ++g_launch_count;
   return e;
 }

@@ -3,20 +3,22 @@
 // north_star item (4): "for long causal contexts, ring attention that passes K/V blocks over NVLink with NCCL send/recv
 // overlapped with compute".
 //
-// One process per GPU.  The sequence is cut into 2*world chunks, rank r owns chunks r and 2*world-1-r (zig-zag, so causal work is
-// balanced) stored next to each other: q / k / v are [B, H, 2C, D] with the low chunk first.  Q stays put, the K/V pair travels
-// round the ring; with that layout the visible chunk pairs of a step are ONE rectangular problem (step_plan), i.e. one kernel
-// launch per step through the library's own C entry points:
-//     step 0           mfa_attention_forward_ex            causal 2C x 2C on local indices
-//     source < rank    mfa_attention_forward_accumulate    2C x C  (both local query chunks see the visitor's low chunk)
-//     source > rank    mfa_attention_forward_accumulate     C x 2C (the high query chunk sees both chunks of the visitor)
-// and the partial (O, L) of a step is merged into the running result inside the attention epilogue.
+// One process per GPU.  The sequence is cut into 2*world chunks, rank r owns chunks r and 2*world-1-r (zig-zag, so causal work
+// is balanced) stored next to each other: q / k / v are [B, H, 2C, D] with the low chunk first.  Q stays put; the K/V pair of
+// rank (r - s) mod world reaches rank r at step s = 1 .. world-1.
 //
-// Transport: ncclSend / ncclRecv of the K and V halves, grouped, on a highest-priority side stream, double-buffered so hop s+1
-// overlaps the attention of hop s.  NCCL is resolved at run time (dlopen of libnccl.so.2: the copy the host process already
-// loaded -- e.g. PyTorch's -- or the system one), so libMFAFFI.so keeps loading on machines without NCCL.
-// The attention grid is persistent (one CTA per SM), so an SM-resident NCCL kernel would only be scheduled when the grid ends:
-// while a hop is in flight the step's attention launch leaves `reserve_sms` SMs to the transport (mfa_ring_set_reserved_sms).
+// B200-first shape of the algorithm: a B200 has memory to spare (180 GB), so the visiting pairs are not double-buffered and
+// thrown away -- every step lands in its own slot -- and NVSwitch gives every pair of GPUs full bandwidth, so step s is a direct
+// exchange with rank r +- s (ncclSend / ncclRecv grouped per step on a highest-priority side stream), not a store-and-forward
+// chain.  The compute side is then ONE persistent attention launch per forward (attn_fwd_tc.cu, launch_fwd_tc_ring): every work
+// item walks its own causal block and then the visiting slots in arrival order, the kernel's TMA producer warps polling a
+// per-slot arrival flag the side stream raises behind each step.  O stays in TMEM across all ring steps: no partial (O, L) is
+// merged or written, there is no per-step launch, and the exchange overlaps the whole computation.
+//
+// NCCL is resolved at run time (dlopen of libnccl.so.2: the copy the host process already loaded -- e.g. PyTorch's -- or the
+// system one), so libMFAFFI.so keeps loading on machines without NCCL.  NCCL's send / recv kernels are SM resident and the
+// attention grid is persistent, so the launch leaves `reserve_sms` SMs (default 8) to the transport while hops are in flight.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -27,10 +29,6 @@
 #include <new>
 
 #include "../../include/mfa_ffi_ext.h"
-
-namespace mfa {
-void fwd_tc_set_sm_limit(int sms);      // attn_fwd_tc.cu: cap the persistent grid of the next launches (0 = all SMs)
-}
 
 namespace {
 
@@ -76,15 +74,41 @@ NcclApi& nccl() {
   return api;
 }
 
+// arrival flag of a slot, raised on the transport stream behind the step's receives
+__global__ void ring_raise_flag_kernel(unsigned int* flag, unsigned int value) {
+  *reinterpret_cast<volatile unsigned int*>(flag) = value;
+  __threadfence_system();
+}
+
+typedef CUresult (*StreamWriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWriteValue32Fn stream_write_value32() {
+  static StreamWriteValue32Fn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    if (getenv("MFA_RING_FLAG_KERNEL")) return;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &ptr, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<StreamWriteValue32Fn>(ptr);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
 struct Ring {
   mfa_context_t ctx = nullptr;
   int rank = 0, world = 1, device = 0;
   ncclComm_t comm = nullptr;
   bool own_comm = false;
   cudaStream_t comm_stream = nullptr;
-  cudaEvent_t ev_ready = nullptr, ev_arrived[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
-  void* kv[2] = {nullptr, nullptr};        // visiting K/V pairs: [K | V], each B*H*2C*D elements
-  size_t kv_cap = 0;
+  cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+  bool have_done = false;
+  void* k_visit = nullptr;                  // [world-1][B][H][2C][D]
+  void* v_visit = nullptr;
+  size_t visit_cap = 0;                     // bytes per array
+  unsigned int* flags = nullptr;            // [world] device words
+  unsigned int epoch = 0;
   int reserve_sms = 8;
   unsigned long long launches = 0;
   std::mutex mu;
@@ -93,25 +117,20 @@ struct Ring {
 bool debug_on() { const char* d = getenv("MFA_DEBUG"); return d && d[0] && d[0] != '0'; }
 #define RDBG(...) do { if (debug_on()) { fprintf(stderr, "[mfa ring] " __VA_ARGS__); fputc('\n', stderr); } } while (0)
 
-// the rectangular problem of ring step `step` on rank `rank` (umfa/ring.py step_plan; units of chunks)
-struct Plan { int q0, qn, k0, kn; bool causal; };
-Plan step_plan(int rank, int world, int step) {
-  const int src = ((rank - step) % world + world) % world;
-  if (src == rank) return {0, 2, 0, 2, true};
-  if (src < rank) return {0, 2, 0, 1, false};
-  return {1, 1, 0, 2, false};
+mfa_error_t ring_finish_create(Ring* r, mfa_ring_t* out) {
+  cudaGetDevice(&r->device);
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);                  // hi = numerically lowest = highest priority
+  bool ok = cudaStreamCreateWithPriority(&r->comm_stream, cudaStreamNonBlocking, hi) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&r->ev_ready, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaMalloc(&r->flags, sizeof(unsigned int) * (size_t)(r->world + 1)) == cudaSuccess;
+  ok = ok && cudaMemset(r->flags, 0, sizeof(unsigned int) * (size_t)(r->world + 1)) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); mfa_ring_destroy(reinterpret_cast<mfa_ring_t>(r)); return MFA_ERROR_EXECUTION_FAILED; }
+  if (const char* e = getenv("MFA_RING_RESERVE_SMS")) r->reserve_sms = atoi(e);
+  *out = reinterpret_cast<mfa_ring_t>(r);
+  return MFA_SUCCESS;
 }
-
-struct Handle {      // a transient strided device view as an mfa_buffer_t
-  mfa_buffer_t h = nullptr;
-  Handle(mfa_context_t ctx, void* base, size_t elem_off, size_t esz, int64_t B, int64_t H, int64_t rows, int64_t D, int64_t row_total) {
-    const int64_t shape[4] = {B, H, rows, D};
-    const int64_t strides[4] = {H * row_total * D, row_total * D, D, 1};
-    const size_t span = (size_t)((B - 1) * strides[0] + (H - 1) * strides[1] + (rows - 1) * D + D) * esz;
-    mfa_buffer_from_mtl_buffer_with_strides(ctx, reinterpret_cast<char*>(base) + elem_off * esz, span, shape, strides, 4, &h);
-  }
-  ~Handle() { if (h) mfa_destroy_buffer(h); }
-};
 
 }  // namespace
 
@@ -128,29 +147,13 @@ mfa_error_t mfa_ring_get_unique_id(void* id_out, size_t id_bytes) {
   return MFA_SUCCESS;
 }
 
-static mfa_error_t ring_finish_create(Ring* r, mfa_ring_t* out) {
-  int lo = 0, hi = 0;
-  cudaDeviceGetStreamPriorityRange(&lo, &hi);                  // hi = numerically lowest = highest priority
-  if (cudaStreamCreateWithPriority(&r->comm_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { cudaGetLastError(); delete r; return MFA_ERROR_EXECUTION_FAILED; }
-  bool ok = cudaEventCreateWithFlags(&r->ev_ready, cudaEventDisableTiming) == cudaSuccess;
-  for (int i = 0; i < 2; ++i) {
-    ok = ok && cudaEventCreateWithFlags(&r->ev_arrived[i], cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&r->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
-  }
-  if (!ok) { cudaGetLastError(); delete r; return MFA_ERROR_EXECUTION_FAILED; }
-  if (const char* e = getenv("MFA_RING_RESERVE_SMS")) r->reserve_sms = atoi(e);
-  *out = reinterpret_cast<mfa_ring_t>(r);
-  return MFA_SUCCESS;
-}
-
 mfa_error_t mfa_ring_create(mfa_context_t context, const void* unique_id, size_t id_bytes, int32_t rank, int32_t world_size,
                             mfa_ring_t* ring) {
-  if (!context || !ring || rank < 0 || world_size < 1 || rank >= world_size) return MFA_ERROR_INVALID_ARGS;
+  if (!context || !ring || rank < 0 || world_size < 1 || rank >= world_size || world_size > 255) return MFA_ERROR_INVALID_ARGS;
   *ring = nullptr;
   Ring* r = new (std::nothrow) Ring();
   if (!r) return MFA_ERROR_MEMORY_ALLOCATION;
   r->ctx = context; r->rank = rank; r->world = world_size;
-  cudaGetDevice(&r->device);
   if (world_size > 1) {
     if (!unique_id || id_bytes < sizeof(ncclUniqueId)) { delete r; return MFA_ERROR_INVALID_ARGS; }
     if (!nccl().ok) { delete r; return MFA_ERROR_DEVICE_NOT_SUPPORTED; }
@@ -168,39 +171,42 @@ mfa_error_t mfa_ring_create(mfa_context_t context, const void* unique_id, size_t
 }
 
 mfa_error_t mfa_ring_create_from_comm(mfa_context_t context, void* nccl_comm, int32_t rank, int32_t world_size, mfa_ring_t* ring) {
-  if (!context || !ring || rank < 0 || world_size < 1 || rank >= world_size) return MFA_ERROR_INVALID_ARGS;
+  if (!context || !ring || rank < 0 || world_size < 1 || rank >= world_size || world_size > 255) return MFA_ERROR_INVALID_ARGS;
   *ring = nullptr;
-  if (world_size > 1 && (!nccl_comm || !nccl().ok)) return nccl_comm ? MFA_ERROR_DEVICE_NOT_SUPPORTED : MFA_ERROR_INVALID_ARGS;
+  if (world_size > 1 && !nccl_comm) return MFA_ERROR_INVALID_ARGS;
+  if (world_size > 1 && !nccl().ok) return MFA_ERROR_DEVICE_NOT_SUPPORTED;
   Ring* r = new (std::nothrow) Ring();
   if (!r) return MFA_ERROR_MEMORY_ALLOCATION;
   r->ctx = context; r->rank = rank; r->world = world_size;
   r->comm = reinterpret_cast<ncclComm_t>(nccl_comm);
-  cudaGetDevice(&r->device);
   return ring_finish_create(r, ring);
 }
 
 void mfa_ring_destroy(mfa_ring_t ring) {
   if (!ring) return;
   Ring* r = reinterpret_cast<Ring*>(ring);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != r->device) cudaSetDevice(r->device);
   if (r->comm_stream) cudaStreamSynchronize(r->comm_stream);
   if (r->own_comm && r->comm) nccl().CommDestroy(r->comm);
-  for (int i = 0; i < 2; ++i) {
-    if (r->kv[i]) cudaFree(r->kv[i]);
-    if (r->ev_arrived[i]) cudaEventDestroy(r->ev_arrived[i]);
-    if (r->ev_consumed[i]) cudaEventDestroy(r->ev_consumed[i]);
-  }
+  if (r->k_visit) cudaFree(r->k_visit);
+  if (r->v_visit) cudaFree(r->v_visit);
+  if (r->flags) cudaFree(r->flags);
   if (r->ev_ready) cudaEventDestroy(r->ev_ready);
+  if (r->ev_done) cudaEventDestroy(r->ev_done);
   if (r->comm_stream) cudaStreamDestroy(r->comm_stream);
   cudaGetLastError();
+  if (prev >= 0 && prev != r->device) cudaSetDevice(prev);
   delete r;
 }
 
-void mfa_ring_set_reserved_sms(mfa_ring_t ring, int32_t sms) { if (ring) reinterpret_cast<Ring*>(ring)->reserve_sms = sms < 0 ? 0 : sms; }
+void mfa_ring_set_reserved_sms(mfa_ring_t ring, int32_t sms) { if (ring) reinterpret_cast<Ring*>(ring)->reserve_sms = sms < 1 ? 1 : sms; }
 uint64_t mfa_ring_launch_count(mfa_ring_t ring) { return ring ? reinterpret_cast<Ring*>(ring)->launches : 0; }
 
 // q, k, v: this rank's [low | high] chunk pair, device-resident, contiguous [B, H, 2C, D] in `precision` (bf16 / fp16).
-// out: fp32 [B, H, 2C, D], lse: fp32 [B, H, 2C] (log2 units).  Everything is enqueued on `stream` (the compute stream; hops on
-// the ring's own side stream) and the call returns without synchronising unless stream is NULL.
+// out: fp32 [B, H, 2C, D], lse: fp32 [B, H, 2C] (log2 units).  The attention launch is enqueued on `stream` (the exchange on
+// the ring's own side stream); the call returns without synchronising unless stream is NULL.
 mfa_error_t mfa_ring_attention_forward(mfa_ring_t ring, mfa_buffer_t q, mfa_buffer_t k, mfa_buffer_t v, mfa_buffer_t out,
                                        mfa_buffer_t lse, uint32_t batch_size, uint32_t chunk_rows, uint32_t num_heads,
                                        uint16_t head_dim, float softmax_scale, mfa_precision_t precision, void* stream) {
@@ -208,13 +214,11 @@ mfa_error_t mfa_ring_attention_forward(mfa_ring_t ring, mfa_buffer_t q, mfa_buff
   if (precision != MFA_PRECISION_BF16 && precision != MFA_PRECISION_FP16) return MFA_ERROR_INVALID_ARGS;
   Ring* r = reinterpret_cast<Ring*>(ring);
   std::lock_guard<std::mutex> lock(r->mu);
-  const int64_t B = batch_size, H = num_heads, C = chunk_rows, T = 2 * C, D = head_dim;
-  if (B == 0 || H == 0 || C == 0 || D == 0) return MFA_SUCCESS;
-  const size_t n = (size_t)B * H * T * D, esz = 2;
-  void* qd = mfa_buffer_contents(q);
+  const size_t n = (size_t)batch_size * num_heads * 2 * chunk_rows * head_dim, esz = 2;
+  if (n == 0) return MFA_SUCCESS;
   void* kd = mfa_buffer_contents(k);
   void* vd = mfa_buffer_contents(v);
-  if (!qd || !kd || !vd) return MFA_ERROR_INVALID_ARGS;
+  if (!kd || !vd) return MFA_ERROR_INVALID_ARGS;
   int prev_dev = -1;
   cudaGetDevice(&prev_dev);
   if (prev_dev != r->device) cudaSetDevice(r->device);
@@ -224,64 +228,63 @@ mfa_error_t mfa_ring_attention_forward(mfa_ring_t ring, mfa_buffer_t q, mfa_buff
   cudaStream_t own = nullptr;
   if (blocking) { if (cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking) != cudaSuccess) return MFA_ERROR_EXECUTION_FAILED; cs = own; }
   mfa_error_t rc = MFA_SUCCESS;
-  if (r->world > 1 && r->kv_cap < 2 * n * esz) {
-    for (int i = 0; i < 2; ++i) { if (r->kv[i]) cudaFree(r->kv[i]); r->kv[i] = nullptr; }
-    r->kv_cap = 0;
-    if (cudaMalloc(&r->kv[0], 2 * n * esz) != cudaSuccess || cudaMalloc(&r->kv[1], 2 * n * esz) != cudaSuccess) {
-      cudaGetLastError();
-      if (own) cudaStreamDestroy(own);
-      return MFA_ERROR_MEMORY_ALLOCATION;
+  const int W = r->world;
+  if (W > 1) {
+    const size_t need = (size_t)(W - 1) * n * esz;
+    if (r->visit_cap < need) {
+      if (r->have_done) cudaEventSynchronize(r->ev_done);
+      if (r->k_visit) cudaFree(r->k_visit);
+      if (r->v_visit) cudaFree(r->v_visit);
+      r->k_visit = r->v_visit = nullptr; r->visit_cap = 0;
+      if (cudaMalloc(&r->k_visit, need) != cudaSuccess || cudaMalloc(&r->v_visit, need) != cudaSuccess) {
+        cudaGetLastError();
+        if (own) cudaStreamDestroy(own);
+        return MFA_ERROR_MEMORY_ALLOCATION;
+      }
+      r->visit_cap = need;
     }
-    r->kv_cap = 2 * n * esz;
-  }
-  const int dst = (r->rank + 1) % r->world, src = (r->rank - 1 + r->world) % r->world;
-  char* cur_k = reinterpret_cast<char*>(kd);
-  char* cur_v = reinterpret_cast<char*>(vd);
-  cudaEventRecord(r->ev_ready, cs);                      // the caller's K / V were produced on the compute stream
-  for (int step = 0; step < r->world && rc == MFA_SUCCESS; ++step) {
-    const bool hop = step + 1 < r->world;
-    if (hop) {
-      const int nb = step & 1;
-      char* nk = reinterpret_cast<char*>(r->kv[nb]);
-      char* nv = nk + n * esz;
-      if (step == 0) cudaStreamWaitEvent(r->comm_stream, r->ev_ready, 0);
-      if (step >= 2) cudaStreamWaitEvent(r->comm_stream, r->ev_consumed[nb], 0);   // the attention of step-1 read this buffer
-      NcclApi& nc = nccl();
+    ++r->epoch;
+    // ---- the exchange: step s sends the rank's pair to rank + s and receives slot s from rank - s
+    cudaEventRecord(r->ev_ready, cs);                          // the caller's K / V were produced on the compute stream
+    cudaStreamWaitEvent(r->comm_stream, r->ev_ready, 0);
+    if (r->have_done) cudaStreamWaitEvent(r->comm_stream, r->ev_done, 0);     // the previous forward still reads the slots
+    NcclApi& nc = nccl();
+    for (int s = 1; s < W; ++s) {
+      const int dst = (r->rank + s) % W, src = (r->rank - s + W) % W;
+      char* nk = reinterpret_cast<char*>(r->k_visit) + (size_t)(s - 1) * n * esz;
+      char* nv = reinterpret_cast<char*>(r->v_visit) + (size_t)(s - 1) * n * esz;
       ncclResult_t e = nc.GroupStart();
-      if (e == 0) e = nc.Send(cur_k, n * esz, 0, dst, r->comm, r->comm_stream);
-      if (e == 0) e = nc.Send(cur_v, n * esz, 0, dst, r->comm, r->comm_stream);
+      if (e == 0) e = nc.Send(kd, n * esz, 0, dst, r->comm, r->comm_stream);
+      if (e == 0) e = nc.Send(vd, n * esz, 0, dst, r->comm, r->comm_stream);
       if (e == 0) e = nc.Recv(nk, n * esz, 0, src, r->comm, r->comm_stream);
       if (e == 0) e = nc.Recv(nv, n * esz, 0, src, r->comm, r->comm_stream);
       const ncclResult_t e2 = nc.GroupEnd();
-      if (e != 0 || e2 != 0) { RDBG("nccl send/recv: %s", nc.GetErrorString ? nc.GetErrorString(e ? e : e2) : "error"); rc = MFA_ERROR_EXECUTION_FAILED; break; }
-      cudaEventRecord(r->ev_arrived[nb], r->comm_stream);
+      if (e != 0 || e2 != 0) {
+        RDBG("nccl send/recv: %s", nc.GetErrorString ? nc.GetErrorString(e ? e : e2) : "error");
+        rc = MFA_ERROR_EXECUTION_FAILED;
+        break;
+      }
+      if (StreamWriteValue32Fn wv = stream_write_value32()) {
+        if (wv(r->comm_stream, reinterpret_cast<CUdeviceptr>(r->flags + s), r->epoch, 0) != CUDA_SUCCESS) rc = MFA_ERROR_EXECUTION_FAILED;
+      } else {
+        ring_raise_flag_kernel<<<1, 1, 0, r->comm_stream>>>(r->flags + s, r->epoch);
+        if (cudaGetLastError() != cudaSuccess) rc = MFA_ERROR_EXECUTION_FAILED;
+      }
+      if (rc != MFA_SUCCESS) break;
     }
-    const Plan pl = step_plan(r->rank, r->world, step);
-    {
-      Handle hq(r->ctx, qd, (size_t)pl.q0 * C * D, esz, B, H, (int64_t)pl.qn * C, D, T);
-      Handle hk(r->ctx, cur_k, (size_t)pl.k0 * C * D, esz, B, H, (int64_t)pl.kn * C, D, T);
-      Handle hv(r->ctx, cur_v, (size_t)pl.k0 * C * D, esz, B, H, (int64_t)pl.kn * C, D, T);
-      if (!hq.h || !hk.h || !hv.h) { rc = MFA_ERROR_MEMORY_ALLOCATION; break; }
-      mfa::fwd_tc_set_sm_limit(hop && r->reserve_sms > 0 ? -r->reserve_sms : 0);      // leave SMs to the transport while a hop runs
-      if (step == 0)
-        rc = mfa_attention_forward_ex(r->ctx, hq.h, hk.h, hv.h, out, lse, batch_size, (uint32_t)(pl.qn * C), (uint32_t)(pl.kn * C),
-                                      num_heads, head_dim, softmax_scale, pl.causal, -1, precision, MFA_PRECISION_FP32,
-                                      nullptr, 0, nullptr, nullptr, 0, MFA_MASK_TYPE_NONE, MFA_MASK_SCALAR_BYTE, cs);
-      else
-        rc = mfa_attention_forward_accumulate(r->ctx, hq.h, hk.h, hv.h, out, lse, batch_size, (uint32_t)(pl.qn * C),
-                                              (uint32_t)(pl.kn * C), num_heads, head_dim, softmax_scale, pl.causal, -1, precision,
-                                              (uint32_t)(pl.q0 * C), (uint32_t)T, cs);
-      mfa::fwd_tc_set_sm_limit(0);
-      ++r->launches;
-    }
-    if (rc != MFA_SUCCESS) break;
-    if (step >= 1) cudaEventRecord(r->ev_consumed[(step - 1) & 1], cs);        // this step's attention read kv[(step-1) & 1]
-    if (hop) {
-      const int nb = step & 1;
-      cudaStreamWaitEvent(cs, r->ev_arrived[nb], 0);
-      cur_k = reinterpret_cast<char*>(r->kv[nb]);
-      cur_v = cur_k + n * esz;
-    }
+  }
+  // ---- the computation: one persistent launch over the rank's own pair and every slot, in arrival order
+  if (rc == MFA_SUCCESS) {
+    rc = mfa_attention_forward_ring_slots(r->ctx, q, k, v, out, lse, r->k_visit, r->v_visit, r->flags, r->epoch, r->rank, W,
+                                          batch_size, chunk_rows, num_heads, head_dim, softmax_scale, precision,
+                                          W > 1 ? r->reserve_sms : 0, cs);
+    ++r->launches;
+  }
+  if (rc == MFA_SUCCESS && W > 1) { cudaEventRecord(r->ev_done, cs); r->have_done = true; }
+  if (rc != MFA_SUCCESS && W > 1) {
+    // never leave a launched kernel polling for slots that will not come: raise every flag
+    for (int s = 1; s < W; ++s) ring_raise_flag_kernel<<<1, 1, 0, r->comm_stream>>>(r->flags + s, r->epoch);
+    cudaGetLastError();
   }
   if (blocking) {
     if (cudaStreamSynchronize(cs) != cudaSuccess) { cudaGetLastError(); rc = rc == MFA_SUCCESS ? MFA_ERROR_EXECUTION_FAILED : rc; }

@@ -53,6 +53,25 @@ inline bool make_map(CUtensorMap* out, const TensorView& t, int dtype, int B, in
   return r == CUDA_SUCCESS;
 }
 
+// [slots][B][Hn][S][D] contiguous 16-bit operand -> 5-D tensor map (ring attention's visiting K/V pairs), same box / swizzle
+typedef CUresult (*EncodeTiledFn5)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline bool make_map5(CUtensorMap* out, const void* base, int dtype, int slots, int B, int Hn, int S, int D) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || slots < 1) return false;
+  const cuuint64_t eb = 2;
+  cuuint64_t dims[5] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)Hn, (cuuint64_t)B, (cuuint64_t)slots};
+  cuuint64_t st[4] = {(cuuint64_t)D * eb, (cuuint64_t)S * D * eb, (cuuint64_t)Hn * S * D * eb, (cuuint64_t)B * Hn * S * D * eb};
+  cuuint32_t box[5] = {64, 128, 1, 1, 1};
+  if (box[0] > (cuuint32_t)D) box[0] = (cuuint32_t)D;
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapDataType ty = dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(out, ty, 5, const_cast<void*>(base), dims, st, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 // TMA needs a 16-byte aligned base, unit inner stride and 16-byte multiples for the outer strides.
 inline bool view_ok(const TensorView& t, int64_t Hn, int64_t B, int elem_bytes = 2) {
   const int64_t q = 16 / elem_bytes;

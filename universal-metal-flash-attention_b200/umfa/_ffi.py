@@ -131,6 +131,16 @@ SIGNATURES = {
     "mfa_quantize": (_i32, [_ctx, _buf, _buf, _buf, _u64, _u64, _u32, _u32, _i32, _i32, _f32, _vp]),
     "mfa_dequantize": (_i32, [_ctx, _buf, _buf, _buf, _u64, _u64, _u32, _u32, _i32, _vp]),
     "mfa_merge_partials": (_i32, [_ctx, _buf, _buf, _buf, _buf, _u64, _u32, _vp]),
+    "mfa_ring_transport_available": (_b, []),
+    "mfa_ring_get_unique_id": (_i32, [_vp, _sz]),
+    "mfa_ring_create": (_i32, [_ctx, _vp, _sz, _i32, _i32, _c.POINTER(_vp)]),
+    "mfa_ring_create_from_comm": (_i32, [_ctx, _vp, _i32, _i32, _c.POINTER(_vp)]),
+    "mfa_ring_destroy": (None, [_vp]),
+    "mfa_ring_set_reserved_sms": (None, [_vp, _i32]),
+    "mfa_ring_launch_count": (_u64, [_vp]),
+    "mfa_ring_attention_forward": (_i32, [_vp, _buf, _buf, _buf, _buf, _buf, _u32, _u32, _u32, _u16, _f32, _i32, _vp]),
+    "mfa_attention_forward_ring_slots": (_i32, [_ctx, _buf, _buf, _buf, _buf, _buf, _vp, _vp, _vp, _u32, _i32, _i32,
+                                                _u32, _u32, _u32, _u16, _f32, _i32, _i32, _vp]),
     "mfa_set_device": (_i32, [_i32]),
     "mfa_get_device_count": (_i32, []),
     "mfa_last_kernel_name": (_c.c_char_p, [_ctx]),

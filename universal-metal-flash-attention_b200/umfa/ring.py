@@ -305,6 +305,12 @@ class PythonRingRunner:
     def forward(self, q_pair, k_pair, v_pair, scale):
         return ring_attention_forward(self.be, q_pair, k_pair, v_pair, self.rank, self.world, scale)
 
+    def pack(self, q_pair, k_pair, v_pair):
+        return (q_pair, k_pair, v_pair)
+
+    def forward_packed(self, pk, scale):
+        return self.forward(*pk, scale)
+
     def close(self):
         pass
 
