@@ -160,31 +160,32 @@ mfa_error_t mfa_attention_forward_accumulate(
  * One process per GPU; the sequence is cut into 2 * world chunks, rank r owns chunks r and 2 * world - 1 - r (zig-zag) stored
  * next to each other: q / k / v are device-resident contiguous [B, H, 2 * chunk_rows, D] (low chunk first), bf16 or fp16,
  * head_dim 64 or 128, chunk_rows a multiple of 256; out fp32 [B, H, 2 * chunk_rows, D], lse fp32 [B, H, 2 * chunk_rows] (log2).
- * The transport is NCCL (ncclSend / ncclRecv over NVLink), loaded at run time; the compute side is one persistent launch that
- * consumes the visiting K/V pairs as they arrive (csrc/ring.cu). */
+ * One attention launch per ring step, the partial (O, L) merged in the kernel epilogue; every visiting pair has its own slot and
+ * step s exchanges directly with ranks r +- s over NVLink / NVSwitch (csrc/ring.cu). */
 typedef struct mfa_ring_opaque* mfa_ring_t;
 bool mfa_ring_transport_available(void);                                   /* libnccl could be loaded */
 mfa_error_t mfa_ring_get_unique_id(void* id_out, size_t id_bytes);         /* 128-byte NCCL id: rank 0 makes it, the host distributes it */
+/* collective (ncclCommInitRank); unique_id NULL = no NCCL communicator, the ring can only use the p2p transport */
 mfa_error_t mfa_ring_create(mfa_context_t context, const void* unique_id, size_t id_bytes, int32_t rank, int32_t world_size,
-                            mfa_ring_t* ring);                             /* collective: ncclCommInitRank */
+                            mfa_ring_t* ring);
 mfa_error_t mfa_ring_create_from_comm(mfa_context_t context, void* nccl_comm, int32_t rank, int32_t world_size,
                                       mfa_ring_t* ring);                   /* caller-owned ncclComm_t of the same libnccl */
 void mfa_ring_destroy(mfa_ring_t ring);
-void mfa_ring_set_reserved_sms(mfa_ring_t ring, int32_t sms);              /* SMs left to NCCL's kernels during a forward (default 8) */
 uint64_t mfa_ring_launch_count(mfa_ring_t ring);
-/* collective; stream = cudaStream_t of the attention launch (NULL: an internal stream, the call blocks until O is ready) */
+int32_t mfa_ring_transport(mfa_ring_t ring);                               /* 0 = NCCL send / recv, 1 = p2p (copy engines) */
+/* p2p transport (copy engines push each K/V pair straight into the receiver's slot, stream memory operations order the
+ * streams; no SM takes part in a hop): prepare allocates the slots for the largest problem to come, export fills a blob of
+ * mfa_ring_handle_bytes() bytes (CUDA IPC handles), the host gathers the blobs of all ranks in rank order -- any channel -- and
+ * import opens them.  From then on mfa_ring_attention_forward uses p2p (MFA_RING_TRANSPORT=nccl|p2p picks the default). */
+size_t mfa_ring_handle_bytes(void);
+mfa_error_t mfa_ring_prepare(mfa_ring_t ring, uint32_t batch_size, uint32_t chunk_rows, uint32_t num_heads, uint16_t head_dim);
+mfa_error_t mfa_ring_export_handles(mfa_ring_t ring, void* blob_out, size_t blob_bytes);
+mfa_error_t mfa_ring_import_handles(mfa_ring_t ring, const void* blobs, size_t bytes_per_rank);
+/* collective; stream = cudaStream_t of the attention launches (NULL: an internal stream, the call blocks until O is ready) */
 mfa_error_t mfa_ring_attention_forward(
     mfa_ring_t ring, mfa_buffer_t q, mfa_buffer_t k, mfa_buffer_t v, mfa_buffer_t out, mfa_buffer_t lse,
     uint32_t batch_size, uint32_t chunk_rows, uint32_t num_heads, uint16_t head_dim, float softmax_scale,
     mfa_precision_t precision, void* stream);
-/* The compute half alone, for callers with their own transport: slot s (1 <= s < world) holds the K/V pair of rank
- * (rank - s) mod world at k_visit / v_visit + (s - 1) * B * H * 2 * chunk_rows * D elements and may be read once
- * arrival_flags[s] (device words) has reached `epoch` (serial-number comparison); reserve_sms SMs are left unused. */
-mfa_error_t mfa_attention_forward_ring_slots(
-    mfa_context_t context, mfa_buffer_t q, mfa_buffer_t k, mfa_buffer_t v, mfa_buffer_t out, mfa_buffer_t lse,
-    const void* k_visit, const void* v_visit, const uint32_t* arrival_flags, uint32_t epoch, int32_t rank, int32_t world_size,
-    uint32_t batch_size, uint32_t chunk_rows, uint32_t num_heads, uint16_t head_dim, float softmax_scale,
-    mfa_precision_t input_precision, int32_t reserve_sms, void* stream);
 
 /* Backward twin of the above (mask and window honoured; the reference's backward takes neither). */
 mfa_error_t mfa_attention_backward_ex(

@@ -185,74 +185,7 @@ def test_accumulate_many_items_per_cta():
     ctx.close()
 
 
-def _ring_slots_case(world, late_flags=False):
-    """All ranks of a single-launch ring (mfa_attention_forward_ring_slots) one after the other on one GPU: slot s of rank r is
-    filled by hand with the packed K/V of rank (r - s) mod world, exactly what the NCCL exchange of csrc/ring.cu delivers."""
-    import ctypes
-    import time
-    import torch
-    sys.path.insert(0, os.path.join(ROOT, "universal-metal-flash-attention_b200"))
-    import umfa
-    from umfa import ring
-    from umfa._ffi import _lib
-    dev = torch.device("cuda", 0)
-    rng = np.random.default_rng(23)
-    B, H, D, C = 1, 3, 128, 256
-    N = 2 * C * world
-    q, k, v = (rng.standard_normal((B, H, N, D)).astype(np.float32) for _ in range(3))
-    o_ref, l_ref = O.attention_forward(*(O.round_bf16(x)[0] for x in (q, k, v)), causal=True)
-    ctx = umfa.MFAContext()
-    pack = lambda x, r: torch.cat([_bf16_dev(c, dev) for c in ring.shard_sequence(x, r, world)], dim=2).contiguous()
-    packed_k = [pack(k, r) for r in range(world)]
-    packed_v = [pack(v, r) for r in range(world)]
-    side = torch.cuda.Stream(dev)
-    for r in range(world):
-        qd = pack(q, r)
-        out = torch.zeros(B, H, 2 * C, D, device=dev, dtype=torch.float32)
-        lse = torch.zeros(B, H, 2 * C, device=dev, dtype=torch.float32)
-        kvis = torch.stack([packed_k[(r - s) % world] for s in range(1, world)]).contiguous() if world > 1 else None
-        vvis = torch.stack([packed_v[(r - s) % world] for s in range(1, world)]).contiguous() if world > 1 else None
-        epoch = 7 + r
-        flags = torch.full((world + 1,), epoch - 1 if late_flags else epoch, device=dev, dtype=torch.int32)
-        bufs = [umfa.MFABuffer(ctx, device_ptr=t.data_ptr(), size=t.numel() * t.element_size()) for t in (qd, packed_k[r], packed_v[r], out, lse)]
-        torch.cuda.synchronize(dev)
-        st = torch.cuda.Stream(dev)                # a real stream: NULL would make the call blocking (it could never see late flags)
-        rc = _lib.mfa_attention_forward_ring_slots(
-            ctx.handle, *[b.handle for b in bufs], ctypes.c_void_p(kvis.data_ptr() if world > 1 else 0),
-            ctypes.c_void_p(vvis.data_ptr() if world > 1 else 0), ctypes.c_void_p(flags.data_ptr()), epoch, r, world,
-            B, C, H, D, 1.0 / np.sqrt(D), 1, 4, ctypes.c_void_p(st.cuda_stream))
-        assert rc == 0, rc
-        assert ctx.last_kernel.startswith("fwd_tc_ring_"), ctx.last_kernel
-        if late_flags and world > 1:
-            time.sleep(0.05)                       # the launch is polling for slot 1 by now
-            with torch.cuda.stream(side):
-                for s in range(1, world):
-                    flags[s:s + 1].fill_(epoch)
-                    time.sleep(0.01)
-        torch.cuda.synchronize(dev)
-        for b in bufs:
-            b.close()
-        lo, hi = ring.chunk_ids(r, world)
-        got_o, got_l = out.cpu().numpy(), lse.cpu().numpy()
-        for cid, sl in ((lo, slice(0, C)), (hi, slice(C, 2 * C))):
-            ref = o_ref[:, :, cid * C:(cid + 1) * C]
-            assert np.abs(got_o[:, :, sl] - ref).max() / np.abs(ref).max() < 2e-2, (r, cid)
-            assert np.abs(got_l[:, :, sl] - l_ref[:, :, cid * C:(cid + 1) * C]).max() < 2e-2, (r, cid)
-    ctx.close()
-
-
-@pytest.mark.parametrize("world", [1, 2, 4])
-def test_ring_single_launch_all_ranks_on_one_gpu(world):
-    _ring_slots_case(world)
-
-
-def test_ring_single_launch_waits_for_arrival_flags():
-    """The slots' arrival flags are raised from another stream while the launch is already running: the producer warps must
-    not read a slot before its flag reaches the epoch (and must proceed once it does)."""
-    _ring_slots_case(3, late_flags=True)
-
-
-def _run_native_rank(rank, world, port, N, out_dir):
+def _run_native_rank(rank, world, port, N, out_dir, transport="nccl"):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ROOT, "universal-metal-flash-attention_b200"))
@@ -268,25 +201,51 @@ def _run_native_rank(rank, world, port, N, out_dir):
     B, H, D = 1, 2, 128
     q, k, v = (rng.standard_normal((B, H, N, D)).astype(np.float32) for _ in range(3))
     ctx = umfa.MFAContext()
+    os.environ["MFA_RING_TRANSPORT"] = transport
     runner = ring.make_runner(ctx, dist, dev, "bf16", rank, world)
     assert runner.kind.startswith("native"), runner.kind
     sh = lambda x: tuple(torch.from_numpy(np.ascontiguousarray(c)).to(dev).to(torch.bfloat16).contiguous()
                          for c in ring.shard_sequence(x, rank, world))
-    for _ in range(2):                                 # twice: the second forward reuses the slots behind ev_done
-        (o_lo, l_lo), (o_hi, l_hi) = runner.forward(sh(q), sh(k), sh(v), 1.0 / np.sqrt(D))
+    pk = runner.pack(sh(q), sh(k), sh(v))
+    for _ in range(3):                                 # repeated: later forwards reuse the slots (ev_done / consumed flags)
+        (o_lo, l_lo), (o_hi, l_hi) = runner.forward_packed(pk, 1.0 / np.sqrt(D))
     torch.cuda.synchronize(dev)
+    assert runner.transport.lower().startswith(transport), runner.transport
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), o_lo=o_lo.cpu().numpy(), l_lo=l_lo.cpu().numpy(),
              o_hi=o_hi.cpu().numpy(), l_hi=l_hi.cpu().numpy())
     runner.close()
     dist.destroy_process_group()
 
 
-def test_ring_native_world2_nccl(tmp_path):
-    """csrc/ring.cu end to end over real NCCL: needs two GPUs (skipped on a one-GPU box)."""
+@pytest.mark.parametrize("transport", ["nccl", "p2p"])
+def test_ring_native_world2(tmp_path, transport):
+    """csrc/ring.cu end to end over NVLink, both transports: needs two GPUs (skipped on a one-GPU box)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_run_native_rank, args=(2, port, 2048, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_run_native_rank, args=(2, port, 2048, str(tmp_path), transport), nprocs=2, join=True)
     _check(tmp_path, 2, 2048)
+
+
+def test_ring_native_world1(tmp_path):
+    """the native driver with a world of one (no transport): a single causal launch through mfa_ring_attention_forward"""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "universal-metal-flash-attention_b200"))
+    import umfa
+    from umfa import ring
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(11)
+    B, H, D, N = 1, 2, 128, 1024
+    q, k, v = (rng.standard_normal((B, H, N, D)).astype(np.float32) for _ in range(3))
+    ctx = umfa.MFAContext()
+    runner = ring.make_runner(ctx, None, dev, "bf16", 0, 1)
+    assert runner.kind.startswith("native"), runner.kind
+    sh = lambda x: tuple(_bf16_dev(c, dev) for c in ring.shard_sequence(x, 0, 1))
+    (o_lo, l_lo), (o_hi, l_hi) = runner.forward(sh(q), sh(k), sh(v), 1.0 / np.sqrt(D))
+    torch.cuda.synchronize(dev)
+    np.savez(os.path.join(str(tmp_path), "rank0.npz"), o_lo=o_lo.cpu().numpy(), l_lo=l_lo.cpu().numpy(),
+             o_hi=o_hi.cpu().numpy(), l_hi=l_hi.cpu().numpy())
+    runner.close()
+    _check(tmp_path, 1, 1024)

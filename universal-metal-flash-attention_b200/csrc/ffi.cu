@@ -17,7 +17,6 @@
 
 #include "../../include/mfa_ffi_ext.h"
 #include "common.h"
-#include "fwd_tc.h"
 
 using namespace mfa;
 
@@ -1039,56 +1038,6 @@ mfa_error_t mfa_attention_forward_accumulate(
   if (e != cudaSuccess) return cuda_fail(e, "forward accumulate launch");
   if (!stream) {
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "forward accumulate sync");
-    tm.read();
-  }
-  return MFA_SUCCESS;
-}
-
-// The compute half of ring attention (ring.cu drives it; also the entry point for callers with their own transport and for the
-// single-GPU tests): ONE persistent launch over the rank's own causal [low | high] pair and the visiting K/V pairs of the other
-// ranks, slot s = the pair of rank (rank - s) mod world at k_visit / v_visit [s - 1][B][H][2C][D], read once flags[s] >= epoch.
-mfa_error_t mfa_attention_forward_ring_slots(
-    mfa_context_t context, mfa_buffer_t q, mfa_buffer_t k, mfa_buffer_t v, mfa_buffer_t out, mfa_buffer_t lse,
-    const void* k_visit, const void* v_visit, const uint32_t* arrival_flags, uint32_t epoch, int32_t rank, int32_t world_size,
-    uint32_t batch_size, uint32_t chunk_rows, uint32_t num_heads, uint16_t head_dim, float softmax_scale,
-    mfa_precision_t input_precision, int32_t reserve_sms, void* stream) {
-  if (!context || !q || !k || !v || !out || !lse) return MFA_ERROR_INVALID_ARGS;
-  Context* ctx = C_(context);
-  Buffer *bq = B_(q), *bk = B_(k), *bv = B_(v), *bo = B_(out), *bl = B_(lse);
-  const int in_dtype = header_precision_to_dtype(input_precision);
-  if (in_dtype != kBF16 && in_dtype != kF16) return MFA_ERROR_INVALID_ARGS;
-  if (world_size < 1 || rank < 0 || rank >= world_size || world_size > 255) return MFA_ERROR_INVALID_ARGS;
-  if (world_size > 1 && (!k_visit || !v_visit || !arrival_flags)) return MFA_ERROR_INVALID_ARGS;
-  if (bq->mirrored || bk->mirrored || bv->mirrored || bo->mirrored || bl->mirrored) return MFA_ERROR_INVALID_ARGS;
-  if (bq->ndim || bk->ndim || bv->ndim) return MFA_ERROR_INVALID_ARGS;           // contiguous [B, H, 2C, D]
-  const uint64_t T = 2ull * chunk_rows;
-  if (T > 0x7fffffffull || (chunk_rows % 256) != 0) return MFA_ERROR_INVALID_ARGS;
-  const size_t n = elems(batch_size, num_heads, (uint32_t)T, head_dim);
-  if (bq->bytes < n * 2 || bk->bytes < n * 2 || bv->bytes < n * 2 || bo->bytes < n * 4 ||
-      bl->bytes < (size_t)batch_size * num_heads * T * 4)
-    return MFA_ERROR_INVALID_ARGS;
-  if (!device_ok(ctx->device)) return MFA_ERROR_DEVICE_NOT_SUPPORTED;
-  if (n == 0) return MFA_SUCCESS;
-  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
-  DeviceGuard dg(ctx->device);
-  cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
-  AttnParams p;
-  init_params(p, batch_size, num_heads, (uint32_t)T, (uint32_t)T, head_dim, softmax_scale, true, -1);
-  p.q = contiguous_view(bq->dev, num_heads, (int64_t)T, head_dim, false);
-  p.k = contiguous_view(bk->dev, num_heads, (int64_t)T, head_dim, false);
-  p.v = contiguous_view(bv->dev, num_heads, (int64_t)T, head_dim, false);
-  p.o = contiguous_view(bo->dev, num_heads, (int64_t)T, head_dim, false);
-  p.lse = reinterpret_cast<float*>(bl->dev);
-  p.in_dtype = in_dtype; p.o_dtype = kF32;
-  RingLaunch rl{rank, world_size, (int)chunk_rows, k_visit, v_visit, arrival_flags, epoch, reserve_sms};
-  Timer tm(ctx, st, stream == nullptr);
-  cudaError_t e = launch_fwd_tc_ring(p, rl, st);
-  tm.stop();
-  ctx->last_kernel = g_last_kernel;
-  if (e == cudaErrorInvalidValue) { cudaGetLastError(); return MFA_ERROR_INVALID_ARGS; }
-  if (e != cudaSuccess) return cuda_fail(e, "ring forward launch");
-  if (!stream) {
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "ring forward sync");
     tm.read();
   }
   return MFA_SUCCESS;

@@ -22,17 +22,6 @@ struct FwdTcParams {
   int o_dtype;
   int H, Hkv, Sq, Skv;
   int nbatch;              // set by launch_fwd_tc_kernel (work items = query blocks x H x nbatch)
-  // dynamic work scheduling (set by launch_fwd_tc_kernel): CTAs take their first item from blockIdx.x and every further one
-  // as gridDim.x + (atomicAdd(sched_counter, 1) - sched_base); null = static striding by gridDim.x
-  unsigned int* sched_counter;
-  unsigned int sched_base;
-  // single-launch ring attention (ring.cu; ring_world <= 1 = off): the rank's own [low | high] K/V through tk / tv, the visiting
-  // pairs of slots 1 .. world-1 through the 5-D maps tkr / tvr ([slot-1][B][H][2C][D]); slot s may be read once
-  // ring_flags[s] has reached ring_epoch
-  CUtensorMap tkr, tvr;
-  int ring_rank, ring_world, ring_C;
-  const unsigned int* ring_flags;
-  unsigned int ring_epoch;
   float c;                 // softmax_scale * log2(e)
   int causal, window;
   // kFwdI8 only: symmetric scales of the int8 codes (value = code * scale)
@@ -62,17 +51,6 @@ bool fwd_tc_mask_ok(const AttnParams& p);
 void fwd_tc_set_mask(FwdTcParams& prm, const AttnParams& p);
 cudaError_t fwd_tc_build_mask_tiles(FwdTcParams& prm, const AttnParams& p, cudaStream_t st);
 void fwd_tc_set_out_map(FwdTcParams& prm, const AttnParams& p);
-
-// Single-launch ring forward: p describes the rank's own causal [low | high] problem (Sq = Skv = 2 * chunk_rows).
-struct RingLaunch {
-  int rank, world, chunk_rows;
-  const void* k_visit;            // [world-1][B][H][2C][D], slot s at index s-1
-  const void* v_visit;
-  const unsigned int* flags;      // [world] device words, flags[s] >= epoch once slot s has arrived
-  unsigned int epoch;
-  int reserve_sms;                // SMs left to the transport while hops are in flight
-};
-cudaError_t launch_fwd_tc_ring(const AttnParams& p, const RingLaunch& r, cudaStream_t st);
 
 // grid = (ceil(Sq / 256), H, B).  mode kFwdI8 needs D == 128 (Q / K tiles are int8, V tiles bf16).
 cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm, int D, int mode, cudaStream_t st, int B);

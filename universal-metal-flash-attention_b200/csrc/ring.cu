@@ -4,20 +4,28 @@
 // overlapped with compute".
 //
 // One process per GPU.  The sequence is cut into 2*world chunks, rank r owns chunks r and 2*world-1-r (zig-zag, so causal work
-// is balanced) stored next to each other: q / k / v are [B, H, 2C, D] with the low chunk first.  Q stays put; the K/V pair of
-// rank (r - s) mod world reaches rank r at step s = 1 .. world-1.
+// is balanced) stored next to each other: q / k / v are [B, H, 2C, D] with the low chunk first.  Q stays put; at step s the
+// rank works on the K/V pair of rank (r - s) mod world.  With that layout the visible chunk pairs of a step are ONE rectangular
+// problem (step_plan), i.e. one attention launch per step through the library's own C entry points:
+//     step 0           mfa_attention_forward_ex            causal 2C x 2C on local indices
+//     source < rank    mfa_attention_forward_accumulate    2C x C  (both local query chunks see the visitor's low chunk)
+//     source > rank    mfa_attention_forward_accumulate     C x 2C (the high query chunk sees both chunks of the visitor)
+// the partial (O, L) of a step being merged into the running result inside the attention epilogue.
 //
-// B200-first shape of the algorithm: a B200 has memory to spare (180 GB), so the visiting pairs are not double-buffered and
-// thrown away -- every step lands in its own slot -- and NVSwitch gives every pair of GPUs full bandwidth, so step s is a direct
-// exchange with rank r +- s (ncclSend / ncclRecv grouped per step on a highest-priority side stream), not a store-and-forward
-// chain.  The compute side is then ONE persistent attention launch per forward (attn_fwd_tc.cu, launch_fwd_tc_ring): every work
-// item walks its own causal block and then the visiting slots in arrival order, the kernel's TMA producer warps polling a
-// per-slot arrival flag the side stream raises behind each step.  O stays in TMEM across all ring steps: no partial (O, L) is
-// merged or written, there is no per-step launch, and the exchange overlaps the whole computation.
-//
-// NCCL is resolved at run time (dlopen of libnccl.so.2: the copy the host process already loaded -- e.g. PyTorch's -- or the
-// system one), so libMFAFFI.so keeps loading on machines without NCCL.  NCCL's send / recv kernels are SM resident and the
-// attention grid is persistent, so the launch leaves `reserve_sms` SMs (default 8) to the transport while hops are in flight.
+// B200-first shape of the exchange: a B200 has memory to spare (180 GB), so every visiting pair lands in its own slot (no
+// double-buffer hand-shake inside a forward), and NVSwitch gives every pair of GPUs full bandwidth, so step s is a DIRECT
+// exchange with ranks r +- s instead of a store-and-forward chain: all world-1 transfers of a forward only read the rank's own
+// K/V and are queued at once on a highest-priority side stream; step s of the computation waits for slot s alone.
+// Two transports:
+//   nccl   ncclSend / ncclRecv grouped per step (the north_star's wording).  NCCL is resolved at run time (dlopen of
+//          libnccl.so.2: the copy the host process already loaded -- e.g. PyTorch's -- or the system one), so libMFAFFI.so keeps
+//          loading on machines without it.  Its kernels are SM resident: they take SMs away from the attention grid while a
+//          hop runs.
+//   p2p    copy engines: the rank pushes its pair straight into the receiver's slot (peer memory mapped through CUDA IPC,
+//          cudaMemcpyAsync over NVLink) and raises the receiver's arrival flag behind it; compute streams wait on the flags
+//          with stream memory operations (cuStreamWaitValue32).  No SM and no host thread is involved in a hop.
+// (A single persistent launch that walks all slots behind arrival flags was built and measured too -- profiles/r02/
+// r02_forward_v2_postmortem.txt: every first-wave work item has to wait for the LAST slot, so it hides far less of the exchange.)
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -27,6 +35,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <vector>
 
 #include "../../include/mfa_ffi_ext.h"
 
@@ -74,48 +83,106 @@ NcclApi& nccl() {
   return api;
 }
 
-// arrival flag of a slot, raised on the transport stream behind the step's receives
-__global__ void ring_raise_flag_kernel(unsigned int* flag, unsigned int value) {
-  *reinterpret_cast<volatile unsigned int*>(flag) = value;
-  __threadfence_system();
-}
-
-typedef CUresult (*StreamWriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-StreamWriteValue32Fn stream_write_value32() {
-  static StreamWriteValue32Fn fn = nullptr;
+// ---- stream memory operations (driver API through the runtime's entry-point query: no libcuda at link time) -----------
+typedef CUresult (*StreamValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+struct MemOps { StreamValue32Fn write = nullptr, wait = nullptr; };
+MemOps& memops() {
+  static MemOps m;
   static std::once_flag once;
   std::call_once(once, [] {
-    if (getenv("MFA_RING_FLAG_KERNEL")) return;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &ptr, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<StreamWriteValue32Fn>(ptr);
-    else
+    auto get = [](const char* name) -> StreamValue32Fn {
+      void* ptr = nullptr;
+      cudaDriverEntryPointQueryResult qr;
+      if (cudaGetDriverEntryPoint(name, &ptr, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+        return reinterpret_cast<StreamValue32Fn>(ptr);
       cudaGetLastError();
+      return nullptr;
+    };
+    m.write = get("cuStreamWriteValue32");
+    m.wait = get("cuStreamWaitValue32");
   });
-  return fn;
+  return m;
 }
+
+enum Transport { kNccl = 0, kP2P = 1 };
+
+// what a rank publishes to its peers for the p2p transport
+struct PeerBlob {
+  cudaIpcMemHandle_t k_visit, v_visit, flags;
+  unsigned long long slot_bytes;          // bytes of one K (or V) slot the handles were made for
+};
+
+struct Peer {
+  char* k_visit = nullptr;
+  char* v_visit = nullptr;
+  unsigned int* flags = nullptr;
+  bool open = false;
+};
 
 struct Ring {
   mfa_context_t ctx = nullptr;
   int rank = 0, world = 1, device = 0;
+  int transport = kNccl;
   ncclComm_t comm = nullptr;
   bool own_comm = false;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+  std::vector<cudaEvent_t> ev_arrived;      // nccl transport: slot s has landed (recorded on the side stream)
   bool have_done = false;
-  void* k_visit = nullptr;                  // [world-1][B][H][2C][D]
-  void* v_visit = nullptr;
-  size_t visit_cap = 0;                     // bytes per array
-  unsigned int* flags = nullptr;            // [world] device words
+  char* k_visit = nullptr;                  // [world-1] slots of slot_bytes each; slot s at index s-1
+  char* v_visit = nullptr;
+  size_t slot_bytes = 0;
+  // flags[0 .. world)   arrival: slot s holds the pair of forward `epoch`     (written by the sender / the side stream)
+  // flags[world .. 2w)  consumed: the pair this rank pushed at step s has been read by its receiver in forward `epoch`
+  // flags[2w], [2w+1]   scratch words: sources of the 4-byte peer copies that raise remote flags (side / compute stream)
+  unsigned int* flags = nullptr;
+  std::vector<Peer> peers;
+  bool peers_ready = false;
   unsigned int epoch = 0;
-  int reserve_sms = 8;
   unsigned long long launches = 0;
   std::mutex mu;
 };
 
 bool debug_on() { const char* d = getenv("MFA_DEBUG"); return d && d[0] && d[0] != '0'; }
 #define RDBG(...) do { if (debug_on()) { fprintf(stderr, "[mfa ring] " __VA_ARGS__); fputc('\n', stderr); } } while (0)
+
+// the rectangular problem of ring step `step` on rank `rank` (units of chunks)
+struct Plan { int q0, qn, k0, kn; bool causal; };
+Plan step_plan(int rank, int world, int step) {
+  const int src = ((rank - step) % world + world) % world;
+  if (src == rank) return {0, 2, 0, 2, true};
+  if (src < rank) return {0, 2, 0, 1, false};
+  return {1, 1, 0, 2, false};
+}
+
+struct Handle {      // a transient strided device view as an mfa_buffer_t
+  mfa_buffer_t h = nullptr;
+  Handle(mfa_context_t ctx, void* base, size_t elem_off, size_t esz, int64_t B, int64_t H, int64_t rows, int64_t D, int64_t row_total) {
+    const int64_t shape[4] = {B, H, rows, D};
+    const int64_t strides[4] = {H * row_total * D, row_total * D, D, 1};
+    const size_t span = (size_t)((B - 1) * strides[0] + (H - 1) * strides[1] + (rows - 1) * D + D) * esz;
+    mfa_buffer_from_mtl_buffer_with_strides(ctx, reinterpret_cast<char*>(base) + elem_off * esz, span, shape, strides, 4, &h);
+  }
+  ~Handle() { if (h) mfa_destroy_buffer(h); }
+};
+
+struct DeviceScope {
+  int prev = -1;
+  explicit DeviceScope(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void close_peers(Ring* r) {
+  for (Peer& p : r->peers) {
+    if (!p.open) continue;
+    if (p.k_visit) cudaIpcCloseMemHandle(p.k_visit);
+    if (p.v_visit) cudaIpcCloseMemHandle(p.v_visit);
+    if (p.flags) cudaIpcCloseMemHandle(p.flags);
+    p = Peer();
+  }
+  r->peers_ready = false;
+  cudaGetLastError();
+}
 
 mfa_error_t ring_finish_create(Ring* r, mfa_ring_t* out) {
   cudaGetDevice(&r->device);
@@ -124,11 +191,28 @@ mfa_error_t ring_finish_create(Ring* r, mfa_ring_t* out) {
   bool ok = cudaStreamCreateWithPriority(&r->comm_stream, cudaStreamNonBlocking, hi) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&r->ev_ready, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming) == cudaSuccess;
-  ok = ok && cudaMalloc(&r->flags, sizeof(unsigned int) * (size_t)(r->world + 1)) == cudaSuccess;
-  ok = ok && cudaMemset(r->flags, 0, sizeof(unsigned int) * (size_t)(r->world + 1)) == cudaSuccess;
+  r->ev_arrived.assign((size_t)r->world, nullptr);
+  for (int s = 1; s < r->world && ok; ++s) ok = cudaEventCreateWithFlags(&r->ev_arrived[s], cudaEventDisableTiming) == cudaSuccess;
+  const size_t nflags = 2 * (size_t)r->world + 2;
+  ok = ok && cudaMalloc(&r->flags, sizeof(unsigned int) * nflags) == cudaSuccess;
+  ok = ok && cudaMemset(r->flags, 0, sizeof(unsigned int) * nflags) == cudaSuccess;
+  r->peers.assign((size_t)r->world, Peer());
   if (!ok) { cudaGetLastError(); mfa_ring_destroy(reinterpret_cast<mfa_ring_t>(r)); return MFA_ERROR_EXECUTION_FAILED; }
-  if (const char* e = getenv("MFA_RING_RESERVE_SMS")) r->reserve_sms = atoi(e);
+  if (const char* e = getenv("MFA_RING_TRANSPORT")) r->transport = strcmp(e, "p2p") == 0 ? kP2P : kNccl;
   *out = reinterpret_cast<mfa_ring_t>(r);
+  return MFA_SUCCESS;
+}
+
+mfa_error_t ensure_slots(Ring* r, size_t slot_bytes) {
+  if (r->world <= 1 || r->slot_bytes >= slot_bytes) return MFA_SUCCESS;
+  if (r->transport == kP2P && r->peers_ready) return MFA_ERROR_INVALID_ARGS;   // peers hold handles of the old slots: mfa_ring_prepare first
+  if (r->have_done) cudaEventSynchronize(r->ev_done);
+  if (r->k_visit) cudaFree(r->k_visit);
+  if (r->v_visit) cudaFree(r->v_visit);
+  r->k_visit = r->v_visit = nullptr; r->slot_bytes = 0;
+  const size_t total = slot_bytes * (size_t)(r->world - 1);
+  if (cudaMalloc(&r->k_visit, total) != cudaSuccess || cudaMalloc(&r->v_visit, total) != cudaSuccess) { cudaGetLastError(); return MFA_ERROR_MEMORY_ALLOCATION; }
+  r->slot_bytes = slot_bytes;
   return MFA_SUCCESS;
 }
 
@@ -154,8 +238,8 @@ mfa_error_t mfa_ring_create(mfa_context_t context, const void* unique_id, size_t
   Ring* r = new (std::nothrow) Ring();
   if (!r) return MFA_ERROR_MEMORY_ALLOCATION;
   r->ctx = context; r->rank = rank; r->world = world_size;
-  if (world_size > 1) {
-    if (!unique_id || id_bytes < sizeof(ncclUniqueId)) { delete r; return MFA_ERROR_INVALID_ARGS; }
+  if (world_size > 1 && unique_id) {                 // a NULL id creates a ring for the p2p transport only
+    if (id_bytes < sizeof(ncclUniqueId)) { delete r; return MFA_ERROR_INVALID_ARGS; }
     if (!nccl().ok) { delete r; return MFA_ERROR_DEVICE_NOT_SUPPORTED; }
     ncclUniqueId id;
     memcpy(&id, unique_id, sizeof(id));
@@ -167,7 +251,9 @@ mfa_error_t mfa_ring_create(mfa_context_t context, const void* unique_id, size_t
     }
     r->own_comm = true;
   }
-  return ring_finish_create(r, ring);
+  mfa_error_t e = ring_finish_create(r, ring);
+  if (e == MFA_SUCCESS && world_size > 1 && !unique_id) r->transport = kP2P;
+  return e;
 }
 
 mfa_error_t mfa_ring_create_from_comm(mfa_context_t context, void* nccl_comm, int32_t rank, int32_t world_size, mfa_ring_t* ring) {
@@ -185,28 +271,87 @@ mfa_error_t mfa_ring_create_from_comm(mfa_context_t context, void* nccl_comm, in
 void mfa_ring_destroy(mfa_ring_t ring) {
   if (!ring) return;
   Ring* r = reinterpret_cast<Ring*>(ring);
-  int prev = -1;
-  cudaGetDevice(&prev);
-  if (prev != r->device) cudaSetDevice(r->device);
+  DeviceScope ds(r->device);
   if (r->comm_stream) cudaStreamSynchronize(r->comm_stream);
+  close_peers(r);
   if (r->own_comm && r->comm) nccl().CommDestroy(r->comm);
   if (r->k_visit) cudaFree(r->k_visit);
   if (r->v_visit) cudaFree(r->v_visit);
   if (r->flags) cudaFree(r->flags);
   if (r->ev_ready) cudaEventDestroy(r->ev_ready);
   if (r->ev_done) cudaEventDestroy(r->ev_done);
+  for (cudaEvent_t e : r->ev_arrived) if (e) cudaEventDestroy(e);
   if (r->comm_stream) cudaStreamDestroy(r->comm_stream);
   cudaGetLastError();
-  if (prev >= 0 && prev != r->device) cudaSetDevice(prev);
   delete r;
 }
 
-void mfa_ring_set_reserved_sms(mfa_ring_t ring, int32_t sms) { if (ring) reinterpret_cast<Ring*>(ring)->reserve_sms = sms < 1 ? 1 : sms; }
 uint64_t mfa_ring_launch_count(mfa_ring_t ring) { return ring ? reinterpret_cast<Ring*>(ring)->launches : 0; }
+int32_t mfa_ring_transport(mfa_ring_t ring) { return ring ? reinterpret_cast<Ring*>(ring)->transport : -1; }
+
+// ---- p2p transport set-up: allocate the slots for the largest problem to come, publish their IPC handles, open the peers'.
+// prepare -> export -> (the host gathers every rank's blob, any channel) -> import; all three are collective in effect.
+size_t mfa_ring_handle_bytes(void) { return sizeof(PeerBlob); }
+
+mfa_error_t mfa_ring_prepare(mfa_ring_t ring, uint32_t batch_size, uint32_t chunk_rows, uint32_t num_heads, uint16_t head_dim) {
+  if (!ring) return MFA_ERROR_INVALID_ARGS;
+  Ring* r = reinterpret_cast<Ring*>(ring);
+  std::lock_guard<std::mutex> lock(r->mu);
+  DeviceScope ds(r->device);
+  close_peers(r);
+  return ensure_slots(r, (size_t)batch_size * num_heads * 2 * chunk_rows * head_dim * 2);
+}
+
+mfa_error_t mfa_ring_export_handles(mfa_ring_t ring, void* blob_out, size_t blob_bytes) {
+  if (!ring || !blob_out || blob_bytes < sizeof(PeerBlob)) return MFA_ERROR_INVALID_ARGS;
+  Ring* r = reinterpret_cast<Ring*>(ring);
+  std::lock_guard<std::mutex> lock(r->mu);
+  if (r->world > 1 && (!r->k_visit || !r->v_visit)) return MFA_ERROR_INVALID_ARGS;
+  DeviceScope ds(r->device);
+  PeerBlob b;
+  memset(&b, 0, sizeof(b));
+  b.slot_bytes = r->slot_bytes;
+  if (r->world > 1 && (cudaIpcGetMemHandle(&b.k_visit, r->k_visit) != cudaSuccess || cudaIpcGetMemHandle(&b.v_visit, r->v_visit) != cudaSuccess ||
+                       cudaIpcGetMemHandle(&b.flags, r->flags) != cudaSuccess)) {
+    RDBG("cudaIpcGetMemHandle: %s", cudaGetErrorString(cudaGetLastError()));
+    return MFA_ERROR_EXECUTION_FAILED;
+  }
+  memcpy(blob_out, &b, sizeof(b));
+  return MFA_SUCCESS;
+}
+
+mfa_error_t mfa_ring_import_handles(mfa_ring_t ring, const void* blobs, size_t bytes_per_rank) {
+  if (!ring || !blobs || bytes_per_rank < sizeof(PeerBlob)) return MFA_ERROR_INVALID_ARGS;
+  Ring* r = reinterpret_cast<Ring*>(ring);
+  std::lock_guard<std::mutex> lock(r->mu);
+  DeviceScope ds(r->device);
+  close_peers(r);
+  if (!memops().write || !memops().wait) return MFA_ERROR_DEVICE_NOT_SUPPORTED;
+  for (int p = 0; p < r->world; ++p) {
+    if (p == r->rank) continue;
+    PeerBlob b;
+    memcpy(&b, reinterpret_cast<const char*>(blobs) + (size_t)p * bytes_per_rank, sizeof(b));
+    if (b.slot_bytes != r->slot_bytes) return MFA_ERROR_INVALID_ARGS;           // every rank prepares for the same problem
+    Peer& pe = r->peers[p];
+    void *a = nullptr, *c = nullptr, *f = nullptr;
+    if (cudaIpcOpenMemHandle(&a, b.k_visit, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&c, b.v_visit, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&f, b.flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      RDBG("cudaIpcOpenMemHandle (peer %d): %s", p, cudaGetErrorString(cudaGetLastError()));
+      close_peers(r);
+      return MFA_ERROR_EXECUTION_FAILED;
+    }
+    pe.k_visit = reinterpret_cast<char*>(a); pe.v_visit = reinterpret_cast<char*>(c); pe.flags = reinterpret_cast<unsigned int*>(f);
+    pe.open = true;
+  }
+  r->peers_ready = true;
+  r->transport = kP2P;
+  return MFA_SUCCESS;
+}
 
 // q, k, v: this rank's [low | high] chunk pair, device-resident, contiguous [B, H, 2C, D] in `precision` (bf16 / fp16).
-// out: fp32 [B, H, 2C, D], lse: fp32 [B, H, 2C] (log2 units).  The attention launch is enqueued on `stream` (the exchange on
-// the ring's own side stream); the call returns without synchronising unless stream is NULL.
+// out: fp32 [B, H, 2C, D], lse: fp32 [B, H, 2C] (log2 units).  Attention launches go to `stream` (the exchange to the ring's own
+// side stream); the call returns without synchronising unless stream is NULL.
 mfa_error_t mfa_ring_attention_forward(mfa_ring_t ring, mfa_buffer_t q, mfa_buffer_t k, mfa_buffer_t v, mfa_buffer_t out,
                                        mfa_buffer_t lse, uint32_t batch_size, uint32_t chunk_rows, uint32_t num_heads,
                                        uint16_t head_dim, float softmax_scale, mfa_precision_t precision, void* stream) {
@@ -214,78 +359,101 @@ mfa_error_t mfa_ring_attention_forward(mfa_ring_t ring, mfa_buffer_t q, mfa_buff
   if (precision != MFA_PRECISION_BF16 && precision != MFA_PRECISION_FP16) return MFA_ERROR_INVALID_ARGS;
   Ring* r = reinterpret_cast<Ring*>(ring);
   std::lock_guard<std::mutex> lock(r->mu);
-  const size_t n = (size_t)batch_size * num_heads * 2 * chunk_rows * head_dim, esz = 2;
+  const int64_t B = batch_size, H = num_heads, C = chunk_rows, T = 2 * C, D = head_dim;
+  const size_t n = (size_t)B * H * T * D, esz = 2, bytes = n * esz;
   if (n == 0) return MFA_SUCCESS;
-  void* kd = mfa_buffer_contents(k);
-  void* vd = mfa_buffer_contents(v);
-  if (!kd || !vd) return MFA_ERROR_INVALID_ARGS;
-  int prev_dev = -1;
-  cudaGetDevice(&prev_dev);
-  if (prev_dev != r->device) cudaSetDevice(r->device);
-  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev != r->device ? prev_dev : -1};
+  void* qd = mfa_buffer_contents(q);
+  char* kd = reinterpret_cast<char*>(mfa_buffer_contents(k));
+  char* vd = reinterpret_cast<char*>(mfa_buffer_contents(v));
+  if (!qd || !kd || !vd) return MFA_ERROR_INVALID_ARGS;
+  DeviceScope ds(r->device);
+  const int W = r->world;
+  if (W > 1) {
+    if (r->transport == kNccl && !r->comm) return MFA_ERROR_INVALID_ARGS;
+    if (r->transport == kP2P && (!r->peers_ready || r->slot_bytes < bytes)) return MFA_ERROR_INVALID_ARGS;
+    if (mfa_error_t e = ensure_slots(r, bytes); e != MFA_SUCCESS) return e;
+  }
   cudaStream_t cs = reinterpret_cast<cudaStream_t>(stream);
   const bool blocking = stream == nullptr;
   cudaStream_t own = nullptr;
   if (blocking) { if (cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking) != cudaSuccess) return MFA_ERROR_EXECUTION_FAILED; cs = own; }
   mfa_error_t rc = MFA_SUCCESS;
-  const int W = r->world;
+  const unsigned int epoch = ++r->epoch;
+  unsigned int* arrived = r->flags;
+  unsigned int* consumed = r->flags + W;
+  unsigned int* scratch = r->flags + 2 * W;
+
+  // ---- the exchange: every transfer of this forward reads the rank's own pair only, so all of them are queued now
   if (W > 1) {
-    const size_t need = (size_t)(W - 1) * n * esz;
-    if (r->visit_cap < need) {
-      if (r->have_done) cudaEventSynchronize(r->ev_done);
-      if (r->k_visit) cudaFree(r->k_visit);
-      if (r->v_visit) cudaFree(r->v_visit);
-      r->k_visit = r->v_visit = nullptr; r->visit_cap = 0;
-      if (cudaMalloc(&r->k_visit, need) != cudaSuccess || cudaMalloc(&r->v_visit, need) != cudaSuccess) {
-        cudaGetLastError();
-        if (own) cudaStreamDestroy(own);
-        return MFA_ERROR_MEMORY_ALLOCATION;
-      }
-      r->visit_cap = need;
-    }
-    ++r->epoch;
-    // ---- the exchange: step s sends the rank's pair to rank + s and receives slot s from rank - s
     cudaEventRecord(r->ev_ready, cs);                          // the caller's K / V were produced on the compute stream
     cudaStreamWaitEvent(r->comm_stream, r->ev_ready, 0);
-    if (r->have_done) cudaStreamWaitEvent(r->comm_stream, r->ev_done, 0);     // the previous forward still reads the slots
-    NcclApi& nc = nccl();
-    for (int s = 1; s < W; ++s) {
-      const int dst = (r->rank + s) % W, src = (r->rank - s + W) % W;
-      char* nk = reinterpret_cast<char*>(r->k_visit) + (size_t)(s - 1) * n * esz;
-      char* nv = reinterpret_cast<char*>(r->v_visit) + (size_t)(s - 1) * n * esz;
-      ncclResult_t e = nc.GroupStart();
-      if (e == 0) e = nc.Send(kd, n * esz, 0, dst, r->comm, r->comm_stream);
-      if (e == 0) e = nc.Send(vd, n * esz, 0, dst, r->comm, r->comm_stream);
-      if (e == 0) e = nc.Recv(nk, n * esz, 0, src, r->comm, r->comm_stream);
-      if (e == 0) e = nc.Recv(nv, n * esz, 0, src, r->comm, r->comm_stream);
-      const ncclResult_t e2 = nc.GroupEnd();
-      if (e != 0 || e2 != 0) {
-        RDBG("nccl send/recv: %s", nc.GetErrorString ? nc.GetErrorString(e ? e : e2) : "error");
-        rc = MFA_ERROR_EXECUTION_FAILED;
-        break;
+    if (r->transport == kNccl) {
+      if (r->have_done) cudaStreamWaitEvent(r->comm_stream, r->ev_done, 0);     // the previous forward still reads the slots
+      NcclApi& nc = nccl();
+      for (int s = 1; s < W && rc == MFA_SUCCESS; ++s) {
+        const int dst = (r->rank + s) % W, src = (r->rank - s + W) % W;
+        ncclResult_t e = nc.GroupStart();
+        if (e == 0) e = nc.Send(kd, bytes, 0, dst, r->comm, r->comm_stream);
+        if (e == 0) e = nc.Send(vd, bytes, 0, dst, r->comm, r->comm_stream);
+        if (e == 0) e = nc.Recv(r->k_visit + (size_t)(s - 1) * r->slot_bytes, bytes, 0, src, r->comm, r->comm_stream);
+        if (e == 0) e = nc.Recv(r->v_visit + (size_t)(s - 1) * r->slot_bytes, bytes, 0, src, r->comm, r->comm_stream);
+        const ncclResult_t e2 = nc.GroupEnd();
+        if (e != 0 || e2 != 0) { RDBG("nccl send/recv: %s", nc.GetErrorString ? nc.GetErrorString(e ? e : e2) : "error"); rc = MFA_ERROR_EXECUTION_FAILED; }
+        cudaEventRecord(r->ev_arrived[s], r->comm_stream);
       }
-      if (StreamWriteValue32Fn wv = stream_write_value32()) {
-        if (wv(r->comm_stream, reinterpret_cast<CUdeviceptr>(r->flags + s), r->epoch, 0) != CUDA_SUCCESS) rc = MFA_ERROR_EXECUTION_FAILED;
-      } else {
-        ring_raise_flag_kernel<<<1, 1, 0, r->comm_stream>>>(r->flags + s, r->epoch);
-        if (cudaGetLastError() != cudaSuccess) rc = MFA_ERROR_EXECUTION_FAILED;
+    } else {
+      MemOps& mo = memops();
+      mo.write(r->comm_stream, reinterpret_cast<CUdeviceptr>(scratch), epoch, 0);        // source word of the remote flag writes
+      for (int s = 1; s < W && rc == MFA_SUCCESS; ++s) {
+        const int dst = (r->rank + s) % W;
+        Peer& pe = r->peers[dst];
+        // the receiver has read what this rank pushed into its slot s in the previous forward
+        if (epoch > 1) mo.wait(r->comm_stream, reinterpret_cast<CUdeviceptr>(consumed + s), epoch - 1, CU_STREAM_WAIT_VALUE_GEQ);
+        cudaError_t e = cudaMemcpyAsync(pe.k_visit + (size_t)(s - 1) * r->slot_bytes, kd, bytes, cudaMemcpyDefault, r->comm_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pe.v_visit + (size_t)(s - 1) * r->slot_bytes, vd, bytes, cudaMemcpyDefault, r->comm_stream);
+        // ... and only then its arrival flag (stream order): a 4-byte peer copy of the epoch word
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pe.flags + s, scratch, sizeof(unsigned int), cudaMemcpyDefault, r->comm_stream);
+        if (e != cudaSuccess) { RDBG("peer copy: %s", cudaGetErrorString(e)); cudaGetLastError(); rc = MFA_ERROR_EXECUTION_FAILED; }
       }
-      if (rc != MFA_SUCCESS) break;
     }
   }
-  // ---- the computation: one persistent launch over the rank's own pair and every slot, in arrival order
-  if (rc == MFA_SUCCESS) {
-    rc = mfa_attention_forward_ring_slots(r->ctx, q, k, v, out, lse, r->k_visit, r->v_visit, r->flags, r->epoch, r->rank, W,
-                                          batch_size, chunk_rows, num_heads, head_dim, softmax_scale, precision,
-                                          W > 1 ? r->reserve_sms : 0, cs);
-    ++r->launches;
+
+  // ---- the computation: one launch per step on the compute stream
+  char* cur_k = kd;
+  char* cur_v = vd;
+  for (int step = 0; step < W && rc == MFA_SUCCESS; ++step) {
+    if (step > 0) {
+      if (r->transport == kNccl) cudaStreamWaitEvent(cs, r->ev_arrived[step], 0);
+      else memops().wait(cs, reinterpret_cast<CUdeviceptr>(arrived + step), epoch, CU_STREAM_WAIT_VALUE_GEQ);
+      cur_k = r->k_visit + (size_t)(step - 1) * r->slot_bytes;
+      cur_v = r->v_visit + (size_t)(step - 1) * r->slot_bytes;
+    }
+    const Plan pl = step_plan(r->rank, W, step);
+    {
+      Handle hq(r->ctx, qd, (size_t)pl.q0 * C * D, esz, B, H, (int64_t)pl.qn * C, D, T);
+      Handle hk(r->ctx, cur_k, (size_t)pl.k0 * C * D, esz, B, H, (int64_t)pl.kn * C, D, T);
+      Handle hv(r->ctx, cur_v, (size_t)pl.k0 * C * D, esz, B, H, (int64_t)pl.kn * C, D, T);
+      if (!hq.h || !hk.h || !hv.h) { rc = MFA_ERROR_MEMORY_ALLOCATION; break; }
+      if (step == 0)
+        rc = mfa_attention_forward_ex(r->ctx, hq.h, hk.h, hv.h, out, lse, batch_size, (uint32_t)(pl.qn * C), (uint32_t)(pl.kn * C),
+                                      num_heads, head_dim, softmax_scale, pl.causal, -1, precision, MFA_PRECISION_FP32,
+                                      nullptr, 0, nullptr, nullptr, 0, MFA_MASK_TYPE_NONE, MFA_MASK_SCALAR_BYTE, cs);
+      else
+        rc = mfa_attention_forward_accumulate(r->ctx, hq.h, hk.h, hv.h, out, lse, batch_size, (uint32_t)(pl.qn * C),
+                                              (uint32_t)(pl.kn * C), num_heads, head_dim, softmax_scale, pl.causal, -1, precision,
+                                              (uint32_t)(pl.q0 * C), (uint32_t)T, cs);
+      ++r->launches;
+    }
+    if (rc != MFA_SUCCESS) break;
+    if (step > 0 && r->transport == kP2P) {
+      // tell the sender of this slot (rank - step) that it may be overwritten by the next forward: its consumed[step]
+      const int src = (r->rank - step + W) % W;
+      memops().write(cs, reinterpret_cast<CUdeviceptr>(scratch + 1), epoch, 0);      // the compute stream's own source word
+      cudaError_t e = cudaMemcpyAsync(r->peers[src].flags + W + step, scratch + 1, sizeof(unsigned int), cudaMemcpyDefault, cs);
+      if (e != cudaSuccess) { cudaGetLastError(); rc = MFA_ERROR_EXECUTION_FAILED; }
+    }
   }
   if (rc == MFA_SUCCESS && W > 1) { cudaEventRecord(r->ev_done, cs); r->have_done = true; }
-  if (rc != MFA_SUCCESS && W > 1) {
-    // never leave a launched kernel polling for slots that will not come: raise every flag
-    for (int s = 1; s < W; ++s) ring_raise_flag_kernel<<<1, 1, 0, r->comm_stream>>>(r->flags + s, r->epoch);
-    cudaGetLastError();
-  }
   if (blocking) {
     if (cudaStreamSynchronize(cs) != cudaSuccess) { cudaGetLastError(); rc = rc == MFA_SUCCESS ? MFA_ERROR_EXECUTION_FAILED : rc; }
     cudaStreamDestroy(own);

@@ -136,11 +136,13 @@ SIGNATURES = {
     "mfa_ring_create": (_i32, [_ctx, _vp, _sz, _i32, _i32, _c.POINTER(_vp)]),
     "mfa_ring_create_from_comm": (_i32, [_ctx, _vp, _i32, _i32, _c.POINTER(_vp)]),
     "mfa_ring_destroy": (None, [_vp]),
-    "mfa_ring_set_reserved_sms": (None, [_vp, _i32]),
+    "mfa_ring_transport": (_i32, [_vp]),
+    "mfa_ring_handle_bytes": (_sz, []),
+    "mfa_ring_prepare": (_i32, [_vp, _u32, _u32, _u32, _u16]),
+    "mfa_ring_export_handles": (_i32, [_vp, _vp, _sz]),
+    "mfa_ring_import_handles": (_i32, [_vp, _vp, _sz]),
     "mfa_ring_launch_count": (_u64, [_vp]),
     "mfa_ring_attention_forward": (_i32, [_vp, _buf, _buf, _buf, _buf, _buf, _u32, _u32, _u32, _u16, _f32, _i32, _vp]),
-    "mfa_attention_forward_ring_slots": (_i32, [_ctx, _buf, _buf, _buf, _buf, _buf, _vp, _vp, _vp, _u32, _i32, _i32,
-                                                _u32, _u32, _u32, _u16, _f32, _i32, _i32, _vp]),
     "mfa_set_device": (_i32, [_i32]),
     "mfa_get_device_count": (_i32, []),
     "mfa_last_kernel_name": (_c.c_char_p, [_ctx]),

@@ -1,25 +1,27 @@
 """Native ring attention: thin caller of libMFAFFI.so's mfa_ring_* symbols (csrc/ring.cu).
 
 The C side owns everything that matters -- the NCCL communicator (its own, made from a unique id), the side stream, the visiting
-K/V slots, the arrival flags and the single persistent attention launch per forward.  Python only moves the 128-byte unique id
-between the ranks (any host channel works; here torch.distributed, which the caller already has) and hands over device pointers.
+K/V slots, the arrival / consumed flags, the per-step attention launches.  Python only carries small blobs between the ranks (the
+128-byte NCCL id; for the p2p transport the CUDA IPC handles of the slots) over a channel the caller already has
+(torch.distributed here; any other works) and hands over device pointers.
 """
 import ctypes
+import os
 
 from . import _ffi
 from .core import MFABuffer
 
 
 class NativeRingRunner:
-    kind = "native driver (csrc/ring.cu: mfa_ring_attention_forward, one persistent launch per forward)"
-    transport = "NCCL ncclSend/ncclRecv (direct exchange with rank +- s per step)"
+    kind = "native driver (csrc/ring.cu: mfa_ring_attention_forward, one launch per ring step, merge in the epilogue)"
 
-    def __init__(self, ctx, dist, device, dtype, rank, world, reserve_sms=None):
+    def __init__(self, ctx, dist, device, dtype, rank, world, transport=None):
         import torch
-        self.torch, self.ctx, self.device, self.rank, self.world = torch, ctx, device, rank, world
+        self.torch, self.ctx, self.dist, self.device, self.rank, self.world = torch, ctx, dist, device, rank, world
         self.lib = _ffi._lib
         self.prec = {"bf16": 1, "fp16": 0}[dtype]
         self.handle = ctypes.c_void_p()
+        self.want = (transport or os.environ.get("MFA_RING_TRANSPORT", "p2p")).lower()      # copy engines unless asked for NCCL
         uid = (ctypes.c_uint8 * 128)()
         if world > 1:
             if not self.lib.mfa_ring_transport_available():
@@ -36,13 +38,39 @@ class NativeRingRunner:
             rc = self.lib.mfa_ring_create(ctx.handle, ctypes.cast(uid, ctypes.c_void_p), 128, rank, world, ctypes.byref(self.handle))
         if rc != 0:
             raise RuntimeError(f"mfa_ring_create failed: {rc}")
-        if reserve_sms is not None:
-            self.lib.mfa_ring_set_reserved_sms(self.handle, int(reserve_sms))
-        self.stream = torch.cuda.current_stream(device)
+        self._p2p_dims = None
+
+    @property
+    def transport(self):
+        t = int(self.lib.mfa_ring_transport(self.handle))
+        return ("NCCL ncclSend/ncclRecv, direct exchange with ranks r +- s" if t == 0 else
+                "p2p copy engines (CUDA IPC peer memory + stream memory operations), direct push to rank r + s")
 
     @property
     def launches(self):
         return int(self.lib.mfa_ring_launch_count(self.handle))
+
+    def _setup_p2p(self, B, C, H, D):
+        """prepare -> export -> all-gather of the handle blobs -> import (collective)"""
+        torch, lib = self.torch, self.lib
+        rc = lib.mfa_ring_prepare(self.handle, B, C, H, D)
+        if rc != 0:
+            raise RuntimeError(f"mfa_ring_prepare failed: {rc}")
+        nb = int(lib.mfa_ring_handle_bytes())
+        blob = (ctypes.c_uint8 * nb)()
+        rc = lib.mfa_ring_export_handles(self.handle, ctypes.cast(blob, ctypes.c_void_p), nb)
+        if rc != 0:
+            raise RuntimeError(f"mfa_ring_export_handles failed: {rc}")
+        mine = torch.frombuffer(bytearray(bytes(blob)), dtype=torch.uint8).to(self.device)
+        allb = [torch.zeros(nb, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
+        self.dist.all_gather(allb, mine)
+        flat = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allb)
+        buf = (ctypes.c_uint8 * len(flat)).from_buffer_copy(flat)
+        rc = lib.mfa_ring_import_handles(self.handle, ctypes.cast(buf, ctypes.c_void_p), nb)
+        if rc != 0:
+            raise RuntimeError(f"mfa_ring_import_handles failed: {rc}")
+        self.dist.barrier()
+        self._p2p_dims = (B, C, H, D)
 
     def pack(self, q_pair, k_pair, v_pair):
         """[low | high] chunk pairs -> the contiguous [B, H, 2C, D] operands the C API takes (do this once, outside timed loops)."""
@@ -52,6 +80,8 @@ class NativeRingRunner:
         o = torch.empty(B, H, T, D, device=self.device, dtype=torch.float32)
         l = torch.empty(B, H, T, device=self.device, dtype=torch.float32)
         bufs = [MFABuffer(self.ctx, device_ptr=t.data_ptr(), size=t.numel() * t.element_size()) for t in (q, k, v, o, l)]
+        if self.world > 1 and self.want == "p2p" and self._p2p_dims != (B, T // 2, H, D):
+            self._setup_p2p(B, T // 2, H, D)
         return {"t": (q, k, v, o, l), "b": bufs, "dims": (B, H, T // 2, D)}
 
     def forward_packed(self, pk, scale):
@@ -68,12 +98,15 @@ class NativeRingRunner:
         forward_packed."""
         pk = self.pack(q_pair, k_pair, v_pair)
         try:
-            return self.forward_packed(pk, scale)
+            res = self.forward_packed(pk, scale)
+            self.torch.cuda.current_stream(self.device).synchronize()      # the packed operands die with this call
+            return res
         finally:
             for b in pk["b"]:
                 b.close()
 
     def close(self):
         if self.handle:
+            self.torch.cuda.synchronize(self.device)
             self.lib.mfa_ring_destroy(self.handle)
             self.handle = ctypes.c_void_p()
