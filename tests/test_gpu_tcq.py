@@ -13,12 +13,30 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
+# P V precision of the quantised tensor-core forward: e4m3 (the default, BASELINE.json config 3) or bf16.  Bound of the output
+# against the oracle ON THE ORACLE'S DEQUANTISED OPERANDS, relative to max|ref|: bf16 P V = 2e-2 like every 16-bit path; e4m3 P and
+# V carry 2^-4 relative rounding each (independent per element, so it averages down with the number of keys a row attends to):
+# 6e-2 stated, measured 1e-2 .. 4e-2 on these shapes (zero-mean random V: O is a random-walk sum, so the relative error of O does
+# not shrink with the number of keys).  Both modes are held to the same cosine / rel-L2 bounds against the
+# UNQUANTISED oracle.
+PV_TOL = {"fp8": 6e-2, "bf16": 2e-2}
+PV_CODE = {"fp8": 5, "bf16": 1}
+
+
 @pytest.fixture(scope="module")
 def ctx():
     import umfa
     c = umfa.MFAContext()
     yield c
     c.close()
+
+
+@pytest.fixture(params=["fp8", "bf16"])
+def pv(request, ctx):
+    from umfa._ffi import _lib
+    assert _lib.mfa_set_quantized_pv_precision(ctx.handle, PV_CODE[request.param]) == 0
+    yield request.param
+    _lib.mfa_set_quantized_pv_precision(ctx.handle, PV_CODE["fp8"])
 
 
 def fake_quant(x, bits, mode, D):
@@ -40,7 +58,7 @@ def cosine(a, b):
     return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
 
 
-def run_case(ctx, B, H, Sq, Skv, target, mode, causal=False, seed=0, outliers=False, in_prec="fp32"):
+def run_case(ctx, B, H, Sq, Skv, target, mode, causal=False, seed=0, outliers=False, in_prec="fp32", pv="bf16"):
     import umfa
     D = 128
     bits = 8 if target == "int8" else 4
@@ -56,12 +74,12 @@ def run_case(ctx, B, H, Sq, Skv, target, mode, causal=False, seed=0, outliers=Fa
         args = (q, k, v)
     out, lse = umfa.runtime_quantized_attention(ctx, *args, target_precision=target, quant_mode=mode,
                                                 input_precision=in_prec, causal=causal)
-    assert ctx.last_kernel.startswith("fwd_tcq_"), ctx.last_kernel
+    assert ctx.last_kernel.startswith("fwd_tcq_") and ("pvf8" in ctx.last_kernel) == (pv == "fp8"), ctx.last_kernel
     qd, kd, vd = (fake_quant(x, bits, mode, D) for x in (q, k, v))
     o_ref, l_ref = O.attention_forward(qd, kd, vd, causal=causal)
     err = float(np.abs(out - o_ref).max() / np.abs(o_ref).max())
     assert np.isfinite(out).all()
-    assert err < 2e-2, f"vs dequantised oracle: {err}"
+    assert err < PV_TOL[pv], f"vs dequantised oracle ({pv} P V): {err}"
     assert np.abs(lse - l_ref).max() < 2e-2
     o_full, _ = O.attention_forward(q, k, v, causal=causal)
     cs, rl2 = cosine(out, o_full), O.rel_l2(out, o_full)
@@ -70,39 +88,39 @@ def run_case(ctx, B, H, Sq, Skv, target, mode, causal=False, seed=0, outliers=Fa
 
 @pytest.mark.parametrize("mode", [0, 2])
 @pytest.mark.parametrize("shape", [(1, 2, 256, 256), (1, 1, 128, 128), (2, 2, 300, 777), (1, 2, 1000, 130), (1, 1, 77, 515)])
-def test_tcq_int8_shapes(ctx, mode, shape):
+def test_tcq_int8_shapes(ctx, pv, mode, shape):
     B, H, Sq, Skv = shape
-    err, cs, rl2 = run_case(ctx, B, H, Sq, Skv, "int8", mode, seed=Sq)
+    err, cs, rl2 = run_case(ctx, B, H, Sq, Skv, "int8", mode, seed=Sq, pv=pv)
     assert cs >= 0.99 and rl2 < 0.25, (cs, rl2)
 
 
 @pytest.mark.parametrize("mode", [0, 2])
-def test_tcq_int8_causal(ctx, mode):
-    err, cs, rl2 = run_case(ctx, 1, 2, 640, 640, "int8", mode, causal=True, seed=3)
+def test_tcq_int8_causal(ctx, pv, mode):
+    err, cs, rl2 = run_case(ctx, 1, 2, 640, 640, "int8", mode, causal=True, seed=3, pv=pv)
     assert cs >= 0.99 and rl2 < 0.25
 
 
 @pytest.mark.parametrize("mode", [0, 2])
-def test_tcq_int4(ctx, mode):
-    err, cs, rl2 = run_case(ctx, 1, 2, 512, 512, "int4", mode, seed=4)
+def test_tcq_int4(ctx, pv, mode):
+    err, cs, rl2 = run_case(ctx, 1, 2, 512, 512, "int4", mode, seed=4, pv=pv)
     assert cs >= 0.95, cs
 
 
 def test_tcq_outlier_channels_block_scales_help(ctx):
     """With outlier K channels per-block scales must not be worse than per-tensor scales (SageAttention motivation)."""
-    _, cs_t, _ = run_case(ctx, 1, 2, 512, 512, "int8", 0, seed=5, outliers=True)
-    _, cs_b, _ = run_case(ctx, 1, 2, 512, 512, "int8", 2, seed=5, outliers=True)
+    _, cs_t, _ = run_case(ctx, 1, 2, 512, 512, "int8", 0, seed=5, outliers=True, pv="fp8")
+    _, cs_b, _ = run_case(ctx, 1, 2, 512, 512, "int8", 2, seed=5, outliers=True, pv="fp8")
     assert cs_t >= 0.99 and cs_b >= 0.99
 
 
-def test_tcq_bf16_inputs(ctx):
-    err, cs, rl2 = run_case(ctx, 1, 2, 384, 384, "int8", 2, seed=6, in_prec="bf16")
+def test_tcq_bf16_inputs(ctx, pv):
+    err, cs, rl2 = run_case(ctx, 1, 2, 384, 384, "int8", 2, seed=6, in_prec="bf16", pv=pv)
     assert cs >= 0.99
 
 
 @pytest.mark.parametrize("mode", [0, 2])
 @pytest.mark.parametrize("kind", ["dense", "neg_inf_blocks"])
-def test_tcq_int8_with_additive_mask(ctx, mode, kind):
+def test_tcq_int8_with_additive_mask(ctx, pv, mode, kind):
     """mfa_quantized_forward_with_lse's fp32 additive mask [B,H,Sq,Skv] (MFABridge+Quantized.swift:227) on the int8
     tensor-core kernel: mask read in place by the softmax warps, hidden KV tiles skipped."""
     import umfa
@@ -118,7 +136,7 @@ def test_tcq_int8_with_additive_mask(ctx, mode, kind):
     qd, kd, vd = (fake_quant(x, 8, mode, D) for x in (q, k, v))
     o_ref, l_ref = O.attention_forward(qd, kd, vd, mask=m)
     assert np.isfinite(out).all()
-    assert float(np.abs(out - o_ref).max() / np.abs(o_ref).max()) < 2e-2
+    assert float(np.abs(out - o_ref).max() / np.abs(o_ref).max()) < PV_TOL[pv]
     assert np.abs(lse - l_ref).max() < 2e-2
 
 
@@ -135,7 +153,7 @@ def _c3_inputs(seed):
 
 
 @pytest.mark.parametrize("target,mode,cos_min,maxabs", [("int8", 2, 0.99, 0.02), ("int8", 0, 0.99, 0.02), ("int4", 2, 0.95, 0.12)])
-def test_c3_flux_size_runtime_quantised(ctx, target, mode, cos_min, maxabs):
+def test_c3_flux_size_runtime_quantised(ctx, pv, target, mode, cos_min, maxabs):
     """mfa_quantized_forward_with_lse at N = 4608: runtime quantise (per tensor / blocks of 64 tokens) + tensor-core kernel."""
     import umfa
     q, k, v = _c3_inputs(11)
@@ -146,7 +164,9 @@ def test_c3_flux_size_runtime_quantised(ctx, target, mode, cos_min, maxabs):
     o_ref, l_ref = O.attention_forward(qd, kd, vd)
     assert np.isfinite(out).all()
     err = float(np.abs(out - o_ref).max() / np.abs(o_ref).max())
-    assert err < 2e-2, f"vs the oracle on dequantised operands: {err}"
+    # e4m3 P and V: the 2^-4 roundings do not average down against |O| here, because O itself is a random-walk sum of zero-mean V
+    # (measured 3.2e-2 .. 3.5e-2 at this size); bf16 P V is held to 2e-2
+    assert err < PV_TOL[pv], f"vs the oracle on dequantised operands ({pv} P V): {err}"
     assert np.abs(lse - l_ref).max() < 2e-2
     o_full, _ = O.attention_forward(q, k, v)
     cs, ma = cosine(out, o_full), float(np.abs(out - o_full).max())
@@ -154,7 +174,7 @@ def test_c3_flux_size_runtime_quantised(ctx, target, mode, cos_min, maxabs):
 
 
 @pytest.mark.parametrize("bits", [8, 4])
-def test_c3_flux_size_prequantised_entry_point(ctx, bits):
+def test_c3_flux_size_prequantised_entry_point(ctx, pv, bits):
     """mfa_attention_forward_quantized at N = 4608: caller-supplied int8 / packed int4 codes, per-tensor scales."""
     import umfa
     from umfa._ffi import _lib, _check_error
@@ -179,7 +199,7 @@ def test_c3_flux_size_prequantised_entry_point(ctx, bits):
     assert ctx.last_kernel.startswith("fwd_tcq_"), ctx.last_kernel
     o_ref, _ = O.attention_forward(*deq)
     assert np.isfinite(out).all()
-    assert float(np.abs(out - o_ref).max() / np.abs(o_ref).max()) < 2e-2
+    assert float(np.abs(out - o_ref).max() / np.abs(o_ref).max()) < PV_TOL[pv]
     o_full, _ = O.attention_forward(q, k, v)
     cs = cosine(out, o_full)
     # one scale for a whole [B*H*S, D] int4 tensor is the coarsest contract the ABI offers: 0.94 measured at this size

@@ -178,7 +178,7 @@ def test_quantisation_mode_routes_sdpa(torch_mod, adapter):
     finally:
         ext.clear_quantization_mode()
     assert ext.get_dispatch_stats()["quantized_autograd"] == 1
-    assert ext._context(q.device).last_kernel == "fwd_tcq_int8_d128"
+    assert ext._context(q.device).last_kernel.startswith("fwd_tcq_int8_")
     cos = torch.nn.functional.cosine_similarity(out.float().flatten(), ref_sdpa(torch, q, k, v).flatten(), dim=0).item()
     assert cos >= 0.99
 

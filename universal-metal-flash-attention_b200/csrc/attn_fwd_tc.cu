@@ -55,14 +55,15 @@ constexpr int kParts = 4;                    // P hand-off granularity: 32 keys 
 
 template <int D, int MODE>
 struct Cfg {
-  static constexpr bool kI8 = MODE == kFwdI8;
+  static constexpr bool kF8 = MODE == kFwdI8F8;                      // int8 Q K^T, e4m3 P V
+  static constexpr bool kI8 = MODE == kFwdI8 || kF8;                 // int8 Q K^T
   static constexpr int kChunkBytes = 128 * 128;                      // one 128-byte swizzle chunk of 128 rows
   static constexpr int kQChunks = kI8 ? 1 : D / 64;                  // chunks per Q / K tile
-  static constexpr int kVChunks = D / 64;                            // V is always 16-bit
+  static constexpr int kVChunks = kF8 ? 1 : D / 64;                  // V: 16-bit, or e4m3 (128 head dims = one 128-byte row)
   static constexpr int kQTile = kQChunks * kChunkBytes;
   static constexpr int kVTile = kVChunks * kChunkBytes;
   static constexpr int kStage = kVTile;                              // ring stage (K tiles may use part of it)
-  static constexpr int kStages = D == 128 ? 5 : 10;
+  static constexpr int kStages = (D == 128 && !kF8) ? 5 : 10;
   static constexpr int kBarBytes = 112 + 16 * kStages + 16 + 32;      // + q_empty, o_empty
   static constexpr int kSmem = 2 * kQTile + kStages * kStage + kBarBytes + 1024;
 };
@@ -87,12 +88,13 @@ __device__ __forceinline__ f32x2 exp2_poly2(f32x2 x) {
                __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23)));
 }
 
-// P = exp2(s a + nk) for 32 scores of one row (one hand-off part), packed to 16-bit pairs; the fp32 row sum
-// accumulates in a packed register.  NP of every 8 element pairs take the polynomial (compile-time pattern, so the
-// loop body is branch-free).
-template <bool BF16, int NP>
+// P = exp2(s a + nk) for 32 scores of one row (one hand-off part), packed for the P V MMA -- PF 0 / 1: f16 / bf16 pairs (16 words),
+// PF 2: e4m3 quads (8 words; element k of the row in byte k & 3 of word k >> 2: tools/f8_probe.cu); the fp32 row sum accumulates
+// in a packed register.  NP of every 8 element pairs take the polynomial (compile-time pattern, so the loop body is branch-free).
+template <int PF, int NP>
 __device__ __forceinline__ void exp_part(const float* s, f32x2 a2, f32x2 nk2, uint32_t* pk, f32x2& acc_a, f32x2& acc_b) {
   constexpr int kSel[5] = {0x00, 0x08, 0x22, 0x52, 0xAA};
+  uint32_t half16[PF == 2 ? 16 : 1];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const f32x2 x = fma2(pack2(s[2 * i], s[2 * i + 1]), a2, nk2);
@@ -107,7 +109,12 @@ __device__ __forceinline__ void exp_part(const float* s, f32x2 a2, f32x2 nk2, ui
     }
     if (i & 1) acc_b = add2(acc_b, pp); else acc_a = add2(acc_a, pp);
     unpack2(pp, p0, p1);
-    pk[i] = BF16 ? pack_bf16(p0, p1) : pack_f16(p0, p1);
+    if constexpr (PF == 2) half16[i] = pack_e4m3(p0, p1);
+    else pk[i] = PF == 1 ? pack_bf16(p0, p1) : pack_f16(p0, p1);
+  }
+  if constexpr (PF == 2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pk[i] = half16[2 * i] | (half16[2 * i + 1] << 16);
   }
 }
 
@@ -115,16 +122,17 @@ __device__ __forceinline__ void exp_part(const float* s, f32x2 a2, f32x2 nk2, ui
 // of arithmetic later (so tcgen05.wait::st never stalls on the store just issued).  One straight-line block: ptxas
 // interleaves the MUFU and polynomial work of neighbouring parts.  Sums of the two 64-key halves are kept apart
 // (int8 mode folds the V block scale of each half into its exponent).
-template <bool BF16, int NP, bool TR>
+template <int PF, int NP, bool TR>
 __device__ __forceinline__ void exp_phase(const float* s, float a0, float a1, float nk0, float nk1, uint32_t tS,
                                           uint32_t bar0, int lane, float& sum_lo, float& sum_hi, unsigned long long* tr) {
+  constexpr int kW = PF == 2 ? 8 : 16;             // TMEM columns of one part
   f32x2 acc[2][2] = {{pack2(0.f, 0.f), pack2(0.f, 0.f)}, {pack2(0.f, 0.f), pack2(0.f, 0.f)}};
-  uint32_t pk[kParts][16];
+  uint32_t pk[kParts][kW];
 #pragma unroll
   for (int part = 0; part < kParts; ++part) {
     const bool hi = part >= kParts / 2;
     const float ah = hi ? a1 : a0, nk = hi ? nk1 : nk0;
-    exp_part<BF16, NP>(s + 32 * part, pack2(ah, ah), pack2(nk, nk), pk[part], acc[hi ? 1 : 0][0], acc[hi ? 1 : 0][1]);
+    exp_part<PF, NP>(s + 32 * part, pack2(ah, ah), pack2(nk, nk), pk[part], acc[hi ? 1 : 0][0], acc[hi ? 1 : 0][1]);
     if (part > 0) {            // part-1's store was issued a whole part of arithmetic ago: publish it
       tmem_wait_st();
       tc_fence_before();
@@ -132,7 +140,8 @@ __device__ __forceinline__ void exp_phase(const float* s, float a0, float a1, fl
       if (lane == 0) mbar_arrive(bar0 + 8 * (part - 1));
       if (TR && tr) tr[3 + part - 1] = clock64();
     }
-    tmem_st_x16(tS + 16 * part, pk[part]);
+    if constexpr (PF == 2) tmem_st_x8(tS + kW * part, pk[part]);
+    else tmem_st_x16(tS + kW * part, pk[part]);
   }
   tmem_wait_st();
   tc_fence_before();
@@ -152,8 +161,12 @@ __device__ __forceinline__ void exp_phase(const float* s, float a0, float a1, fl
 template <int D, int MODE, int POLY, bool TR = false, bool MASKED = false>
 __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_constant__ FwdTcParams p) {
   using C = Cfg<D, MODE>;
-  constexpr bool I8 = C::kI8;
-  constexpr bool PBF16 = MODE != kFwdF16;                 // 16-bit format of P (and of V)
+  constexpr bool I8 = C::kI8, F8 = C::kF8;
+  constexpr int PF = F8 ? 2 : (MODE == kFwdF16 ? 0 : 1);  // format of P (and of V): f16 / bf16 / e4m3
+  // e4m3 P: the exponent carries +kShift so that P' = 2^kShift P uses the format's range (max 448), and the running max
+  // may lag the true one by kThr = 2 only (P' <= 2^8); 16-bit P: lag 2^8 (bf16 / fp32-range exponent, f16 P <= 256 < 65504)
+  constexpr float kShift = F8 ? 6.f : 0.f;
+  constexpr float kThr = F8 ? 2.f : kRescaleThreshold;
   constexpr int QT = C::kQTile, VT = C::kVTile, STG = C::kStage, NS = C::kStages, CHB = C::kChunkBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -272,10 +285,11 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     // ------------------------------------------------------------------ MMA issuer of tile t (whole warp, one elected lane issues)
     reg_dealloc<40>();
     const int t = (warp - 8) >> 1;
-    constexpr uint32_t FMT = PBF16 ? 1u : 0u;
+    constexpr uint32_t FMT = PF == 0 ? 0u : 1u;
     constexpr uint32_t IDESC_S = I8 ? make_idesc(2, 1, 1, 0, 0, 128, 128)        // s32 += s8 * s8, K-major A and B
                                     : make_idesc(1, FMT, FMT, 0, 0, 128, 128);
-    constexpr uint32_t IDESC_O = make_idesc(1, FMT, FMT, 0, 1, 128, D);          // f32 += P (tmem) * V, V MN-major
+    constexpr uint32_t IDESC_O = F8 ? make_idesc(1, 0, 0, 0, 1, 128, D)          // kind::f8f6f4: f32 += e4m3 P (tmem) * e4m3 V
+                                    : make_idesc(1, FMT, FMT, 0, 1, 128, D);     // f32 += P (tmem) * V, V MN-major
     const uint32_t q_lo = desc_lo(sQ, 16) + t * (QT >> 4), k_lo = desc_lo(sKV, 16), v_lo = desc_lo(sKV, CHB);
     const uint32_t tS = tmem + t * 128, tO = tmem + 256 + t * D;
     auto issue_s = [&](int idx) {
@@ -294,9 +308,13 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     };
     auto issue_o_part = [&](int idx, int part, bool acc) {
       const uint32_t b0 = v_lo + (idx % NS) * (STG >> 4);
+      if constexpr (F8) {        // one K = 32 MMA per part: 8 TMEM columns of e4m3 quads, 32 key rows of 128 bytes
+        mma_f8_ts_u(tO, tS + part * 8, b0 + part * (4096 >> 4), kDescHiSw128, IDESC_O, (acc || part > 0) ? 1u : 0u);
+      } else {
 #pragma unroll
-      for (int kk = 2 * part; kk < 2 * part + 2; ++kk)
-        mma_f16_ts_u(tO, tS + kk * 8, b0 + kk * (2048 >> 4), kDescHiSw128, IDESC_O, (acc || kk > 0) ? 1u : 0u);
+        for (int kk = 2 * part; kk < 2 * part + 2; ++kk)
+          mma_f16_ts_u(tO, tS + kk * 8, b0 + kk * (2048 >> 4), kDescHiSw128, IDESC_O, (acc || kk > 0) ? 1u : 0u);
+      }
     };
     auto wait_full = [&](int idx) { mbar_wait(kv_full(idx % NS), (idx / NS) & 1); };
     int kvbase = 0, qc = 0, pc = 0;                // ring index at the start of the item; items / KV steps done by this tile
@@ -374,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       ksp = p.ks ? p.ks + ((size_t)b * p.Hkv + hk) * p.sk_ : nullptr;
       vsp = p.vs ? p.vs + ((size_t)b * p.Hkv + hk) * p.sv_ : nullptr;
     }
-    const bool v_blocks = I8 && vsp != nullptr;
+    const bool v_blocks = I8 && !F8 && vsp != nullptr;     // (e4m3 V carries one scale per (b, head): applied in the epilogue)
     const bool pingpong = nt == 2 && p.pingpong;
 
     if (t < nt) {
@@ -402,9 +420,12 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         const bool mask_noop = (jt_next & kTileNoMask) != 0;
         // multipliers of the two 64-key halves of this tile (int8: blocks are multiples of 64 keys)
         float a0 = qsc, a1 = qsc, lv0 = 0.f, lv1 = 0.f, iv0 = 1.f, iv1 = 1.f;
+        float cb0 = 0.f, cb1 = 0.f;              // int8: - s_bias a_h, folded into every addend that follows a multiplication by a_h
         if constexpr (I8) {
           a0 = qsc * ksn0;
           a1 = qsc * ksn1;
+          cb0 = -p.s_bias * a0;
+          cb1 = -p.s_bias * a1;
           if (v_blocks) {
             lv0 = log2f(vsn0); lv1 = log2f(vsn1);    // bf16 P' = P v_h has fp32's exponent range: no reference scale needed
             iv0 = 1.f / vsn0; iv1 = 1.f / vsn1;
@@ -428,12 +449,17 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         if (TR && tr) tr[1] = clock64();
         if (it + 1 < n) { jt_next = tile_of(im, it + 1); fetch_scales(jt_next); }
         if constexpr (I8) {
-          // exact widening (|s| <= 2^21).  Measured alternatives (profiles/r01d_int8_notes.txt): I2FP here = 3553 clk per
-          // KV step pair, integer add onto the bits of 1.5 * 2^23 + packed subtract = 3750; the bf16 kernel = 2757.  The
-          // softmax warps issue at ~0.5 IPC per SMSP in either mode, so every extra instruction per score lengthens the
-          // step by ~2 x 128 x 2 clk -- more than the 2 x 256 clk the int8 Q K^T saves on the tensor pipe.
+          // Widening without a conversion instruction: (s << k) plus the bit pattern of B = 1.5 * 2^(23-k), read as a float, IS
+          // B + s (exact for |s| <= 2^(22-k)), and the - B a_h that undoes the offset rides in the addend of the multiply-add
+          // that scales the score anyway (cb_h above).  One integer multiply-add per score on the FMA / ALU pipes instead of I2FP
+          // on the XU pipe, which the exp2 MUFUs need (16 / clk / SM: 1157 clk per tile and step in round 1,
+          // profiles/r01d_int8_notes.txt).  k is the largest shift the code range allows (int8: |s| <= 2^21, k = 1; int4:
+          // |s| <= 2^13, k = 8): the addend nk_h = cb_h + ... is ONE fp32, so its rounding, <= 2^-25 B a_h, is the error of the
+          // scaled score -- 0.19 a_h (int8) / 1.5e-3 a_h (int4, whose a_h is ~300x larger), far below one quantum a_h of S.
+          const int smul = p.s_mul;
+          const uint32_t sadd = p.s_add;
 #pragma unroll
-          for (int i = 0; i < 128; ++i) s[i] = __int2float_rn((int)su[i]);
+          for (int i = 0; i < 128; ++i) su[i] = su[i] * smul + sadd;
         }
         if (TR && tr) tr[15] = clock64();
         if (MASKED && !mask_noop) {
@@ -467,12 +493,12 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
                   ldg256(mp + 8 * c, w);
                   const float ah = c < 8 ? a0 : a1;
 #pragma unroll
-                  for (int k = 0; k < 8; ++k) s[8 * c + k] = fmaf(s[8 * c + k], ah, __uint_as_float(w[k]) * kLog2e);
+                  for (int k = 0; k < 8; ++k) s[8 * c + k] = fmaf(s[8 * c + k], ah, fmaf(__uint_as_float(w[k]), kLog2e, c < 8 ? cb0 : cb1));
                 }
               } else {
 #pragma unroll
                 for (int i = 0; i < 128; ++i)
-                  s[i] = fmaf(s[i], i < 64 ? a0 : a1, (i < ncol ? __ldg(mp + i) : 0.f) * kLog2e);
+                  s[i] = fmaf(s[i], i < 64 ? a0 : a1, fmaf(i < ncol ? __ldg(mp + i) : 0.f, kLog2e, i < 64 ? cb0 : cb1));
               }
             } else {
               const uint16_t* mp = reinterpret_cast<const uint16_t*>(p.mask) + eoff;
@@ -486,24 +512,25 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
                   uint32_t w[4][8];
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) ldg256(mp + 16 * (4 * g + k4), w[k4]);
-                  const float ah = g == 0 ? a0 : a1;
+                  const float ah = g == 0 ? a0 : a1, cbh = g == 0 ? cb0 : cb1;
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) {
                     const int c = 4 * g + k4;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                      s[16 * c + 2 * k] = fmaf(s[16 * c + 2 * k], ah, widen(w[k4][k] & 0xffffu) * kLog2e);
-                      s[16 * c + 2 * k + 1] = fmaf(s[16 * c + 2 * k + 1], ah, widen(w[k4][k] >> 16) * kLog2e);
+                      s[16 * c + 2 * k] = fmaf(s[16 * c + 2 * k], ah, fmaf(widen(w[k4][k] & 0xffffu), kLog2e, cbh));
+                      s[16 * c + 2 * k + 1] = fmaf(s[16 * c + 2 * k + 1], ah, fmaf(widen(w[k4][k] >> 16), kLog2e, cbh));
                     }
                   }
                 }
               } else {
 #pragma unroll
                 for (int i = 0; i < 128; ++i)
-                  s[i] = fmaf(s[i], i < 64 ? a0 : a1, (i < ncol ? widen(__ldg(mp + i)) : 0.f) * kLog2e);
+                  s[i] = fmaf(s[i], i < 64 ? a0 : a1, fmaf(i < ncol ? widen(__ldg(mp + i)) : 0.f, kLog2e, i < 64 ? cb0 : cb1));
               }
             }
             a0 = a1 = 1.f;
+            cb0 = cb1 = 0.f;
           }
         }
         const bool need_mask = (c0 < clo) || (c0 + 127 > chi);
@@ -520,10 +547,10 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         }
         // per-half maxima to scaled log2 units; a_h > 0 so the max commutes with the scaling (-inf if all masked)
         float mx;
-        if constexpr (I8) mx = fmaxf(fmaxf(mxa, mxb) * a0, fmaxf(mxc, mxd) * a1);
+        if constexpr (I8) mx = fmaxf(fmaf(fmaxf(mxa, mxb), a0, cb0), fmaf(fmaxf(mxc, mxd), a1, cb1));
         else mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd)) * a0;
         float m_new = fmaxf(m, mx);
-        const bool grow = (m_new - m) > kRescaleThreshold;          // false when both are -inf (NaN compare)
+        const bool grow = (m_new - m) > kThr;                       // false when both are -inf (NaN compare)
         if (!grow) m_new = m;
         if (__any_sync(0xffffffffu, grow)) {
           const float alpha = grow ? ex2(m - m_new) : 1.f;          // m = -inf -> 0
@@ -544,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         const float mm = (m == -CUDART_INF_F) ? 0.f : m;
         // int8 mode: the V scale of each 64-key half rides in the exponent (P' = P v_h feeds the P V MMA; l takes
         // sum(P') / v_h), so the inner loop is the same as the 16-bit one.
-        const float nk0 = lv0 - mm, nk1 = lv1 - mm;
+        const float nk0 = (lv0 - mm) + (cb0 + kShift), nk1 = (lv1 - mm) + (cb1 + kShift);
         float sum_lo, sum_hi;
         // exp2 turn-taking: the two tiles' exp2 phases are MUFU-bound and share the four SMSPs, so run them one after
         // the other (tile 0 first) -- this locks the tiles in anti-phase: one is in exp2 while the tensor pipe works
@@ -560,8 +587,8 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           else named_bar_sync(3, 256);
         }
         if (TR && tr) tr[2] = clock64();
-        if (POLY > 0 && !any_mask && (!MASKED || mask_noop)) exp_phase<PBF16, POLY, TR>(s, a0, a1, nk0, nk1, tS, p_part(t, 0), lane, sum_lo, sum_hi, tr);
-        else exp_phase<PBF16, 0, TR>(s, a0, a1, nk0, nk1, tS, p_part(t, 0), lane, sum_lo, sum_hi, tr);
+        if (POLY > 0 && !any_mask && (!MASKED || mask_noop)) exp_phase<PF, POLY, TR>(s, a0, a1, nk0, nk1, tS, p_part(t, 0), lane, sum_lo, sum_hi, tr);
+        else exp_phase<PF, 0, TR>(s, a0, a1, nk0, nk1, tS, p_part(t, 0), lane, sum_lo, sum_hi, tr);
         if (pingpong) {
           if (t == 0) named_bar_arrive(3, 256);
           else named_bar_arrive(2, 256);
@@ -577,10 +604,11 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       }
       if (TR && ct && w == (int)blockIdx.x) ct[4] = globaltimer_ns();
       float inv = (l > 0.f ? 1.f / l : 0.f) * ((I8 && !v_blocks) ? p.vs1 : 1.f);
+      if constexpr (F8) { if (p.vs) inv = (l > 0.f ? 1.f / l : 0.f) * __ldg(p.vs + (size_t)b * p.Hkv + hk); }     // per-(b, head) scale of the e4m3 V
       const bool live = r < p.Sq && !p.debug_skip_store;
       const size_t orow = (size_t)b * p.o_sb + (size_t)h * p.o_sh + (size_t)r * p.o_ss;
       const size_t lrow = ((size_t)b * p.H + h) * p.lse_sh + r;
-      float l_out = l > 0.f ? m + log2f(l) : -CUDART_INF_F;
+      float l_out = l > 0.f ? m + log2f(l) - kShift : -CUDART_INF_F;
       // accumulate mode (ring attention): the partial of this launch is merged in place with the (O, L) already there,
       //   L = log2(2^L_old + 2^L_new),  O = O_old 2^(L_old - L) + O_new 2^(L_new - L)      (fp32 O only)
       float c_old = 0.f;
@@ -900,7 +928,7 @@ cudaError_t launch(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
   else return cudaErrorNotSupported;
 #else
   if (prm.mask) return launch_masked<D, MODE>(prm, grid, st);
-  if constexpr (D == 128 && MODE != kFwdF16) {
+  if constexpr (D == 128 && (MODE == kFwdBF16 || MODE == kFwdI8F8)) {
     if (const char* path = getenv("MFA_FWD_TRACE"))
       return poly_setting() == 2 ? launch_traced<MODE, 2>(prm, grid, st, path) : launch_traced<MODE, 0>(prm, grid, st, path);
     if (const char* path = getenv("MFA_FWD_CTATRACE"))
@@ -949,6 +977,7 @@ cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm_in, int D, int mode, cud
   if (persist) prm.o_tma = 0;                    // the staging tile of the TMA-store epilogue aliases the operand ring
   dim3 grid((unsigned)(persist ? sm_count() : items), 1, 1);
   if (mode == kFwdI8) return D == 128 ? launch<128, kFwdI8>(prm, grid, st) : cudaErrorInvalidValue;
+  if (mode == kFwdI8F8) return D == 128 ? launch<128, kFwdI8F8>(prm, grid, st) : cudaErrorInvalidValue;
   if (D == 128) return mode == kFwdBF16 ? launch<128, kFwdBF16>(prm, grid, st) : launch<128, kFwdF16>(prm, grid, st);
   if (D == 64) return mode == kFwdBF16 ? launch<64, kFwdBF16>(prm, grid, st) : launch<64, kFwdF16>(prm, grid, st);
   return cudaErrorInvalidValue;

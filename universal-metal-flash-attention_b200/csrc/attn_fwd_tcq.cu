@@ -1,6 +1,10 @@
 // attn_fwd_tcq.cu -- front end of the quantised attention forward on the sm_100a tensor pipe (SageAttention2-style):
 //     S_int = Q_i8 K_i8^T            tcgen05.mma kind::i8 (int32 accumulator in TMEM, 2x the bf16 MMA rate)
 //     S     = S_int * qs[row block] * ks[key block]          (fp32, in the softmax warps)
+//   P V in e4m3 (default; BASELINE.json config 3 "int8 Q K^T and fp8 P V"):
+//     P'    = 2^6 exp2(S c - m) -> e4m3 in TMEM,  O += P' V_e4m3      (kind::f8f6f4, 2x the bf16 MMA rate, half the V bytes);
+//             V_e4m3 = e4m3(code * vs[key block] / vh) with one scale vh per (b, head), applied to O in the epilogue
+//   P V in bf16 (mfa_set_quantized_pv_precision(ctx, MFA_PRECISION_BF16) / MFA_TCQ_PV=bf16):
 //     P     = exp2(S c - m)  -> bf16 in TMEM,  O += (P * vs[key block]) V_codes      (kind::f16, V codes exact in bf16)
 // Replaces the reference's quantised forward (metal-flash-attention/Sources/FlashAttention/Attention/
 // QuantizedAttention.swift:71-91,358-463 -- attention on dequantised int8 operands with fp32 statistics) for symmetric
@@ -12,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <math_constants.h>
+#include <cstring>
 
 #include "common.h"
 #include "fwd_tc.h"
@@ -65,11 +70,53 @@ __global__ void int4_to_int8_kernel(const uint8_t* __restrict__ src, int8_t* __r
   }
 }
 
+// ---- e4m3 V for the fp8 P V path.  One fp32 scale per (b, head): vh = max over the head's blocks of (block scale) * qmax / 448,
+// so every dequantised value code * vs[block] maps into e4m3's range (|x / vh| <= 448); e4m3 is a floating format, so one scale
+// per head loses no relative precision against per-block scales.  Pass 1 reads the scale array only.
+__global__ void head_vscale_kernel(const float* __restrict__ scales, float one_scale, int nb_per_head, int heads, float qmax,
+                                   float* __restrict__ vh) {
+  const int hd = blockIdx.x * blockDim.x + threadIdx.x;
+  if (hd >= heads) return;
+  float mx = 0.f;
+  if (scales && nb_per_head > 0) for (int i = 0; i < nb_per_head; ++i) mx = fmaxf(mx, scales[(size_t)hd * nb_per_head + i]);
+  else mx = scales ? scales[0] : one_scale;
+  const float v = mx * qmax * (1.f / 448.f);
+  vh[hd] = v > 0.f ? v : 1.f;
+}
+
+// int8 codes -> e4m3(code * vs[block] / vh[head]); 16 codes per thread per step, a (b, head) spans rows_per_head * D elements
+__global__ void codes_to_e4m3_kernel(const int8_t* __restrict__ src, uint8_t* __restrict__ dst, const float* __restrict__ scales,
+                                     float one_scale, const float* __restrict__ vh, int block_rows, int nb_per_head,
+                                     uint64_t rows_per_head, uint32_t D, uint64_t n16) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t e = i * 16;
+    const uint64_t row = e / D;
+    const uint64_t hd = row / rows_per_head;
+    float sc = one_scale;
+    if (scales) sc = nb_per_head > 0 ? scales[hd * nb_per_head + (row - hd * rows_per_head) / block_rows] : scales[0];
+    const float r = sc / vh[hd];
+    const int4 v = reinterpret_cast<const int4*>(src)[i];
+    const int w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float f0 = (float)(int8_t)(w[k] & 0xff) * r, f1 = (float)(int8_t)((w[k] >> 8) & 0xff) * r;
+      const float f2 = (float)(int8_t)((w[k] >> 16) & 0xff) * r, f3 = (float)(int8_t)((w[k] >> 24) & 0xff) * r;
+      out[k] = pack_e4m3(f0, f1) | (pack_e4m3(f2, f3) << 16);
+    }
+    reinterpret_cast<uint4*>(dst)[i] = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+
+unsigned __float_as_uint_host(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+
 unsigned grid_for(uint64_t n, int threads) {
   uint64_t g = (n + threads - 1) / threads;
   const uint64_t cap = 148ull * 16;
   return (unsigned)(g < cap ? (g ? g : 1) : cap);
 }
+
+int g_tcq_pv = -1;       // 0 = e4m3 P V (default), 1 = bf16 P V
 
 bool scales_ok(const QuantView& q, bool need64) {
   if (q.zero_point != 0) return false;
@@ -98,6 +145,16 @@ cudaError_t launch_int4_to_int8(const void* packed, void* codes, uint64_t n, cud
   return cudaGetLastError();
 }
 
+}  // namespace mfa
+
+namespace mfa {
+// P V precision of the quantised tensor-core forward: e4m3 (default) or bf16; MFA_TCQ_PV=bf16|fp8 sets the initial value
+int fwd_tcq_pv_mode() {
+  if (g_tcq_pv < 0) { const char* e = getenv("MFA_TCQ_PV"); g_tcq_pv = (e && (e[0] == 'b' || e[0] == 'B')) ? 1 : 0; }
+  return g_tcq_pv;
+}
+void fwd_tcq_set_pv_mode(int bf16) { g_tcq_pv = bf16 ? 1 : 0; }
+
 // Eligibility of the int8 tensor-core forward: int8 or int4 codes, symmetric, head_dim 128, contiguous operands, per-tensor
 // scales or per-block scales with K / V blocks that are multiples of 64 tokens, no external mask.
 bool fwd_tcq_eligible(const AttnParams& p) {
@@ -106,7 +163,8 @@ bool fwd_tcq_eligible(const AttnParams& p) {
   if (p.D != 128 || !fwd_tc_mask_ok(p)) return false;
   if (!(p.scale > 0.f) || p.Sq <= 0 || p.Skv <= 0 || p.B <= 0 || p.H <= 0 || p.Hkv <= 0 || p.H % p.Hkv) return false;
   if (p.B > 65535 || p.H > 65535) return false;
-  if (!scales_ok(p.qq, false) || !scales_ok(p.qk, true) || !scales_ok(p.qv, true)) return false;
+  // V: the bf16 P V path folds its block scales into the exponent per 64-key half; the e4m3 path takes any block size
+  if (!scales_ok(p.qq, false) || !scales_ok(p.qk, true) || !scales_ok(p.qv, fwd_tcq_pv_mode() == 1)) return false;
   const TensorView* vs[3] = {&p.q, &p.k, &p.v};
   const int64_t S[3] = {p.Sq, p.Skv, p.Skv}, Hn[3] = {p.H, p.Hkv, p.Hkv};
   for (int i = 0; i < 3; ++i) {      // contiguous BHSD (the pre-passes work on flat arrays)
@@ -120,10 +178,11 @@ bool fwd_tcq_eligible(const AttnParams& p) {
   return tc::encode_fn() != nullptr;
 }
 
-// scratch: at least  Skv*B*Hkv*D*2 (V as bf16)  [+ (Sq*B*H + Skv*B*Hkv)*D bytes of int8 codes when the input is int4].
+// scratch: at least  Skv*B*Hkv*D*2 (V as bf16; the e4m3 path uses half of it, plus B*Hkv head scales)
+// [+ (Sq*B*H + Skv*B*Hkv)*D bytes of int8 codes when the input is int4].
 size_t fwd_tcq_scratch_bytes(const AttnParams& p) {
   const size_t nq = (size_t)p.B * p.H * p.Sq * p.D, nkv = (size_t)p.B * p.Hkv * p.Skv * p.D;
-  return nkv * 2 + (p.in_dtype == kI4 ? nq + 2 * nkv : 0) + 1024;
+  return nkv * 2 + (p.in_dtype == kI4 ? nq + 2 * nkv : 0) + (size_t)p.B * p.Hkv * 4 + 2048;
 }
 
 cudaError_t launch_fwd_tcq(const AttnParams& p, void* scratch, cudaStream_t st) {
@@ -141,13 +200,31 @@ cudaError_t launch_fwd_tcq(const AttnParams& p, void* scratch, cudaStream_t st) 
     if ((e = launch_int4_to_int8(vc, v8, nkv, st)) != cudaSuccess) return e;
     qc = q8; kc = k8; vc = v8;
   }
-  if ((e = launch_codes_to_bf16(vc, v16, nkv, st)) != cudaSuccess) return e;
+  const bool f8 = fwd_tcq_pv_mode() == 0;
+  float* vh = nullptr;                      // e4m3 path: one scale per (b, head), behind everything else in the scratch
+  if (f8) {
+    const size_t off = (nkv * 2 + (p.in_dtype == kI4 ? nq + 2 * nkv : 0) + 1023) & ~(size_t)255;
+    vh = reinterpret_cast<float*>(sc + off);
+    const int heads = p.B * p.Hkv;
+    const bool blocks = p.qv.scales && p.qv.block_rows > 0;
+    const int nb = blocks ? (p.Skv + p.qv.block_rows - 1) / p.qv.block_rows : 0;
+    const float qmax = p.in_dtype == kI4 ? 8.f : 128.f;
+    head_vscale_kernel<<<(heads + 127) / 128, 128, 0, st>>>(p.qv.scales, p.qv.scale, nb, heads, qmax, vh);
+    if (nkv % 16) return cudaErrorInvalidValue;
+    codes_to_e4m3_kernel<<<grid_for(nkv / 16, 256), 256, 0, st>>>(reinterpret_cast<const int8_t*>(vc), reinterpret_cast<uint8_t*>(v16),
+                                                                 p.qv.scales, p.qv.scale, vh, blocks ? p.qv.block_rows : 1, nb,
+                                                                 (uint64_t)p.Skv, (uint32_t)p.D, nkv / 16);
+    g_launch_count += 2;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  } else if ((e = launch_codes_to_bf16(vc, v16, nkv, st)) != cudaSuccess) {
+    return e;
+  }
 
   FwdTcParams prm = {};
   TensorView tq = p.q, tk = p.k, tv = p.v;
   tq.ptr = qc; tk.ptr = kc; tv.ptr = v16;
   if (!tc::make_map(&prm.tq, tq, kI8, p.B, p.H, p.Sq, p.D) || !tc::make_map(&prm.tk, tk, kI8, p.B, p.Hkv, p.Skv, p.D) ||
-      !tc::make_map(&prm.tv, tv, kBF16, p.B, p.Hkv, p.Skv, p.D))
+      !tc::make_map(&prm.tv, tv, f8 ? kI8 : kBF16, p.B, p.Hkv, p.Skv, p.D))
     return cudaErrorInvalidValue;
   prm.o = const_cast<void*>(p.o.ptr);
   prm.o_sb = p.o.sb; prm.o_sh = p.o.sh; prm.o_ss = p.o.ss;
@@ -170,10 +247,18 @@ cudaError_t launch_fwd_tcq(const AttnParams& p, void* scratch, cudaStream_t st) 
   setq(p.qq, p.Sq, prm.qs, prm.qs1, prm.qbr, prm.nbq, prm.sq_);
   setq(p.qk, p.Skv, prm.ks, prm.ks1, prm.kbr, prm.nbk, prm.sk_);
   setq(p.qv, p.Skv, prm.vs, prm.vs1, prm.vbr, prm.nbv, prm.sv_);
-  e = launch_fwd_tc_kernel(prm, p.D, kFwdI8, st, p.B);
+  {   // |S_int| <= 128 * 128 * 128 = 2^21 (int8) or 8 * 8 * 128 = 2^13 (int4): the widest shift whose +-2^(22-k) window holds it
+    const int k = p.in_dtype == kI4 ? 8 : 1;
+    prm.s_mul = 1 << k;
+    prm.s_bias = 1.5f * (float)(1u << (23 - k));
+    prm.s_add = __float_as_uint_host(prm.s_bias);
+  }
+  if (f8) { prm.vs = vh; prm.vs1 = 1.f; }        // e4m3 V: the kernel reads vs[b * Hkv + head] in its epilogue
+  e = launch_fwd_tc_kernel(prm, p.D, f8 ? kFwdI8F8 : kFwdI8, st, p.B);
   if (e != cudaSuccess) return e;
   ++g_launch_count;
-  g_last_kernel = p.in_dtype == kI4 ? "fwd_tcq_int4_d128" : "fwd_tcq_int8_d128";
+  g_last_kernel = f8 ? (p.in_dtype == kI4 ? "fwd_tcq_int4_pvf8_d128" : "fwd_tcq_int8_pvf8_d128")
+                     : (p.in_dtype == kI4 ? "fwd_tcq_int4_d128" : "fwd_tcq_int8_d128");
   return cudaGetLastError();
 }
 

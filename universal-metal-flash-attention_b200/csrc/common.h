@@ -97,6 +97,8 @@ bool fwd_tcq_eligible(const AttnParams& p);
 size_t fwd_tcq_scratch_bytes(const AttnParams& p);
 cudaError_t launch_fwd_tcq(const AttnParams& p, void* scratch, cudaStream_t st);
 cudaError_t launch_codes_to_bf16(const void* codes, void* dst, uint64_t n, cudaStream_t st);
+int fwd_tcq_pv_mode();                      // P V of the quantised tensor-core forward: 0 = e4m3 (default), 1 = bf16
+void fwd_tcq_set_pv_mode(int bf16);
 cudaError_t launch_int4_to_int8(const void* packed, void* codes, uint64_t n, cudaStream_t st);
 
 // quantiser & friends
@@ -104,6 +106,10 @@ cudaError_t launch_quantize(const void* src, int src_dtype, void* codes, float* 
                             uint32_t block_rows, uint32_t block_cols, int bits, float scale_floor, cudaStream_t st);
 cudaError_t launch_dequantize(const void* codes, const float* scales, float* out, uint64_t rows, uint64_t cols,
                               uint32_t block_rows, uint32_t block_cols, int bits, cudaStream_t st);
+// tensor-core backward of quantised operands: dequantised codes / the upstream gradient as bf16
+cudaError_t launch_dequantize_bf16(const void* codes, int bits, const QuantView& q, void* out, uint64_t heads,
+                                   uint64_t rows_per_head, uint32_t D, cudaStream_t st);
+cudaError_t launch_to_bf16(const void* src, int src_dtype, void* out, uint64_t n, cudaStream_t st);
 cudaError_t launch_merge_partials(float* o_acc, float* l_acc, const float* o_part, const float* l_part,
                                   uint64_t rows, uint32_t D, cudaStream_t st);
 cudaError_t launch_hadamard(float* data, uint32_t block_size, uint32_t num_blocks, cudaStream_t st);

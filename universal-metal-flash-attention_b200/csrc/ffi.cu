@@ -584,9 +584,41 @@ mfa_error_t backward_core(Context* ctx, const BwdArgs& a) {
     p.mask_tile_scratch = reinterpret_cast<int*>(scope.take(Context::kMaskTiles, mb));     // null = no tile skipping
   Timer tm(ctx, st, !a.async);
   cudaError_t e = cudaSuccess;
+  // Quantised operands at the head dim the quantised tensor-core forward serves (128): the backward runs on the tensor pipe
+  // too, over the values the reference's backward sees (dequantised codes: QuantizedAttention.swift:1428-1608,
+  // MFABridge+Quantized.swift:365-533) held as bf16 -- one HBM-bound pass per operand, then the bf16 dK/dV and dQ kernels.
+  // Other head dims keep the exact SIMT route (dequantise on load).
+  const char* tcq_name = nullptr;
+  if ((p.in_dtype == kI8 || p.in_dtype == kI4) && a.D == 128 && !a.tq && !a.tk && !a.tv && !a.to &&
+      !getenv("MFA_DISABLE_TC") && !getenv("MFA_DISABLE_TCQ") && !getenv("MFA_DISABLE_TC_BWD")) {
+    auto packed_ok = [&](const TensorView& t, int64_t Hn, int64_t S) {
+      return t.sd == 1 && t.ss == (int64_t)a.D && t.sh == S * (int64_t)a.D && t.sb == Hn * S * (int64_t)a.D;
+    };
+    if (packed_ok(p.q, a.H, a.Sq) && packed_ok(p.k, a.Hkv, a.Skv) && packed_ok(p.v, a.Hkv, a.Skv)) {
+      const size_t qb = (nq * 2 + 255) & ~(size_t)255, kb = (nkv * 2 + 255) & ~(size_t)255;
+      uint8_t* tmp = reinterpret_cast<uint8_t*>(scope.take(Context::kQTmp, 2 * qb + 2 * kb + 256));
+      if (!tmp) return MFA_ERROR_MEMORY_ALLOCATION;
+      const int bits = p.in_dtype == kI8 ? 8 : 4;
+      void *q16 = tmp, *k16 = tmp + qb, *v16 = tmp + qb + kb, *g16 = tmp + qb + 2 * kb;
+      e = launch_dequantize_bf16(p.q.ptr, bits, p.qq, q16, (uint64_t)a.B * a.H, a.Sq, a.D, st);
+      if (e == cudaSuccess) e = launch_dequantize_bf16(p.k.ptr, bits, p.qk, k16, (uint64_t)a.B * a.Hkv, a.Skv, a.D, st);
+      if (e == cudaSuccess) e = launch_dequantize_bf16(p.v.ptr, bits, p.qv, v16, (uint64_t)a.B * a.Hkv, a.Skv, a.D, st);
+      const void* g = a.dout->dev;
+      if (e == cudaSuccess && a.do_dtype != kBF16) { e = launch_to_bf16(g, a.do_dtype, g16, nq, st); g = g16; }
+      if (e != cudaSuccess) return cuda_fail(e, "dequantise for the tensor-core backward");
+      tcq_name = p.in_dtype == kI8 ? "bwd_tcq_int8_d128" : "bwd_tcq_int4_d128";
+      p.q = contiguous_view(q16, a.H, a.Sq, a.D, false);
+      p.k = contiguous_view(k16, a.Hkv, a.Skv, a.D, false);
+      p.v = contiguous_view(v16, a.Hkv, a.Skv, a.D, false);
+      p.d_o = contiguous_view(g, a.H, a.Sq, a.D, false);
+      p.in_dtype = kBF16; p.do_dtype = kBF16;
+      p.qq = p.qk = p.qv = QuantView{nullptr, 1.f, 0, 0};
+    }
+  }
   if (bwd_tc_eligible(p)) {
     e = launch_dterm(p, st);
     if (e == cudaSuccess) e = launch_bwd_tc(p, st);
+    if (e == cudaSuccess && tcq_name) g_last_kernel = tcq_name;
   } else {
     e = launch_bwd_simt(p, st);   // empty Sq / Skv degrade to zero-filled gradients inside the kernels
   }
@@ -1610,6 +1642,16 @@ mfa_error_t mfa_merge_partials(mfa_context_t context, mfa_buffer_t o_acc, mfa_bu
   sync.out(bs[0]); sync.out(bs[1]);
   return sync.finish() == cudaSuccess ? MFA_SUCCESS : MFA_ERROR_EXECUTION_FAILED;
 }
+
+mfa_error_t mfa_set_quantized_pv_precision(mfa_context_t context, int32_t precision) {
+  if (!context) return MFA_ERROR_INVALID_ARGS;
+  if (precision != MFA_PRECISION_BF16 && precision != MFA_PRECISION_FP8_E4M3) return MFA_ERROR_INVALID_ARGS;
+  std::lock_guard<std::recursive_mutex> lock(C_(context)->mu);
+  fwd_tcq_set_pv_mode(precision == MFA_PRECISION_BF16);
+  return MFA_SUCCESS;
+}
+
+int32_t mfa_get_quantized_pv_precision(mfa_context_t) { return fwd_tcq_pv_mode() == 1 ? MFA_PRECISION_BF16 : MFA_PRECISION_FP8_E4M3; }
 
 const char* mfa_last_kernel_name(mfa_context_t context) { return context ? C_(context)->last_kernel : "none"; }
 uint64_t mfa_launch_count(mfa_context_t) { return g_launch_count; }

@@ -8,7 +8,7 @@
 
 namespace mfa {
 
-enum FwdMode : int { kFwdF16 = 0, kFwdBF16 = 1, kFwdI8 = 2 };
+enum FwdMode : int { kFwdF16 = 0, kFwdBF16 = 1, kFwdI8 = 2, kFwdI8F8 = 3 };   // I8: int8 Q K^T + bf16 P V; I8F8: int8 Q K^T + e4m3 P V
 
 struct FwdTcParams {
   CUtensorMap tq, tk, tv;
@@ -30,6 +30,8 @@ struct FwdTcParams {
   int qbr, kbr, vbr;                                    // tokens per block (multiple of 64 for K / V)
   int nbq, nbk, nbv;                                    // blocks per (b, h)
   int sq_, sk_, sv_;                                    // scale-array stride per (b, h): nb, or 0 for a single device scale
+  // int32 score -> float without a conversion: bits(s * s_mul + s_add) = s_bias + s  (s_mul = 2^k, s_bias = 1.5 * 2^(23-k))
+  int s_mul; unsigned s_add; float s_bias;
   // external mask (kernels instantiated with MASKED): bool bytes (non-zero = attend) or additive values, element strides
   // over [B, H, Sq, Skv] with broadcast dims = 0 and mask_sk == 1
   const void* mask;

@@ -259,6 +259,57 @@ __global__ void dequant_kernel(const uint8_t* __restrict__ codes, const float* _
   }
 }
 
+// ---- operands of the tensor-core backward of quantised attention: the values the reference's backward sees (dequantised
+// codes, QuantizedAttention.swift:1428-1608 / MFABridge+Quantized.swift:365-533) as bf16, 16 elements per thread.  Scales:
+// one per tensor (by value or scales[0]) or one per block of `block_rows` tokens inside each (b, head) of rows_per_head rows.
+template <int BITS>
+__global__ void dequant_bf16_kernel(const uint8_t* __restrict__ codes, __nv_bfloat16* __restrict__ out,
+                                    const float* __restrict__ scales, float one_scale, int zero_point, int block_rows,
+                                    int nb_per_head, uint64_t rows_per_head, uint32_t D, uint64_t n16) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = (i * 16) / D;
+    float sc = one_scale;
+    if (scales) {
+      const uint64_t hd = row / rows_per_head;
+      sc = nb_per_head > 0 ? scales[hd * nb_per_head + (row - hd * rows_per_head) / block_rows] : scales[0];
+    }
+    int q[16];
+    if (BITS == 8) {
+      const int4 v = reinterpret_cast<const int4*>(codes)[i];
+      const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 16; ++k) q[k] = (int)(int8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xff);
+    } else {
+      const uint2 v = reinterpret_cast<const uint2*>(codes)[i];
+      const uint32_t w[2] = {v.x, v.y};
+#pragma unroll
+      for (int k = 0; k < 16; ++k) q[k] = (int)((w[k >> 3] >> (4 * (k & 7))) & 0xf) - 8;
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn((float)(q[2 * k] - zero_point) * sc, (float)(q[2 * k + 1] - zero_point) * sc);
+      o[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    reinterpret_cast<uint4*>(out)[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<uint4*>(out)[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// fp32 / fp16 -> bf16 (the upstream gradient of the same backward), 8 elements per thread
+template <typename T>
+__global__ void to_bf16_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ out, uint64_t n8) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(to_f32<T>(src[8 * i + 2 * k]), to_f32<T>(src[8 * i + 2 * k + 1]));
+      o[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ---- merge of two attention partials over disjoint key sets (log2-domain L)
 __global__ void merge_partials_kernel(float* __restrict__ o_acc, float* __restrict__ l_acc,
                                       const float* __restrict__ o_part, const float* __restrict__ l_part,
@@ -437,6 +488,36 @@ cudaError_t launch_dequantize(const void* codes, const float* scales, float* out
   unsigned grid = grid_for(rows * cols, 256);
   if (bits == 8) dequant_kernel<8><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(codes), scales, out, rows, cols, br, bc, nbc);
   else if (bits == 4) dequant_kernel<4><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(codes), scales, out, rows, cols, br, bc, nbc);
+  else return cudaErrorInvalidValue;
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dequantize_bf16(const void* codes, int bits, const QuantView& q, void* out, uint64_t heads,
+                                   uint64_t rows_per_head, uint32_t D, cudaStream_t st) {
+  const uint64_t n = heads * rows_per_head * D;
+  if (n == 0) return cudaSuccess;
+  if ((n % 16) || (D % 16)) return cudaErrorInvalidValue;
+  const bool blocks = q.scales && q.block_rows > 0;
+  const int nb = blocks ? (int)((rows_per_head + q.block_rows - 1) / q.block_rows) : 0;
+  const unsigned grid = grid_for(n / 16, 256);
+  if (bits == 8)
+    dequant_bf16_kernel<8><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(codes), reinterpret_cast<__nv_bfloat16*>(out),
+                                                q.scales, q.scale, q.zero_point, blocks ? q.block_rows : 1, nb, rows_per_head, D, n / 16);
+  else if (bits == 4)
+    dequant_bf16_kernel<4><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(codes), reinterpret_cast<__nv_bfloat16*>(out),
+                                                q.scales, q.scale, q.zero_point, blocks ? q.block_rows : 1, nb, rows_per_head, D, n / 16);
+  else return cudaErrorInvalidValue;
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_to_bf16(const void* src, int src_dtype, void* out, uint64_t n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  if (n % 8) return cudaErrorInvalidValue;
+  const unsigned grid = grid_for(n / 8, 256);
+  if (src_dtype == kF32) to_bf16_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), reinterpret_cast<__nv_bfloat16*>(out), n / 8);
+  else if (src_dtype == kF16) to_bf16_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(src), reinterpret_cast<__nv_bfloat16*>(out), n / 8);
   else return cudaErrorInvalidValue;
   ++g_launch_count;
   return cudaGetLastError();

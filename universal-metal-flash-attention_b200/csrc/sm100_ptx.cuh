@@ -420,6 +420,13 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
   return r;
 }
 
+// two fp32 -> e4m3x2 (saturating): `lo` lands in bits [0,8), `hi` in [8,16)  (tools/f8_probe.cu: the first PTX operand is the high byte)
+__device__ __forceinline__ uint32_t pack_e4m3(float lo, float hi) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+  return (uint32_t)r;
+}
+
 // ---- packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two lanes of softmax arithmetic
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
