@@ -205,3 +205,32 @@ def test_c3_flux_size_prequantised_entry_point(ctx, pv, bits):
     # one scale for a whole [B*H*S, D] int4 tensor is the coarsest contract the ABI offers: 0.94 measured at this size
     # (block-64 scales, the C3 configuration, are held to 0.95 in the runtime-quantised test above)
     assert cs >= (0.99 if bits == 8 else 0.93), cs
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Backward of quantised attention at the head dim the tensor-core forward serves: mfa_quantized_backward re-quantises Q, K, V,
+# dequantises the codes to bf16 once and runs the bf16 dK/dV + dQ tensor-core kernels (csrc/ffi.cu backward_core).  Oracle:
+# the fp64 backward on the oracle's dequantised operands (the reference's semantics, MFABridge+Quantized.swift:365-533); the
+# kernels see those operands and dO ROUNDED to bf16 while the oracle keeps them in fp32 (the 16-bit tests elsewhere hand the
+# oracle the rounded inputs), hence 3e-2 relative to max|ref| instead of 2e-2 (measured 0.8e-2 .. 2.0e-2).
+@pytest.mark.parametrize("target,mode", [("int8", 2), ("int8", 0), ("int4", 2)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_tcq_backward_tensor_core(ctx, target, mode, causal):
+    import umfa
+    B, H, S, D = 1, 2, 384, 128
+    bits = 8 if target == "int8" else 4
+    rng = np.random.default_rng(21)
+    q, k, v, g = (rng.standard_normal((B, H, S, D)).astype(np.float32) for _ in range(4))
+    out, lse = umfa.runtime_quantized_attention(ctx, q, k, v, target_precision=target, quant_mode=mode,
+                                                input_precision="fp32", causal=causal)
+    qd, kd, vd = (fake_quant(x, bits, mode, D) for x in (q, k, v))
+    o_ref, l_ref = O.attention_forward(qd, kd, vd, causal=causal)
+    # feed the oracle's own (O, L) so that the backward is checked on its own
+    dq, dk, dv = umfa.runtime_quantized_backward(ctx, q, k, v, o_ref.astype(np.float32), g, l_ref.astype(np.float32),
+                                                 target_precision=target, quant_mode=mode, input_precision="fp32", causal=causal)
+    assert ctx.last_kernel.startswith("bwd_tcq_"), ctx.last_kernel
+    rq, rk, rv, _ = O.attention_backward(qd, kd, vd, g, causal=causal)
+    for name, got, ref in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+        assert np.isfinite(got).all(), name
+        err = float(np.abs(got - ref).max() / np.abs(ref).max())
+        assert err < 3e-2, (name, err)
