@@ -57,13 +57,16 @@ template <int D, int MODE>
 struct Cfg {
   static constexpr bool kF8 = MODE == kFwdI8F8;                      // int8 Q K^T, e4m3 P V
   static constexpr bool kI8 = MODE == kFwdI8 || kF8;                 // int8 Q K^T
+  static constexpr bool kSplit = MODE == kFwdSplit;                  // fp32 operands as fp16 (hi, lo) pairs, 3 MMAs per product
   static constexpr int kChunkBytes = 128 * 128;                      // one 128-byte swizzle chunk of 128 rows
-  static constexpr int kQChunks = kI8 ? 1 : D / 64;                  // chunks per Q / K tile
+  static constexpr int kQChunks = kI8 ? 1 : D / 64;                  // chunks per Q / K tile (split: per hi / lo half)
   static constexpr int kVChunks = kF8 ? 1 : D / 64;                  // V: 16-bit, or e4m3 (128 head dims = one 128-byte row)
-  static constexpr int kQTile = kQChunks * kChunkBytes;
+  static constexpr int kHalf = kQChunks * kChunkBytes;               // one K tile, or one half (hi / lo) of a split tile
+  static constexpr int kQTile = kHalf * (kSplit ? 2 : 1);            // split: Q_hi then Q_lo
   static constexpr int kVTile = kVChunks * kChunkBytes;
   static constexpr int kStage = kVTile;                              // ring stage (K tiles may use part of it)
-  static constexpr int kStages = (D == 128 && !kF8) ? 5 : 10;
+  static constexpr int kSPS = kSplit ? 4 : 2;                        // ring stages per KV step (split: K_lo, K_hi, V_hi, V_lo)
+  static constexpr int kStages = kSplit ? 3 : (D == 128 && !kF8) ? 5 : 10;   // split: 2 x 64 KB of Q leave room for 3 x 32 KB
   static constexpr int kBarBytes = 112 + 16 * kStages + 16 + 32;      // + q_empty, o_empty
   static constexpr int kSmem = 2 * kQTile + kStages * kStage + kBarBytes + 1024;
 };
@@ -89,7 +92,8 @@ __device__ __forceinline__ f32x2 exp2_poly2(f32x2 x) {
 }
 
 // P = exp2(s a + nk) for 32 scores of one row (one hand-off part), packed for the P V MMA -- PF 0 / 1: f16 / bf16 pairs (16 words),
-// PF 2: e4m3 quads (8 words; element k of the row in byte k & 3 of word k >> 2: tools/f8_probe.cu); the fp32 row sum accumulates
+// PF 2: e4m3 quads (8 words; element k of the row in byte k & 3 of word k >> 2: tools/f8_probe.cu), PF 3: f16 pairs of P_hi = f16(P)
+// (words 0-15) and of P_lo = f16(P - P_hi) (words 16-31), together 22 significant bits of P; the fp32 row sum accumulates
 // in a packed register.  NP of every 8 element pairs take the polynomial (compile-time pattern, so the loop body is branch-free).
 template <int PF, int NP>
 __device__ __forceinline__ void exp_part(const float* s, f32x2 a2, f32x2 nk2, uint32_t* pk, f32x2& acc_a, f32x2& acc_b) {
@@ -110,6 +114,12 @@ __device__ __forceinline__ void exp_part(const float* s, f32x2 a2, f32x2 nk2, ui
     if (i & 1) acc_b = add2(acc_b, pp); else acc_a = add2(acc_a, pp);
     unpack2(pp, p0, p1);
     if constexpr (PF == 2) half16[i] = pack_e4m3(p0, p1);
+    else if constexpr (PF == 3) {
+      const uint32_t h = pack_f16(p0, p1);
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
+      pk[i] = h;
+      pk[16 + i] = pack_f16(p0 - hf.x, p1 - hf.y);
+    }
     else pk[i] = PF == 1 ? pack_bf16(p0, p1) : pack_f16(p0, p1);
   }
   if constexpr (PF == 2) {
@@ -127,7 +137,7 @@ __device__ __forceinline__ void exp_phase(const float* s, float a0, float a1, fl
                                           uint32_t bar0, int lane, float& sum_lo, float& sum_hi, unsigned long long* tr) {
   constexpr int kW = PF == 2 ? 8 : 16;             // TMEM columns of one part
   f32x2 acc[2][2] = {{pack2(0.f, 0.f), pack2(0.f, 0.f)}, {pack2(0.f, 0.f), pack2(0.f, 0.f)}};
-  uint32_t pk[kParts][kW];
+  uint32_t pk[kParts][PF == 3 ? 32 : kW];
 #pragma unroll
   for (int part = 0; part < kParts; ++part) {
     const bool hi = part >= kParts / 2;
@@ -142,6 +152,7 @@ __device__ __forceinline__ void exp_phase(const float* s, float a0, float a1, fl
     }
     if constexpr (PF == 2) tmem_st_x8(tS + kW * part, pk[part]);
     else tmem_st_x16(tS + kW * part, pk[part]);
+    if constexpr (PF == 3) tmem_st_x16(tS + 64 + kW * part, pk[part] + 16);      // P_lo: columns [64, 128) of the S region
   }
   tmem_wait_st();
   tc_fence_before();
@@ -161,13 +172,14 @@ __device__ __forceinline__ void exp_phase(const float* s, float a0, float a1, fl
 template <int D, int MODE, int POLY, bool TR = false, bool MASKED = false>
 __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_constant__ FwdTcParams p) {
   using C = Cfg<D, MODE>;
-  constexpr bool I8 = C::kI8, F8 = C::kF8;
-  constexpr int PF = F8 ? 2 : (MODE == kFwdF16 ? 0 : 1);  // format of P (and of V): f16 / bf16 / e4m3
+  constexpr bool I8 = C::kI8, F8 = C::kF8, SPLIT = C::kSplit;
+  constexpr int PF = SPLIT ? 3 : F8 ? 2 : (MODE == kFwdF16 ? 0 : 1);  // format of P (and of V): f16 / bf16 / e4m3 / f16 (hi, lo) pairs
   // e4m3 P: the exponent carries +kShift so that P' = 2^kShift P uses the format's range (max 448), and the running max
   // may lag the true one by kThr = 2 only (P' <= 2^8); 16-bit P: lag 2^8 (bf16 / fp32-range exponent, f16 P <= 256 < 65504)
   constexpr float kShift = F8 ? 6.f : 0.f;
   constexpr float kThr = F8 ? 2.f : kRescaleThreshold;
-  constexpr int QT = C::kQTile, VT = C::kVTile, STG = C::kStage, NS = C::kStages, CHB = C::kChunkBytes;
+  constexpr int QT = C::kQTile, HT = C::kHalf, VT = C::kVTile, STG = C::kStage, NS = C::kStages, CHB = C::kChunkBytes;
+  constexpr int SPS = C::kSPS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -203,6 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     it.nt = (it.r0 + 128 < p.Sq) ? 2 : 1;
     int klo, khi;
     visible_key_range(p.causal, p.window, p.Skv, it.r0, min(it.r0 + 256, p.Sq), klo, khi);
+    if (p.kv_end > 0) { klo = max(klo, p.kv_begin); khi = max(klo, min(khi, p.kv_end)); }      // this launch covers a slice of the keys
     it.j_lo = klo >> 7;
     it.n = khi > klo ? ((khi + 127) >> 7) - it.j_lo : 0;
     it.lid = 0;
@@ -250,34 +263,45 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         const Item im = decode(w);
         const int r0 = im.r0, h = im.h, b = im.b, hk = im.hk, nt = im.nt, n = im.n;
         if (n == 0) continue;
-        auto load_qk = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int row, int head) {
-          mbar_arrive_expect_tx(bar, QT);
+        // one Q / K tile (or one hi / lo half of a split tile); the caller has armed the barrier with the bytes
+        auto load_half = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int row, int head) {
 #pragma unroll
           for (int c = 0; c < C::kQChunks; ++c) tma_load_4d(dst + c * CHB, m, bar, c * (I8 ? 128 : 64), row, head, b);
         };
-        auto load_v = [&](uint32_t dst, uint32_t bar, int row) {
-          mbar_arrive_expect_tx(bar, VT);
+        auto load_q = [&](int t2) {
+          mbar_arrive_expect_tx(q_full(t2), QT);
+          load_half(sQ + t2 * QT, &p.tq, q_full(t2), r0 + t2 * 128, h);
+          if constexpr (SPLIT) load_half(sQ + t2 * QT + HT, &p.tq2, q_full(t2), r0 + t2 * 128, h);
+        };
+        auto load_k = [&](const CUtensorMap* m, int row) {
+          const int s = kvi % NS;
+          mbar_wait(kv_empty(s), ((kvi / NS) & 1) ^ 1);
+          mbar_arrive_expect_tx(kv_full(s), HT);
+          load_half(sKV + s * STG, m, kv_full(s), row, hk);
+          ++kvi;
+        };
+        auto load_v = [&](const CUtensorMap* m, int row) {
+          const int s = kvi % NS;
+          mbar_wait(kv_empty(s), ((kvi / NS) & 1) ^ 1);
+          mbar_arrive_expect_tx(kv_full(s), VT);
 #pragma unroll
-          for (int c = 0; c < C::kVChunks; ++c) tma_load_4d(dst + c * CHB, &p.tv, bar, c * 64, row, hk, b);
+          for (int c = 0; c < C::kVChunks; ++c) tma_load_4d(sKV + s * STG + c * CHB, m, kv_full(s), c * 64, row, hk, b);
+          ++kvi;
         };
         if (qc[0] > 0) mbar_wait(q_empty(0), (qc[0] - 1) & 1);
-        load_qk(sQ, &p.tq, q_full(0), r0, h);
+        load_q(0);
         ++qc[0];
         for (int it = 0; it < n; ++it) {
           const int row = (tile_of(im, it) & (kTileNoMask - 1)) * 128;
-          int s = kvi % NS;
-          mbar_wait(kv_empty(s), ((kvi / NS) & 1) ^ 1);
-          load_qk(sKV + s * STG, &p.tk, kv_full(s), row, hk);
-          ++kvi;
+          if constexpr (SPLIT) load_k(&p.tk2, row);         // K_lo first: its stage is released after the first MMA group
+          load_k(&p.tk, row);
           if (it == 0 && nt == 2) {
             if (qc[1] > 0) mbar_wait(q_empty(1), (qc[1] - 1) & 1);
-            load_qk(sQ + QT, &p.tq, q_full(1), r0 + 128, h);
+            load_q(1);
             ++qc[1];
           }
-          s = kvi % NS;
-          mbar_wait(kv_empty(s), ((kvi / NS) & 1) ^ 1);
-          load_v(sKV + s * STG, kv_full(s), row);
-          ++kvi;
+          load_v(&p.tv, row);
+          if constexpr (SPLIT) load_v(&p.tv2, row);         // V_lo last: only the closing MMA group of the step reads it
         }
       }
     }
@@ -285,13 +309,24 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     // ------------------------------------------------------------------ MMA issuer of tile t (whole warp, one elected lane issues)
     reg_dealloc<40>();
     const int t = (warp - 8) >> 1;
-    constexpr uint32_t FMT = PF == 0 ? 0u : 1u;
+    constexpr uint32_t FMT = (PF == 0 || PF == 3) ? 0u : 1u;      // f16 / bf16 operands of kind::f16
     constexpr uint32_t IDESC_S = I8 ? make_idesc(2, 1, 1, 0, 0, 128, 128)        // s32 += s8 * s8, K-major A and B
                                     : make_idesc(1, FMT, FMT, 0, 0, 128, 128);
     constexpr uint32_t IDESC_O = F8 ? make_idesc(1, 0, 0, 0, 1, 128, D)          // kind::f8f6f4: f32 += e4m3 P (tmem) * e4m3 V
                                     : make_idesc(1, FMT, FMT, 0, 1, 128, D);     // f32 += P (tmem) * V, V MN-major
     const uint32_t q_lo = desc_lo(sQ, 16) + t * (QT >> 4), k_lo = desc_lo(sKV, 16), v_lo = desc_lo(sKV, CHB);
     const uint32_t tS = tmem + t * 128, tO = tmem + 256 + t * D;
+    // S of one KV step.  idx = ring index of the step's first stage.  Split operands: S = Q_hi K_lo^T + Q_hi K_hi^T + Q_lo K_hi^T
+    // (the dropped Q_lo K_lo^T is 2^-22 of the product); the K_lo stage goes back to the producer after the first group.
+    auto wait_full = [&](int idx) { mbar_wait(kv_full(idx % NS), (idx / NS) & 1); };
+    auto issue_qk = [&](uint32_t a0, int idx, bool acc0) {
+      const uint32_t b0 = k_lo + (idx % NS) * (STG >> 4);
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) {
+        const uint32_t off = ((kk >> 2) * CHB + (kk & 3) * 32) >> 4;
+        mma_f16_ss_u(tS, a0 + off, kDescHiSw128, b0 + off, kDescHiSw128, IDESC_S, acc0 || kk > 0);
+      }
+    };
     auto issue_s = [&](int idx) {
       const uint32_t b0 = k_lo + (idx % NS) * (STG >> 4);
       if constexpr (I8) {
@@ -299,11 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         for (int kk = 0; kk < 4; ++kk)           // 32 int8 per MMA = 32 bytes of the 128-byte row
           mma_i8_ss_u(tS, q_lo + kk * 2, kDescHiSw128, b0 + kk * 2, kDescHiSw128, IDESC_S, kk > 0);
       } else {
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = ((kk >> 2) * CHB + (kk & 3) * 32) >> 4;
-          mma_f16_ss_u(tS, q_lo + off, kDescHiSw128, b0 + off, kDescHiSw128, IDESC_S, kk > 0);
-        }
+        issue_qk(q_lo, idx, false);
       }
     };
     auto issue_o_part = [&](int idx, int part, bool acc) {
@@ -312,11 +343,12 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         mma_f8_ts_u(tO, tS + part * 8, b0 + part * (4096 >> 4), kDescHiSw128, IDESC_O, (acc || part > 0) ? 1u : 0u);
       } else {
 #pragma unroll
-        for (int kk = 2 * part; kk < 2 * part + 2; ++kk)
+        for (int kk = 2 * part; kk < 2 * part + 2; ++kk) {
           mma_f16_ts_u(tO, tS + kk * 8, b0 + kk * (2048 >> 4), kDescHiSw128, IDESC_O, (acc || kk > 0) ? 1u : 0u);
+          if constexpr (SPLIT) mma_f16_ts_u(tO, tS + 64 + kk * 8, b0 + kk * (2048 >> 4), kDescHiSw128, IDESC_O, 1u);   // P_lo V_hi
+        }
       }
     };
-    auto wait_full = [&](int idx) { mbar_wait(kv_full(idx % NS), (idx / NS) & 1); };
     int kvbase = 0, qc = 0, pc = 0;                // ring index at the start of the item; items / KV steps done by this tile
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const Item im = decode(w);
@@ -324,17 +356,32 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       if (n > 0 && t < nt) {
         // a lone tile (ragged last query block) releases every ring stage for the absent one as well
         auto release = [&](int idx) { tc_commit_u(kv_empty(idx % NS)); if (nt == 1) tc_commit_u(kv_empty(idx % NS)); };
+        // all of S of the step whose stages start at ring index idx: wait for the K stages, issue, publish S, free the stages
+        auto do_s = [&](int idx) {
+          wait_full(idx);
+          tc_fence_after();
+          if constexpr (SPLIT) {
+            issue_qk(q_lo, idx, false);                  // Q_hi K_lo^T
+            release(idx);
+            wait_full(idx + 1);
+            tc_fence_after();
+            issue_qk(q_lo, idx + 1, true);               // Q_hi K_hi^T
+            issue_qk(q_lo + (HT >> 4), idx + 1, true);   // Q_lo K_hi^T
+            tc_commit_u(s_full(t));
+            release(idx + 1);
+          } else {
+            issue_s(idx);
+            tc_commit_u(s_full(t));
+            release(idx);
+          }
+        };
         unsigned long long* tr = nullptr;            // timeline of the first item of CTA 0: MFA_FWD_TRACE (debug builds of the launch only)
         if (TR && p.trace && w == 0 && lane == 0) tr = p.trace + (size_t)t * 64 * 16;
         mbar_wait(q_full(t), qc & 1);
-        wait_full(kvbase);
-        tc_fence_after();
-        issue_s(kvbase);
-        tc_commit_u(s_full(t));
-        release(kvbase);
+        do_s(kvbase);
         if (n == 1) tc_commit_u(q_empty(t));
         for (int it = 0; it < n; ++it) {
-          const int vi = kvbase + 2 * it + 1, ki = kvbase + 2 * it + 2;
+          const int vi = kvbase + SPS * it + SPS / 2, ki = kvbase + SPS * (it + 1);
           wait_full(vi);
           if (TR && tr && it < 64) tr[it * 16 + 13] = clock64();
 #pragma unroll
@@ -347,13 +394,17 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
             issue_o_part(vi, part, it > 0);
           }
           release(vi);
-          if (it + 1 < n) {
-            wait_full(ki);
+          if constexpr (SPLIT) {                         // closing group of the step: P_hi V_lo over all 128 keys
+            wait_full(vi + 1);
             tc_fence_after();
+            const uint32_t b0 = v_lo + ((vi + 1) % NS) * (STG >> 4);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) mma_f16_ts_u(tO, tS + kk * 8, b0 + kk * (2048 >> 4), kDescHiSw128, IDESC_O, 1u);
+            release(vi + 1);
+          }
+          if (it + 1 < n) {
             if (TR && tr && it < 64) tr[it * 16 + 14] = clock64();
-            issue_s(ki);
-            tc_commit_u(s_full(t));
-            release(ki);
+            do_s(ki);
             if (it + 2 == n) tc_commit_u(q_empty(t));          // last S of the item: Q_t may be reloaded for the next one
             if (TR && tr && it < 64) tr[it * 16 + 12] = clock64();
           } else {
@@ -363,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         }
         ++qc;
       }
-      kvbase += 2 * n;
+      kvbase += SPS * n;
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------ softmax warpgroups
@@ -380,8 +431,9 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     const int r0 = im.r0, h = im.h, b = im.b, hk = im.hk, nt = im.nt, n = im.n;
     const int r = r0 + t * 128 + row;
     float m = -CUDART_INF_F, l = 0.f;                      // m in scaled log2 units (score * scale * log2 e)
-    const int chi = p.causal ? min(p.Skv - 1, r) : p.Skv - 1;
-    const int clo = p.window >= 0 ? max(0, r - p.window) : 0;
+    const int kv_hi = p.kv_end > 0 ? p.kv_end : p.Skv, kv_lo = p.kv_end > 0 ? p.kv_begin : 0;
+    const int chi = p.causal ? min(kv_hi - 1, r) : kv_hi - 1;
+    const int clo = p.window >= 0 ? max(kv_lo, r - p.window) : kv_lo;
     // int8 mode: per-row Q scale (folded with c), per-64-key K and V block scales
     float qsc = p.c;
     const float* ksp = nullptr;
@@ -392,6 +444,8 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       ksp = p.ks ? p.ks + ((size_t)b * p.Hkv + hk) * p.sk_ : nullptr;
       vsp = p.vs ? p.vs + ((size_t)b * p.Hkv + hk) * p.sv_ : nullptr;
     }
+    // split mode: the operands were scaled by powers of two into fp16's range (qs / ks / vs point at the inverse scales)
+    if constexpr (SPLIT) qsc = p.c * __ldg(p.qs) * __ldg(p.ks);
     const bool v_blocks = I8 && !F8 && vsp != nullptr;     // (e4m3 V carries one scale per (b, head): applied in the epilogue)
     const bool pingpong = nt == 2 && p.pingpong;
 
@@ -605,6 +659,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       if (TR && ct && w == (int)blockIdx.x) ct[4] = globaltimer_ns();
       float inv = (l > 0.f ? 1.f / l : 0.f) * ((I8 && !v_blocks) ? p.vs1 : 1.f);
       if constexpr (F8) { if (p.vs) inv = (l > 0.f ? 1.f / l : 0.f) * __ldg(p.vs + (size_t)b * p.Hkv + hk); }     // per-(b, head) scale of the e4m3 V
+      if constexpr (SPLIT) inv *= __ldg(p.vs);
       const bool live = r < p.Sq && !p.debug_skip_store;
       const size_t orow = (size_t)b * p.o_sb + (size_t)h * p.o_sh + (size_t)r * p.o_ss;
       const size_t lrow = ((size_t)b * p.H + h) * p.lse_sh + r;
@@ -978,6 +1033,10 @@ cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm_in, int D, int mode, cud
   dim3 grid((unsigned)(persist ? sm_count() : items), 1, 1);
   if (mode == kFwdI8) return D == 128 ? launch<128, kFwdI8>(prm, grid, st) : cudaErrorInvalidValue;
   if (mode == kFwdI8F8) return D == 128 ? launch<128, kFwdI8F8>(prm, grid, st) : cudaErrorInvalidValue;
+  if (mode == kFwdSplit) {        // exact exp2 only (the polynomial's 8.6e-5 would show at fp32 tolerances)
+    if (D != 128) return cudaErrorInvalidValue;
+    return prm.mask ? launch_masked_k<128, kFwdSplit, 0>(prm, grid, st) : launch_k<128, kFwdSplit, 0>(prm, grid, st);
+  }
   if (D == 128) return mode == kFwdBF16 ? launch<128, kFwdBF16>(prm, grid, st) : launch<128, kFwdF16>(prm, grid, st);
   if (D == 64) return mode == kFwdBF16 ? launch<64, kFwdBF16>(prm, grid, st) : launch<64, kFwdF16>(prm, grid, st);
   return cudaErrorInvalidValue;

@@ -92,6 +92,11 @@ cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st);
 bool bwd_tc_eligible(const AttnParams& p);
 cudaError_t launch_bwd_tc(const AttnParams& p, cudaStream_t st);
 
+// fp32 operands on the tensor pipe as fp16 (hi, lo) pairs (attn_fwd_split.cu): head_dim 128
+bool fwd_split_eligible(const AttnParams& p);
+size_t fwd_split_scratch_bytes(const AttnParams& p);
+cudaError_t launch_fwd_split(const AttnParams& p, void* scratch, cudaStream_t st);
+
 // int8 tensor-core forward (attn_fwd_tcq.cu): int8 / int4 codes, symmetric, D = 128, per-tensor or 64-multiple block scales.
 bool fwd_tcq_eligible(const AttnParams& p);
 size_t fwd_tcq_scratch_bytes(const AttnParams& p);

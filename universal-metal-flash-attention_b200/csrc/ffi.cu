@@ -504,6 +504,11 @@ mfa_error_t forward_core(Context* ctx, const FwdArgs& a) {
   Timer tm(ctx, st, !a.async);
   if (fwd_tc_eligible(p)) {
     e = launch_fwd_tc(p, st);
+  } else if (fwd_split_eligible(p)) {
+    // fp32 operands (the reference adapters' default precision) at head_dim 128: tensor pipe through fp16 (hi, lo) pairs
+    void* tmp = scope.take(Context::kQTmp, fwd_split_scratch_bytes(p));
+    if (!tmp) return MFA_ERROR_MEMORY_ALLOCATION;
+    e = launch_fwd_split(p, tmp, st);
   } else {
     e = launch_fwd_simt(p, st);
   }

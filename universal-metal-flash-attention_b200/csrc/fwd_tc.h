@@ -8,10 +8,12 @@
 
 namespace mfa {
 
-enum FwdMode : int { kFwdF16 = 0, kFwdBF16 = 1, kFwdI8 = 2, kFwdI8F8 = 3 };   // I8: int8 Q K^T + bf16 P V; I8F8: int8 Q K^T + e4m3 P V
+// I8: int8 Q K^T + bf16 P V; I8F8: int8 Q K^T + e4m3 P V; Split: fp32 operands as scaled fp16 (hi, lo) pairs, three MMAs per product
+enum FwdMode : int { kFwdF16 = 0, kFwdBF16 = 1, kFwdI8 = 2, kFwdI8F8 = 3, kFwdSplit = 4 };
 
 struct FwdTcParams {
   CUtensorMap tq, tk, tv;
+  CUtensorMap tq2, tk2, tv2;   // kFwdSplit: the lo halves (tq / tk / tv map the hi halves)
   CUtensorMap to;          // O in its output type, box = 128 bytes (32 floats / 64 halves) x 128 rows (valid when o_tma != 0)
   int o_tma;               // epilogue stages O in shared memory and writes it with TMA bulk stores
   void* o;
@@ -24,6 +26,8 @@ struct FwdTcParams {
   int nbatch;              // set by launch_fwd_tc_kernel (work items = query blocks x H x nbatch)
   float c;                 // softmax_scale * log2(e)
   int causal, window;
+  int kv_begin, kv_end;    // kv_end > 0: this launch attends to keys [kv_begin, kv_end) only (kv_begin a multiple of 128); the fp32
+                           // split mode covers long key ranges in slices merged by the accumulate epilogue
   // kFwdI8 only: symmetric scales of the int8 codes (value = code * scale)
   const float* qs; const float* ks; const float* vs;   // per-block scale arrays (device) or nullptr
   float qs1, ks1, vs1;                                  // per-tensor scales when the array is null
