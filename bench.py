@@ -46,6 +46,9 @@ WORKLOADS = {
     # name: (B, H, Sq, Skv, D, causal, window, dtype)
     "flux": dict(B=1, H=24, Sq=4608, Skv=4608, D=128, causal=False, window=-1, dtype="bf16",
                  label="FLUX.1-schnell joint attention bf16 B=1 H=24 N=4608 D=128 forward"),
+    # the reference adapters' default precision: fp32 operands, served on the tensor pipe as fp16 (hi, lo) pairs (3 MMAs / product)
+    "flux_fp32": dict(B=1, H=24, Sq=4608, Skv=4608, D=128, causal=False, window=-1, dtype="fp32",
+                      label="FLUX shape with fp32 operands (reference default precision) B=1 H=24 N=4608 D=128 forward"),
     "flux_causal": dict(B=1, H=24, Sq=4608, Skv=4608, D=128, causal=True, window=-1, dtype="bf16",
                         label="FLUX shape, causal"),
     "long_window": dict(B=1, H=32, Sq=32768, Skv=32768, D=128, causal=True, window=4096, dtype="bf16",
@@ -61,7 +64,7 @@ WORKLOADS = {
     "ring16k": dict(B=1, H=8, Sq=16384, Skv=16384, D=128, causal=True, window=-1, dtype="bf16", ring=True,
                     label="16k-token causal ring attention (smoke size)"),
 }
-ALL_EXTRAS = ["fwdbwd_flux", "c4_fwdbwd_heads_sharded", "int8_block", "int4_block", "ring128k"]
+ALL_EXTRAS = ["fwdbwd_flux", "c4_fwdbwd_heads_sharded", "int8_block", "int4_block", "fp32_flux", "ring128k"]
 
 
 def visible_pairs(Sq, Skv, causal, window):
@@ -294,10 +297,10 @@ def make_attention_sets(hz, w, H, mode, o_dtype="fp32", seed=1234):
     import numpy as np
     torch = hz.torch
     B, Sq, Skv, D = w["B"], w["Sq"], w["Skv"], w["D"]
-    tdt = {"bf16": torch.bfloat16, "fp16": torch.float16}[w["dtype"]]
+    tdt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[w["dtype"]]
     o_tdt = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[o_dtype]
     o_es = 4 if o_dtype == "fp32" else 2
-    in_bytes = (B * H * Sq * D + 2 * B * H * Skv * D) * 2
+    in_bytes = (B * H * Sq * D + 2 * B * H * Skv * D) * (4 if w["dtype"] == "fp32" else 2)
     out_bytes = B * H * Sq * D * o_es
     nsets = max(3, int(np.ceil(3 * 126e6 / (in_bytes + out_bytes))))
     nsets = min(nsets, 16)
@@ -325,7 +328,7 @@ def attention_enqueue(hz, w, H, mode, sets, o_prec=2):
     lib, ctx = hz.lib, hz.ctx
     B, Sq, Skv, D = w["B"], w["Sq"], w["Skv"], w["D"]
     scale = 1.0 / float(np.sqrt(D))
-    prec = {"bf16": 1, "fp16": 0}[w["dtype"]]
+    prec = {"bf16": 1, "fp16": 0, "fp32": 2}[w["dtype"]]
     nsets = len(sets)
 
     def enqueue(i):
@@ -374,7 +377,10 @@ def section_attention(hz, w, mode, steps, warmup, heads_sharded=False, o_dtype="
                       "cache": f"inputs rotate over {len(sets)} buffer sets ({len(sets) * (in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2)",
                       "kernel": kernel, "mode": mode,
                       "output": "fp32 O (reference contract)" if o_dtype == "fp32" else f"{o_dtype} O (opt-in)"},
-           "roofline": hz.roofline(per_rank_flops, med, note="per-GPU launch(es) of one step" if mode == "fwdbwd" else None),
+           "roofline": hz.roofline(per_rank_flops, med, note=(
+               "per-GPU launch(es) of one step" if mode == "fwdbwd" else
+               "algorithmic FLOPs; the fp32 path issues 3 fp16 MMAs per product (hi/lo operand pairs), so the tensor pipe does 3x this work"
+               if w["dtype"] == "fp32" else None)),
            "gpu_launches": launches, "clocks": clocks}
     del sets
     hz.torch.cuda.empty_cache()
@@ -534,6 +540,8 @@ def run_extras(hz, names, args):
                 rec = section_quant(hz, min(args.steps, 10), 3, 3, "int8 block-64 codes")
             elif name == "int4_block":
                 rec = section_quant(hz, min(args.steps, 10), 3, 4, "int4 block-64 codes")
+            elif name == "fp32_flux":
+                rec = section_attention(hz, WORKLOADS["flux_fp32"], "fwd", min(args.steps, 10), 3)[0]
             elif name == "ring128k":
                 rec = section_ring(hz, WORKLOADS["ring128k"], min(args.steps, 4), 3)
             else:
