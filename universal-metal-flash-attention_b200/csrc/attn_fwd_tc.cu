@@ -35,6 +35,7 @@
 
 #include <cstdio>
 #include <mutex>
+#include <type_traits>
 
 #include "common.h"
 #include "fwd_tc.h"
@@ -55,8 +56,9 @@ constexpr int kParts = 4;                    // P hand-off granularity: 32 keys 
 
 template <int D, int MODE>
 struct Cfg {
-  static constexpr bool kF8 = MODE == kFwdI8F8;                      // int8 Q K^T, e4m3 P V
-  static constexpr bool kI8 = MODE == kFwdI8 || kF8;                 // int8 Q K^T
+  static constexpr bool kI4 = MODE == kFwdI4 || MODE == kFwdI4F8;    // Q / K arrive as packed int4 and are unpacked in shared memory
+  static constexpr bool kF8 = MODE == kFwdI8F8 || MODE == kFwdI4F8;  // int8 Q K^T, e4m3 P V
+  static constexpr bool kI8 = MODE == kFwdI8 || kF8 || kI4;          // int8 Q K^T
   static constexpr bool kSplit = MODE == kFwdSplit;                  // fp32 operands as fp16 (hi, lo) pairs, 3 MMAs per product
   static constexpr int kChunkBytes = 128 * 128;                      // one 128-byte swizzle chunk of 128 rows
   static constexpr int kQChunks = kI8 ? 1 : D / 64;                  // chunks per Q / K tile (split: per hi / lo half)
@@ -67,8 +69,12 @@ struct Cfg {
   static constexpr int kStage = kVTile;                              // ring stage (K tiles may use part of it)
   static constexpr int kSPS = kSplit ? 4 : 2;                        // ring stages per KV step (split: K_lo, K_hi, V_hi, V_lo)
   static constexpr int kStages = kSplit ? 3 : (D == 128 && !kF8) ? 5 : 10;   // split: 2 x 64 KB of Q leave room for 3 x 32 KB
-  static constexpr int kBarBytes = 112 + 16 * kStages + 16 + 32;      // + q_empty, o_empty
-  static constexpr int kSmem = 2 * kQTile + kStages * kStage + kBarBytes + 1024;
+  static constexpr int kBarBytes = 112 + 16 * kStages + 16 + 32 + 64; // + q_empty, o_empty, + raw-tile barriers (int4)
+  // int4: raw (packed) tiles as TMA delivers them -- a 3-deep ring of K tiles + one Q tile, 128 rows x 64 bytes each -- and
+  // the per-row sums of the Q codes (2 x 128 ints)
+  static constexpr int kRawTile = 128 * 64, kRawStages = 3;
+  static constexpr int kRawBytes = kI4 ? (kRawStages + 1) * kRawTile + 1024 + 128 : 0;
+  static constexpr int kSmem = 2 * kQTile + kStages * kStage + kBarBytes + kRawBytes + 1024;
 };
 
 // 2^x for a pair of x <= ~8 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max rel err 8.6e-5),
@@ -172,7 +178,7 @@ __device__ __forceinline__ void exp_phase(const float* s, float a0, float a1, fl
 template <int D, int MODE, int POLY, bool TR = false, bool MASKED = false>
 __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_constant__ FwdTcParams p) {
   using C = Cfg<D, MODE>;
-  constexpr bool I8 = C::kI8, F8 = C::kF8, SPLIT = C::kSplit;
+  constexpr bool I8 = C::kI8, F8 = C::kF8, SPLIT = C::kSplit, I4 = C::kI4;
   constexpr int PF = SPLIT ? 3 : F8 ? 2 : (MODE == kFwdF16 ? 0 : 1);  // format of P (and of V): f16 / bf16 / e4m3 / f16 (hi, lo) pairs
   // e4m3 P: the exponent carries +kShift so that P' = 2^kShift P uses the format's range (max 448), and the running max
   // may lag the true one by kThr = 2 only (P' <= 2^8); 16-bit P: lag 2^8 (bf16 / fp32-range exponent, f16 P <= 256 < 65504)
@@ -180,6 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
   constexpr float kThr = F8 ? 2.f : kRescaleThreshold;
   constexpr int QT = C::kQTile, HT = C::kHalf, VT = C::kVTile, STG = C::kStage, NS = C::kStages, CHB = C::kChunkBytes;
   constexpr int SPS = C::kSPS;
+  constexpr int kWg2Regs = 40;      // 8 x 232 + 4 x 40 = 504 x 32 per lane slot: an exact fit (4 x 48) leaves setmaxnreg.inc waiting forever
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -193,6 +200,12 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
   const uint32_t tmem_slot = sBar + 112 + 16 * NS;
   auto q_empty = [&](int t) { return sBar + 112 + 16 * NS + 16 + 8 * t; };   // MMA warp: Q_t smem may be reloaded
   auto o_empty = [&](int t) { return sBar + 112 + 16 * NS + 32 + 8 * t; };   // softmax warps: O_t left TMEM (epilogue read it)
+  // int4 operands: raw_full / raw_empty of the packed K ring, qraw_full / qraw_empty of the packed Q tile
+  constexpr int NR = C::kRawStages, RAW = C::kRawTile;
+  auto raw_full = [&](int s) { return sBar + 112 + 16 * NS + 48 + 8 * s; };
+  auto raw_empty = [&](int s) { return sBar + 112 + 16 * NS + 72 + 8 * s; };
+  const uint32_t qraw_full = sBar + 112 + 16 * NS + 96, qraw_empty = sBar + 112 + 16 * NS + 104;
+  const uint32_t sRawK = (sBar + C::kBarBytes + 127u) & ~127u, sRawQ = sRawK + NR * RAW, sQsum = sRawQ + RAW;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
   // MFA_FWD_CTATRACE (debug build of the launch only): per-CTA wall-clock stamps written by thread 0
@@ -240,6 +253,10 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     }
     for (int s = 0; s < NS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2); }   // a lone tile releases twice
     for (int t = 0; t < 2; ++t) { mbar_init(q_empty(t), 1); mbar_init(o_empty(t), 4); }
+    if constexpr (I4) {
+      for (int r = 0; r < NR; ++r) { mbar_init(raw_full(r), 1); mbar_init(raw_empty(r), 1); }
+      mbar_init(qraw_full, 1); mbar_init(qraw_empty, 1);
+    }
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -256,9 +273,10 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
 
   if (warp == 9) {
     // ------------------------------------------------------------------ TMA producer
-    reg_dealloc<40>();
+    reg_dealloc<kWg2Regs>();
     if (lane == 0) {
       int kvi = 0, qc[2] = {0, 0};                      // running ring index; items in which tile t took part
+      int kr = 0, nqraw = 0;                            // int4: packed K / Q tiles requested so far
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
         const Item im = decode(w);
         const int r0 = im.r0, h = im.h, b = im.b, hk = im.hk, nt = im.nt, n = im.n;
@@ -269,11 +287,27 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           for (int c = 0; c < C::kQChunks; ++c) tma_load_4d(dst + c * CHB, m, bar, c * (I8 ? 128 : 64), row, head, b);
         };
         auto load_q = [&](int t2) {
+          if constexpr (I4) {              // packed tile into the raw Q buffer; the converter warp unpacks it into sQ
+            if (nqraw > 0) mbar_wait(qraw_empty, (nqraw - 1) & 1);
+            mbar_arrive_expect_tx(qraw_full, RAW);
+            tma_load_4d(sRawQ, &p.tq, qraw_full, 0, r0 + t2 * 128, h, b);
+            ++nqraw;
+            return;
+          }
+          if (qc[t2] > 0) mbar_wait(q_empty(t2), (qc[t2] - 1) & 1);
           mbar_arrive_expect_tx(q_full(t2), QT);
           load_half(sQ + t2 * QT, &p.tq, q_full(t2), r0 + t2 * 128, h);
           if constexpr (SPLIT) load_half(sQ + t2 * QT + HT, &p.tq2, q_full(t2), r0 + t2 * 128, h);
         };
         auto load_k = [&](const CUtensorMap* m, int row) {
+          if constexpr (I4) {              // packed tile into the raw ring; its operand stage (ring index kvi) is the converter's
+            const int rs = kr % NR;
+            mbar_wait(raw_empty(rs), ((kr / NR) & 1) ^ 1);
+            mbar_arrive_expect_tx(raw_full(rs), RAW);
+            tma_load_4d(sRawK + rs * RAW, m, raw_full(rs), 0, row, hk, b);
+            ++kr; ++kvi;
+            return;
+          }
           const int s = kvi % NS;
           mbar_wait(kv_empty(s), ((kvi / NS) & 1) ^ 1);
           mbar_arrive_expect_tx(kv_full(s), HT);
@@ -288,7 +322,6 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           for (int c = 0; c < C::kVChunks; ++c) tma_load_4d(sKV + s * STG + c * CHB, m, kv_full(s), c * 64, row, hk, b);
           ++kvi;
         };
-        if (qc[0] > 0) mbar_wait(q_empty(0), (qc[0] - 1) & 1);
         load_q(0);
         ++qc[0];
         for (int it = 0; it < n; ++it) {
@@ -296,7 +329,6 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           if constexpr (SPLIT) load_k(&p.tk2, row);         // K_lo first: its stage is released after the first MMA group
           load_k(&p.tk, row);
           if (it == 0 && nt == 2) {
-            if (qc[1] > 0) mbar_wait(q_empty(1), (qc[1] - 1) & 1);
             load_q(1);
             ++qc[1];
           }
@@ -307,10 +339,11 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     }
   } else if (warp == 8 || warp == 10) {
     // ------------------------------------------------------------------ MMA issuer of tile t (whole warp, one elected lane issues)
-    reg_dealloc<40>();
+    reg_dealloc<kWg2Regs>();
     const int t = (warp - 8) >> 1;
     constexpr uint32_t FMT = (PF == 0 || PF == 3) ? 0u : 1u;      // f16 / bf16 operands of kind::f16
-    constexpr uint32_t IDESC_S = I8 ? make_idesc(2, 1, 1, 0, 0, 128, 128)        // s32 += s8 * s8, K-major A and B
+    constexpr uint32_t IDESC_S = I4 ? make_idesc(2, 1, 0, 0, 0, 128, 128)        // s32 += s8 * u8: K nibbles stay unsigned (see converter)
+                               : I8 ? make_idesc(2, 1, 1, 0, 0, 128, 128)        // s32 += s8 * s8, K-major A and B
                                     : make_idesc(1, FMT, FMT, 0, 0, 128, 128);
     constexpr uint32_t IDESC_O = F8 ? make_idesc(1, 0, 0, 0, 1, 128, D)          // kind::f8f6f4: f32 += e4m3 P (tmem) * e4m3 V
                                     : make_idesc(1, FMT, FMT, 0, 1, 128, D);     // f32 += P (tmem) * V, V MN-major
@@ -446,6 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     }
     // split mode: the operands were scaled by powers of two into fp16's range (qs / ks / vs point at the inverse scales)
     if constexpr (SPLIT) qsc = p.c * __ldg(p.qs) * __ldg(p.ks);
+    float sb_row = p.s_bias;                               // offset of the widened integer score of this row (int4: set at step 0)
     const bool v_blocks = I8 && !F8 && vsp != nullptr;     // (e4m3 V carries one scale per (b, head): applied in the epilogue)
     const bool pingpong = nt == 2 && p.pingpong;
 
@@ -474,12 +508,12 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         const bool mask_noop = (jt_next & kTileNoMask) != 0;
         // multipliers of the two 64-key halves of this tile (int8: blocks are multiples of 64 keys)
         float a0 = qsc, a1 = qsc, lv0 = 0.f, lv1 = 0.f, iv0 = 1.f, iv1 = 1.f;
-        float cb0 = 0.f, cb1 = 0.f;              // int8: - s_bias a_h, folded into every addend that follows a multiplication by a_h
+        float cb0 = 0.f, cb1 = 0.f;              // int8: - (s_bias [+ 8 rowsum(q)]) a_h, folded into every addend that follows a multiplication by a_h
         if constexpr (I8) {
           a0 = qsc * ksn0;
           a1 = qsc * ksn1;
-          cb0 = -p.s_bias * a0;
-          cb1 = -p.s_bias * a1;
+          cb0 = -sb_row * a0;
+          cb1 = -sb_row * a1;
           if (v_blocks) {
             lv0 = log2f(vsn0); lv1 = log2f(vsn1);    // bf16 P' = P v_h has fp32's exponent range: no reference scale needed
             iv0 = 1.f / vsn0; iv1 = 1.f / vsn1;
@@ -491,6 +525,15 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         mbar_wait(s_full(t), pc & 1);
         ++pc;
         tc_fence_after();
+        if constexpr (I4) {
+          // unsigned K nibbles: S_true = S_mma - 8 sum_d q[row][d]; the row constant joins the widening offset (both exact integers
+          // in fp32).  The converter wrote the sums before it published Q, S of this item was computed from that Q.
+          if (it == 0) {
+            sb_row = p.s_bias + 8.f * (float)(int)ld_shared_u32(sQsum + t * 512 + row * 4);
+            cb0 = -sb_row * a0;
+            cb1 = -sb_row * a1;
+          }
+        }
         if (TR && tr) tr[0] = clock64();
         if (TR && ct && it == 0 && w == (int)blockIdx.x) ct[2] = globaltimer_ns();
         uint32_t su[128];
@@ -792,7 +835,78 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     if (p.pingpong && t == 0) named_bar_sync(2, 256);      // take the credit nobody will use: the barriers end balanced
   }
   else {
-    reg_dealloc<40>();      // idle warp of the third warpgroup (setmaxnreg is warpgroup-wide)
+    reg_dealloc<kWg2Regs>();      // warp 11 (setmaxnreg is warpgroup-wide): idle, or the int4 converter
+    if constexpr (I4) {
+      // ---------------------------------------------------------------- int4 -> int8 in shared memory (north_star item 2;
+      // the reference dequantises on load as well: MFA/GEMM/GEMMHeaders.swift:757-772).  TMA delivers the packed tile (128 rows x
+      // 64 bytes, byte j = codes 2j | 2j+1 << 4, each stored + 8: GEMMQuantization.swift:501-516); this warp expands it into the
+      // 128-byte-swizzled K-major operand tile the MMA reads.  Lane = one 16-byte unit (32 codes) of a row per pass, 16 passes per
+      // tile: reads are consecutive, the two 16-byte stores of a pass land on 8 distinct bank groups per quarter warp.
+      //   K: nibbles stay UNSIGNED (u8 operand): sum_d q (n - 8) = sum_d q n - 8 sum_d q, and the second term is a per-row constant
+      //      the softmax warps fold into their addend -- so a K tile costs split + interleave only (5 ops per 8 codes);
+      //   Q: signed codes (n ^ 8, sign-extended), and the row sums of the codes go to sQsum for that correction.
+      auto unpack_tile = [&](uint32_t src, uint32_t dst, auto is_q, uint32_t qsum_addr) {
+#pragma unroll 1
+        for (int i = 0; i < 16; ++i) {
+          const int id = i * 32 + lane, row = id >> 2, su = id & 3;
+          float f0, f1, f2, f3;
+          ld_shared_v4(src + id * 16, f0, f1, f2, f3);
+          const uint32_t wv[4] = {__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)};
+          uint32_t o[8];
+          int rs = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint32_t lo = wv[k] & 0x0f0f0f0fu, hi = (wv[k] >> 4) & 0x0f0f0f0fu;
+            if constexpr (decltype(is_q)::value) {
+              lo ^= 0x08080808u; hi ^= 0x08080808u;                          // n - 8 as a 4-bit two's complement ...
+              lo |= (lo & 0x08080808u) * 30u; hi |= (hi & 0x08080808u) * 30u; // ... sign-extended to the byte (0x08 * 30 = 0xF0)
+              rs = __dp4a((int)lo, 0x01010101, rs);
+              rs = __dp4a((int)hi, 0x01010101, rs);
+            }
+            o[2 * k] = __byte_perm(lo, hi, 0x5140);        // codes 0 1 2 3 of this word
+            o[2 * k + 1] = __byte_perm(lo, hi, 0x7362);    // codes 4 5 6 7
+          }
+          const uint32_t line = dst + (uint32_t)row * 128u;
+          st_shared_v4(line + (uint32_t)(((2 * su) ^ (row & 7)) << 4), __uint_as_float(o[0]), __uint_as_float(o[1]),
+                       __uint_as_float(o[2]), __uint_as_float(o[3]));
+          st_shared_v4(line + (uint32_t)(((2 * su + 1) ^ (row & 7)) << 4), __uint_as_float(o[4]), __uint_as_float(o[5]),
+                       __uint_as_float(o[6]), __uint_as_float(o[7]));
+          if constexpr (decltype(is_q)::value) {
+            rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+            rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+            if (su == 0) st_shared_u32(qsum_addr + row * 4, (uint32_t)rs);
+          }
+        }
+      };
+      int kvbase = 0, kr = 0, cq = 0, qc[2] = {0, 0};
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const Item im = decode(w);
+        const int nt = im.nt, n = im.n;
+        if (n == 0) continue;
+        auto convert_q = [&](int t2) {
+          if (qc[t2] > 0) mbar_wait(q_empty(t2), (qc[t2] - 1) & 1);      // the MMA warp has issued the last S that reads Q_t2
+          mbar_wait(qraw_full, cq & 1);
+          unpack_tile(sRawQ, sQ + t2 * QT, std::true_type{}, sQsum + t2 * 512);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(q_full(t2)); mbar_arrive(qraw_empty); }
+          ++cq; ++qc[t2];
+        };
+        convert_q(0);
+        for (int it = 0; it < n; ++it) {
+          const int idx = kvbase + 2 * it, s = idx % NS, rs = kr % NR;
+          mbar_wait(raw_full(rs), (kr / NR) & 1);
+          mbar_wait(kv_empty(s), ((idx / NS) & 1) ^ 1);
+          unpack_tile(sRawK + rs * RAW, sKV + s * STG, std::false_type{}, 0u);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(kv_full(s)); mbar_arrive(raw_empty(rs)); }
+          ++kr;
+          if (it == 0 && nt == 2) convert_q(1);
+        }
+        kvbase += 2 * n;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1033,6 +1147,16 @@ cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm_in, int D, int mode, cud
   dim3 grid((unsigned)(persist ? sm_count() : items), 1, 1);
   if (mode == kFwdI8) return D == 128 ? launch<128, kFwdI8>(prm, grid, st) : cudaErrorInvalidValue;
   if (mode == kFwdI8F8) return D == 128 ? launch<128, kFwdI8F8>(prm, grid, st) : cudaErrorInvalidValue;
+  if (mode == kFwdI4 || mode == kFwdI4F8) {       // packed int4 Q / K: default exp2 mix, or all-MUFU when the polynomial is off
+    if (D != 128) return cudaErrorInvalidValue;
+    const bool poly = poly_setting() > 0;
+    if (mode == kFwdI4) {
+      if (prm.mask) return poly ? launch_masked_k<128, kFwdI4, 3>(prm, grid, st) : launch_masked_k<128, kFwdI4, 0>(prm, grid, st);
+      return poly ? launch_k<128, kFwdI4, 3>(prm, grid, st) : launch_k<128, kFwdI4, 0>(prm, grid, st);
+    }
+    if (prm.mask) return poly ? launch_masked_k<128, kFwdI4F8, 3>(prm, grid, st) : launch_masked_k<128, kFwdI4F8, 0>(prm, grid, st);
+    return poly ? launch_k<128, kFwdI4F8, 3>(prm, grid, st) : launch_k<128, kFwdI4F8, 0>(prm, grid, st);
+  }
   if (mode == kFwdSplit) {        // exact exp2 only (the polynomial's 8.6e-5 would show at fp32 tolerances)
     if (D != 128) return cudaErrorInvalidValue;
     return prm.mask ? launch_masked_k<128, kFwdSplit, 0>(prm, grid, st) : launch_k<128, kFwdSplit, 0>(prm, grid, st);

@@ -10,8 +10,9 @@
 // QuantizedAttention.swift:71-91,358-463 -- attention on dequantised int8 operands with fp32 statistics) for symmetric
 // int8 codes (zero_point 0) with per-tensor or per-block scales (block = a multiple of 64 tokens of one (b, h); the
 // SageAttention2 contract SURVEY Q5 settles on), head_dim 128.  The fused kernel is the int8 operand mode of
-// attn_fwd_tc.cu (same pipeline, masking and P hand-off); this file holds the HBM-bound pre-passes (int4 -> int8
-// codes, V codes -> bf16), eligibility and parameter set-up.
+// attn_fwd_tc.cu (same pipeline, masking and P hand-off; packed int4 Q / K are unpacked in shared
+// memory by its converter warp); this file holds the HBM-bound pre-passes over V (codes -> e4m3 or bf16), eligibility and
+// parameter set-up.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -31,40 +32,33 @@ using namespace ptx;
 
 constexpr float kLog2e = 1.4426950408889634f;
 
-// ---- HBM-bound pre-passes -------------------------------------------------------------------------------------------
-// int8 codes -> bf16 (exact: |code| <= 128 needs 8 significant bits); 16 codes per thread per step.
-__global__ void codes_to_bf16_kernel(const int8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, uint64_t n16) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+// ---- HBM-bound pre-passes over V (Q and K go to the MMA as they are: int8 codes through TMA, packed int4 through TMA + the
+// in-kernel converter warp) -----------------------------------------------------------------------------------------------
+// 16 codes of V as ints: int8 bytes, or packed int4 (byte j = codes 2j | 2j+1 << 4, each stored + 8: GEMMQuantization.swift:501-516)
+template <int BITS>
+__device__ __forceinline__ void load_codes16(const uint8_t* __restrict__ src, uint64_t i, int* q) {
+  if (BITS == 8) {
     const int4 v = reinterpret_cast<const int4*>(src)[i];
     const int w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t out[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float f0 = (float)(int8_t)(w[k] & 0xff), f1 = (float)(int8_t)((w[k] >> 8) & 0xff);
-      const float f2 = (float)(int8_t)((w[k] >> 16) & 0xff), f3 = (float)(int8_t)((w[k] >> 24) & 0xff);
-      out[2 * k] = pack_bf16(f0, f1);
-      out[2 * k + 1] = pack_bf16(f2, f3);
-    }
-    reinterpret_cast<uint4*>(dst)[2 * i] = make_uint4(out[0], out[1], out[2], out[3]);
-    reinterpret_cast<uint4*>(dst)[2 * i + 1] = make_uint4(out[4], out[5], out[6], out[7]);
+    for (int k = 0; k < 16; ++k) q[k] = (int)(int8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xff);
+  } else {
+    const uint2 v = reinterpret_cast<const uint2*>(src)[i];
+    const uint32_t w[2] = {v.x, v.y};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) q[k] = (int)((w[k >> 3] >> (4 * (k & 7))) & 0xf) - 8;
   }
 }
 
-// packed int4 (element 2i in the low nibble, stored +8: GEMMQuantization.swift:501-516) -> int8 codes; 32 codes / thread.
-__global__ void int4_to_int8_kernel(const uint8_t* __restrict__ src, int8_t* __restrict__ dst, uint64_t n16) {
+// V codes -> bf16 (exact: |code| <= 128 needs 8 significant bits); 16 codes per thread per step.
+template <int BITS>
+__global__ void codes_to_bf16_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, uint64_t n16) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint4 v = reinterpret_cast<const uint4*>(src)[i];
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    int q[16];
+    load_codes16<BITS>(src, i, q);
     uint32_t out[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      // byte j of w[k] holds codes 2j (low nibble) and 2j+1 (high nibble)
-      uint32_t lo = w[k] & 0x0f0f0f0fu, hi = (w[k] >> 4) & 0x0f0f0f0fu;
-      // interleave: out bytes = lo0 hi0 lo1 hi1 | lo2 hi2 lo3 hi3, each minus 8
-      const uint32_t e0 = __byte_perm(lo, hi, 0x5140), e1 = __byte_perm(lo, hi, 0x7362);
-      out[2 * k] = __vsub4(e0, 0x08080808u);
-      out[2 * k + 1] = __vsub4(e1, 0x08080808u);
-    }
+    for (int k = 0; k < 8; ++k) out[k] = pack_bf16((float)q[2 * k], (float)q[2 * k + 1]);
     reinterpret_cast<uint4*>(dst)[2 * i] = make_uint4(out[0], out[1], out[2], out[3]);
     reinterpret_cast<uint4*>(dst)[2 * i + 1] = make_uint4(out[4], out[5], out[6], out[7]);
   }
@@ -84,8 +78,9 @@ __global__ void head_vscale_kernel(const float* __restrict__ scales, float one_s
   vh[hd] = v > 0.f ? v : 1.f;
 }
 
-// int8 codes -> e4m3(code * vs[block] / vh[head]); 16 codes per thread per step, a (b, head) spans rows_per_head * D elements
-__global__ void codes_to_e4m3_kernel(const int8_t* __restrict__ src, uint8_t* __restrict__ dst, const float* __restrict__ scales,
+// V codes -> e4m3(code * vs[block] / vh[head]); 16 codes per thread per step, a (b, head) spans rows_per_head * D elements
+template <int BITS>
+__global__ void codes_to_e4m3_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const float* __restrict__ scales,
                                      float one_scale, const float* __restrict__ vh, int block_rows, int nb_per_head,
                                      uint64_t rows_per_head, uint32_t D, uint64_t n16) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -95,15 +90,12 @@ __global__ void codes_to_e4m3_kernel(const int8_t* __restrict__ src, uint8_t* __
     float sc = one_scale;
     if (scales) sc = nb_per_head > 0 ? scales[hd * nb_per_head + (row - hd * rows_per_head) / block_rows] : scales[0];
     const float r = sc / vh[hd];
-    const int4 v = reinterpret_cast<const int4*>(src)[i];
-    const int w[4] = {v.x, v.y, v.z, v.w};
+    int q[16];
+    load_codes16<BITS>(src, i, q);
     uint32_t out[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float f0 = (float)(int8_t)(w[k] & 0xff) * r, f1 = (float)(int8_t)((w[k] >> 8) & 0xff) * r;
-      const float f2 = (float)(int8_t)((w[k] >> 16) & 0xff) * r, f3 = (float)(int8_t)((w[k] >> 24) & 0xff) * r;
-      out[k] = pack_e4m3(f0, f1) | (pack_e4m3(f2, f3) << 16);
-    }
+    for (int k = 0; k < 4; ++k)
+      out[k] = pack_e4m3((float)q[4 * k] * r, (float)q[4 * k + 1] * r) | (pack_e4m3((float)q[4 * k + 2] * r, (float)q[4 * k + 3] * r) << 16);
     reinterpret_cast<uint4*>(dst)[i] = make_uint4(out[0], out[1], out[2], out[3]);
   }
 }
@@ -127,20 +119,13 @@ bool scales_ok(const QuantView& q, bool need64) {
 
 }  // namespace
 
-cudaError_t launch_codes_to_bf16(const void* codes, void* dst, uint64_t n, cudaStream_t st) {
+cudaError_t launch_codes_to_bf16(const void* codes, int bits, void* dst, uint64_t n, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   if (n % 16) return cudaErrorInvalidValue;
-  codes_to_bf16_kernel<<<grid_for(n / 16, 256), 256, 0, st>>>(reinterpret_cast<const int8_t*>(codes),
-                                                             reinterpret_cast<__nv_bfloat16*>(dst), n / 16);
-  ++g_launch_count;
-  return cudaGetLastError();
-}
-
-cudaError_t launch_int4_to_int8(const void* packed, void* codes, uint64_t n, cudaStream_t st) {
-  if (n == 0) return cudaSuccess;
-  if (n % 32) return cudaErrorInvalidValue;
-  int4_to_int8_kernel<<<grid_for(n / 32, 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(packed),
-                                                            reinterpret_cast<int8_t*>(codes), n / 32);
+  if (bits == 8)
+    codes_to_bf16_kernel<8><<<grid_for(n / 16, 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(codes), reinterpret_cast<__nv_bfloat16*>(dst), n / 16);
+  else
+    codes_to_bf16_kernel<4><<<grid_for(n / 16, 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(codes), reinterpret_cast<__nv_bfloat16*>(dst), n / 16);
   ++g_launch_count;
   return cudaGetLastError();
 }
@@ -178,54 +163,55 @@ bool fwd_tcq_eligible(const AttnParams& p) {
   return tc::encode_fn() != nullptr;
 }
 
-// scratch: at least  Skv*B*Hkv*D*2 (V as bf16; the e4m3 path uses half of it, plus B*Hkv head scales)
-// [+ (Sq*B*H + Skv*B*Hkv)*D bytes of int8 codes when the input is int4].
+// scratch: Skv*B*Hkv*D*2 bytes (V as bf16; the e4m3 path uses half of it) + B*Hkv head scales
 size_t fwd_tcq_scratch_bytes(const AttnParams& p) {
-  const size_t nq = (size_t)p.B * p.H * p.Sq * p.D, nkv = (size_t)p.B * p.Hkv * p.Skv * p.D;
-  return nkv * 2 + (p.in_dtype == kI4 ? nq + 2 * nkv : 0) + (size_t)p.B * p.Hkv * 4 + 2048;
+  const size_t nkv = (size_t)p.B * p.Hkv * p.Skv * p.D;
+  return nkv * 2 + (size_t)p.B * p.Hkv * 4 + 2048;
 }
 
 cudaError_t launch_fwd_tcq(const AttnParams& p, void* scratch, cudaStream_t st) {
-  const size_t nq = (size_t)p.B * p.H * p.Sq * p.D, nkv = (size_t)p.B * p.Hkv * p.Skv * p.D;
+  const size_t nkv = (size_t)p.B * p.Hkv * p.Skv * p.D;
   uint8_t* sc = reinterpret_cast<uint8_t*>(scratch);
   void* v16 = sc;
   const void *qc = p.q.ptr, *kc = p.k.ptr, *vc = p.v.ptr;
+  const bool i4 = p.in_dtype == kI4;
+  const int bits = i4 ? 4 : 8;
   cudaError_t e;
-  if (p.in_dtype == kI4) {
-    uint8_t* q8 = sc + ((nkv * 2 + 127) & ~(size_t)127);
-    uint8_t* k8 = q8 + ((nq + 127) & ~(size_t)127);
-    uint8_t* v8 = k8 + ((nkv + 127) & ~(size_t)127);
-    if ((e = launch_int4_to_int8(qc, q8, nq, st)) != cudaSuccess) return e;
-    if ((e = launch_int4_to_int8(kc, k8, nkv, st)) != cudaSuccess) return e;
-    if ((e = launch_int4_to_int8(vc, v8, nkv, st)) != cudaSuccess) return e;
-    qc = q8; kc = k8; vc = v8;
-  }
   const bool f8 = fwd_tcq_pv_mode() == 0;
-  float* vh = nullptr;                      // e4m3 path: one scale per (b, head), behind everything else in the scratch
+  float* vh = nullptr;                      // e4m3 path: one scale per (b, head), behind V in the scratch
+  if (nkv % 16) return cudaErrorInvalidValue;
   if (f8) {
-    const size_t off = (nkv * 2 + (p.in_dtype == kI4 ? nq + 2 * nkv : 0) + 1023) & ~(size_t)255;
+    const size_t off = (nkv * 2 + 1023) & ~(size_t)255;
     vh = reinterpret_cast<float*>(sc + off);
     const int heads = p.B * p.Hkv;
     const bool blocks = p.qv.scales && p.qv.block_rows > 0;
     const int nb = blocks ? (p.Skv + p.qv.block_rows - 1) / p.qv.block_rows : 0;
-    const float qmax = p.in_dtype == kI4 ? 8.f : 128.f;
+    const float qmax = i4 ? 8.f : 128.f;
     head_vscale_kernel<<<(heads + 127) / 128, 128, 0, st>>>(p.qv.scales, p.qv.scale, nb, heads, qmax, vh);
-    if (nkv % 16) return cudaErrorInvalidValue;
-    codes_to_e4m3_kernel<<<grid_for(nkv / 16, 256), 256, 0, st>>>(reinterpret_cast<const int8_t*>(vc), reinterpret_cast<uint8_t*>(v16),
-                                                                 p.qv.scales, p.qv.scale, vh, blocks ? p.qv.block_rows : 1, nb,
-                                                                 (uint64_t)p.Skv, (uint32_t)p.D, nkv / 16);
+    if (i4)
+      codes_to_e4m3_kernel<4><<<grid_for(nkv / 16, 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(vc), reinterpret_cast<uint8_t*>(v16),
+                                                                      p.qv.scales, p.qv.scale, vh, blocks ? p.qv.block_rows : 1, nb,
+                                                                      (uint64_t)p.Skv, (uint32_t)p.D, nkv / 16);
+    else
+      codes_to_e4m3_kernel<8><<<grid_for(nkv / 16, 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(vc), reinterpret_cast<uint8_t*>(v16),
+                                                                      p.qv.scales, p.qv.scale, vh, blocks ? p.qv.block_rows : 1, nb,
+                                                                      (uint64_t)p.Skv, (uint32_t)p.D, nkv / 16);
     g_launch_count += 2;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  } else if ((e = launch_codes_to_bf16(vc, v16, nkv, st)) != cudaSuccess) {
+  } else if ((e = launch_codes_to_bf16(vc, bits, v16, nkv, st)) != cudaSuccess) {
     return e;
   }
 
   FwdTcParams prm = {};
   TensorView tq = p.q, tk = p.k, tv = p.v;
   tq.ptr = qc; tk.ptr = kc; tv.ptr = v16;
-  if (!tc::make_map(&prm.tq, tq, kI8, p.B, p.H, p.Sq, p.D) || !tc::make_map(&prm.tk, tk, kI8, p.B, p.Hkv, p.Skv, p.D) ||
-      !tc::make_map(&prm.tv, tv, f8 ? kI8 : kBF16, p.B, p.Hkv, p.Skv, p.D))
+  if (i4) {     // packed rows of D / 2 bytes, unpacked by the kernel's converter warp
+    if (!tc::make_map_raw(&prm.tq, qc, p.B, p.H, p.Sq, p.D / 2) || !tc::make_map_raw(&prm.tk, kc, p.B, p.Hkv, p.Skv, p.D / 2))
+      return cudaErrorInvalidValue;
+  } else if (!tc::make_map(&prm.tq, tq, kI8, p.B, p.H, p.Sq, p.D) || !tc::make_map(&prm.tk, tk, kI8, p.B, p.Hkv, p.Skv, p.D)) {
     return cudaErrorInvalidValue;
+  }
+  if (!tc::make_map(&prm.tv, tv, f8 ? kI8 : kBF16, p.B, p.Hkv, p.Skv, p.D)) return cudaErrorInvalidValue;
   prm.o = const_cast<void*>(p.o.ptr);
   prm.o_sb = p.o.sb; prm.o_sh = p.o.sh; prm.o_ss = p.o.ss;
   prm.lse = p.lse; prm.o_dtype = p.o_dtype;
@@ -248,13 +234,13 @@ cudaError_t launch_fwd_tcq(const AttnParams& p, void* scratch, cudaStream_t st) 
   setq(p.qk, p.Skv, prm.ks, prm.ks1, prm.kbr, prm.nbk, prm.sk_);
   setq(p.qv, p.Skv, prm.vs, prm.vs1, prm.vbr, prm.nbv, prm.sv_);
   {   // |S_int| <= 128 * 128 * 128 = 2^21 (int8) or 8 * 8 * 128 = 2^13 (int4): the widest shift whose +-2^(22-k) window holds it
-    const int k = p.in_dtype == kI4 ? 8 : 1;
+    const int k = i4 ? 8 : 1;          // int4: q in [-8, 7] times UNSIGNED k nibbles in [0, 15], |S_mma| <= 8 * 15 * 128 < 2^14
     prm.s_mul = 1 << k;
     prm.s_bias = 1.5f * (float)(1u << (23 - k));
     prm.s_add = __float_as_uint_host(prm.s_bias);
   }
   if (f8) { prm.vs = vh; prm.vs1 = 1.f; }        // e4m3 V: the kernel reads vs[b * Hkv + head] in its epilogue
-  e = launch_fwd_tc_kernel(prm, p.D, f8 ? kFwdI8F8 : kFwdI8, st, p.B);
+  e = launch_fwd_tc_kernel(prm, p.D, i4 ? (f8 ? kFwdI4F8 : kFwdI4) : (f8 ? kFwdI8F8 : kFwdI8), st, p.B);
   if (e != cudaSuccess) return e;
   ++g_launch_count;
   g_last_kernel = f8 ? (p.in_dtype == kI4 ? "fwd_tcq_int4_pvf8_d128" : "fwd_tcq_int8_pvf8_d128")

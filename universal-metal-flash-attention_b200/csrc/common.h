@@ -101,10 +101,9 @@ cudaError_t launch_fwd_split(const AttnParams& p, void* scratch, cudaStream_t st
 bool fwd_tcq_eligible(const AttnParams& p);
 size_t fwd_tcq_scratch_bytes(const AttnParams& p);
 cudaError_t launch_fwd_tcq(const AttnParams& p, void* scratch, cudaStream_t st);
-cudaError_t launch_codes_to_bf16(const void* codes, void* dst, uint64_t n, cudaStream_t st);
+cudaError_t launch_codes_to_bf16(const void* codes, int bits, void* dst, uint64_t n, cudaStream_t st);
 int fwd_tcq_pv_mode();                      // P V of the quantised tensor-core forward: 0 = e4m3 (default), 1 = bf16
 void fwd_tcq_set_pv_mode(int bf16);
-cudaError_t launch_int4_to_int8(const void* packed, void* codes, uint64_t n, cudaStream_t st);
 
 // quantiser & friends
 cudaError_t launch_quantize(const void* src, int src_dtype, void* codes, float* scales, uint64_t rows, uint64_t cols,

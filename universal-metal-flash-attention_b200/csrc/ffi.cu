@@ -31,6 +31,20 @@ namespace {
 bool g_debug = false;
 #define DBG(...) do { if (g_debug) { fprintf(stderr, "[mfa] " __VA_ARGS__); fputc('\n', stderr); } } while (0)
 
+// A call that the tensor-core kernels cannot serve runs on the exact fp32-math SIMT kernels, ~100x slower.  Small calls are
+// served there by design; for anything sizeable say so ONCE per process and direction (MFA_QUIET_FALLBACK=1 silences it,
+// last_kernel always tells the route).
+void note_simt_route(const char* what, const AttnParams& p) {
+  static bool said[2] = {false, false};
+  const int i = what[0] == 'b' ? 1 : 0;
+  if (said[i] || (double)p.B * p.H * p.Sq * p.Skv < 64.0 * 1024 * 1024 || getenv("MFA_QUIET_FALLBACK")) return;
+  said[i] = true;
+  const char* dt[] = {"fp16", "bf16", "fp32", "int8", "int4"};
+  fprintf(stderr, "[mfa] %s of B=%d H=%d Sq=%d Skv=%d D=%d (%s operands) runs on the exact SIMT kernels, not the tensor pipe: "
+          "tensor-core routes need head_dim 64/128 (fp32 / int8 / int4: 128), unit stride along D, masks with unit key stride, "
+          "no transposed operands\n", what, p.B, p.H, p.Sq, p.Skv, p.D, (p.in_dtype >= 0 && p.in_dtype <= 4) ? dt[p.in_dtype] : "?");
+}
+
 struct Scratch {
   void* ptr = nullptr;
   size_t cap = 0;
@@ -510,6 +524,7 @@ mfa_error_t forward_core(Context* ctx, const FwdArgs& a) {
     if (!tmp) return MFA_ERROR_MEMORY_ALLOCATION;
     e = launch_fwd_split(p, tmp, st);
   } else {
+    note_simt_route("forward", p);
     e = launch_fwd_simt(p, st);
   }
   tm.stop();
@@ -625,6 +640,7 @@ mfa_error_t backward_core(Context* ctx, const BwdArgs& a) {
     if (e == cudaSuccess) e = launch_bwd_tc(p, st);
     if (e == cudaSuccess && tcq_name) g_last_kernel = tcq_name;
   } else {
+    note_simt_route("backward", p);
     e = launch_bwd_simt(p, st);   // empty Sq / Skv degrade to zero-filled gradients inside the kernels
   }
   tm.stop();
@@ -757,6 +773,7 @@ mfa_error_t qforward_core(Context* ctx, const QFwdArgs& a) {
     if (!tmp) return MFA_ERROR_MEMORY_ALLOCATION;
     e = launch_fwd_tcq(p, tmp, st);
   } else {
+    note_simt_route("forward", p);
     e = launch_fwd_simt(p, st);
   }
   tm.stop();

@@ -9,7 +9,8 @@
 namespace mfa {
 
 // I8: int8 Q K^T + bf16 P V; I8F8: int8 Q K^T + e4m3 P V; Split: fp32 operands as scaled fp16 (hi, lo) pairs, three MMAs per product
-enum FwdMode : int { kFwdF16 = 0, kFwdBF16 = 1, kFwdI8 = 2, kFwdI8F8 = 3, kFwdSplit = 4 };
+// I4 / I4F8: as I8 / I8F8 with Q and K delivered as packed int4 and unpacked in shared memory (tq / tk map the packed bytes)
+enum FwdMode : int { kFwdF16 = 0, kFwdBF16 = 1, kFwdI8 = 2, kFwdI8F8 = 3, kFwdSplit = 4, kFwdI4 = 5, kFwdI4F8 = 6 };
 
 struct FwdTcParams {
   CUtensorMap tq, tk, tv;

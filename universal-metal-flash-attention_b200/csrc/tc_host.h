@@ -53,6 +53,20 @@ inline bool make_map(CUtensorMap* out, const TensorView& t, int dtype, int B, in
   return r == CUDA_SUCCESS;
 }
 
+// packed bytes [B, Hn, S, row_bytes] contiguous (int4 codes, two per byte) -> 4-D tensor map, box = row_bytes x 128 rows,
+// NO swizzle: the tile lands row-major in shared memory, where a converter warp expands it (attn_fwd_tc.cu, int4 modes)
+inline bool make_map_raw(CUtensorMap* out, const void* ptr, int B, int Hn, int S, int row_bytes) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || row_bytes <= 0 || (row_bytes & 15)) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)row_bytes, (cuuint64_t)S, (cuuint64_t)Hn, (cuuint64_t)B};
+  cuuint64_t st[3] = {(cuuint64_t)row_bytes, (cuuint64_t)row_bytes * S, (cuuint64_t)row_bytes * S * Hn};
+  cuuint32_t box[4] = {(cuuint32_t)row_bytes, 128, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(ptr), dims, st, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 // [slots][B][Hn][S][D] contiguous 16-bit operand -> 5-D tensor map (ring attention's visiting K/V pairs), same box / swizzle
 typedef CUresult (*EncodeTiledFn5)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
