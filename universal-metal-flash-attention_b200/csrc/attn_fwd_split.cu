@@ -9,7 +9,8 @@
 //     S = Q_hi K_lo^T + Q_hi K_hi^T + Q_lo K_hi^T,      O += P_hi V_hi + P_lo V_hi + P_hi V_lo,
 // P being split the same way by the softmax warps (P_hi / P_lo share the TMEM columns S has just left).  The dropped lo * lo
 // terms are 2^-22 of a product, the fp16 products are exact and accumulate in fp32, the softmax itself is the fp32 code of
-// the 16-bit kernel with MUFU exp2 only -- the result agrees with the fp64 oracle to ~1e-6 of max|O| (tests hold 1e-5),
+// the 16-bit kernel with MUFU exp2 only -- the result agrees with the fp64 oracle to ~5e-6 of max|O| (tests hold 1e-5; what
+// limits it is the truncating accumulation of tcgen05.mma, see launch_fwd_split),
 // at three times the MMA work of the bf16 kernel instead of the 9 TFLOP/s of the exact SIMT kernel it replaces at D = 128.
 // The power-of-two scales are undone exactly: 2^-(kq + kk) rides in the softmax scale, 2^-kv in the epilogue's 1 / l.
 //
@@ -18,6 +19,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "common.h"
 #include "fwd_tc.h"
@@ -28,16 +31,29 @@ namespace mfa {
 namespace {
 
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr int kSliceKeys = 1024;      // keys per launch (see launch_fwd_split)
+// keys per launch (see launch_fwd_split); MFA_FP32_SLICE_KEYS overrides it (a multiple of 128; 0 = one launch over all keys)
+int slice_keys() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MFA_FP32_SLICE_KEYS");
+    v = e ? atoi(e) : 1024;
+    if (v < 0 || (v & 127)) v = 1024;
+  }
+  return v;
+}
 
 struct SplitView {
   const float* src;
   long long sb, sh, ss;        // element strides of the [B, H, S, D] source view (unit stride along D)
   int H, S, D4;                // D / 4
+  int contiguous;              // packed BHSD: element index = linear index
   unsigned long long n4;       // B * H * S * D / 4
 };
 
+// float4 group i of the packed [B, H, S, D] order.  Contiguous sources (the common case) need no index arithmetic; strided
+// ones pay three integer divisions per 16 bytes (still far cheaper than what the pass replaces).
 __device__ __forceinline__ const float4* row_ptr(const SplitView& v, unsigned long long i, int& d4) {
+  if (v.contiguous) { d4 = 0; return reinterpret_cast<const float4*>(v.src) + i; }
   d4 = (int)(i % v.D4);
   unsigned long long r = i / v.D4;
   const int s = (int)(r % v.S); r /= v.S;
@@ -46,19 +62,7 @@ __device__ __forceinline__ const float4* row_ptr(const SplitView& v, unsigned lo
   return reinterpret_cast<const float4*>(v.src + b * v.sb + (long long)h * v.sh + (long long)s * v.ss) + d4;
 }
 
-// max |x| of one tensor: bit pattern of a non-negative float orders like the float, so one atomicMax per warp does it
-__global__ void split_absmax_kernel(const SplitView v, unsigned int* __restrict__ amax) {
-  float m = 0.f;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.n4;
-       i += (unsigned long long)gridDim.x * blockDim.x) {
-    int d4;
-    const float4 x = __ldg(row_ptr(v, i, d4));
-    m = fmaxf(fmaxf(m, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
-}
+struct SplitViews { SplitView v[3]; };      // Q, K, V of one call: blockIdx.y picks the tensor, so each pre-pass is ONE launch
 
 // exponent k of the power-of-two scale: max|x| 2^k in [2^13, 2^14), clamped so that 2^k and 2^-k stay normal floats
 __device__ __forceinline__ int split_exponent(unsigned int amax_bits) {
@@ -69,25 +73,63 @@ __device__ __forceinline__ int split_exponent(unsigned int amax_bits) {
   return max(-100, min(100, 14 - e));
 }
 
-// hi / lo halves, packed [B, H, S, D] fp16 each; thread 0 leaves the inverse scale for the attention kernel
-__global__ void split_f16_kernel(const SplitView v, const unsigned int* __restrict__ amax, __half* __restrict__ hi,
-                                 __half* __restrict__ lo, float* __restrict__ inv_scale) {
-  const int k = split_exponent(*amax);
-  const float sc = ldexpf(1.f, k);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *inv_scale = ldexpf(1.f, -k);
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.n4;
-       i += (unsigned long long)gridDim.x * blockDim.x) {
-    int d4;
-    const float4 x = __ldg(row_ptr(v, i, d4));
-    const float xs[4] = {x.x * sc, x.y * sc, x.z * sc, x.w * sc};
-    __half h[4], l[4];
+constexpr int kIlp = 4;                // independent 16-byte loads in flight per thread and pass
+
+// max |x| per tensor: bit pattern of a non-negative float orders like the float, so one atomicMax per warp does it
+__global__ void __launch_bounds__(256) split_absmax_kernel(const SplitViews vs, unsigned int* __restrict__ amax) {
+  const SplitView& v = vs.v[blockIdx.y];
+  float m = 0.f;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < v.n4; i0 += stride * kIlp) {
+    float4 x[kIlp];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      h[j] = __float2half_rn(xs[j]);
-      l[j] = __float2half_rn(xs[j] - __half2float(h[j]));
+    for (int j = 0; j < kIlp; ++j) {
+      const unsigned long long i = i0 + j * stride;
+      int d4;
+      x[j] = i < v.n4 ? __ldg(row_ptr(v, i, d4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<const uint2*>(h);
-    reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<const uint2*>(l);
+#pragma unroll
+    for (int j = 0; j < kIlp; ++j)
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(x[j].x), fabsf(x[j].y))), fmaxf(fabsf(x[j].z), fabsf(x[j].w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax + blockIdx.y, __float_as_uint(m));
+}
+
+// hi / lo halves, packed [B, H, S, D] fp16 each (lo right behind hi); thread 0 leaves the inverse scale for the attention kernel
+struct SplitOut { __half* hi[3]; };
+__global__ void __launch_bounds__(256) split_f16_kernel(const SplitViews vs, const unsigned int* __restrict__ amax, const SplitOut out,
+                                                        float* __restrict__ inv_scale) {
+  const SplitView& v = vs.v[blockIdx.y];
+  const int k = split_exponent(amax[blockIdx.y]);
+  const float sc = ldexpf(1.f, k);
+  if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[blockIdx.y] = ldexpf(1.f, -k);
+  __half* hi = out.hi[blockIdx.y];
+  __half* lo = hi + v.n4 * 4;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < v.n4; i0 += stride * kIlp) {
+    float4 x[kIlp];
+#pragma unroll
+    for (int j = 0; j < kIlp; ++j) {
+      const unsigned long long i = i0 + j * stride;
+      int d4;
+      if (i < v.n4) x[j] = __ldg(row_ptr(v, i, d4));
+    }
+#pragma unroll
+    for (int j = 0; j < kIlp; ++j) {
+      const unsigned long long i = i0 + j * stride;
+      if (i >= v.n4) break;
+      const float xs[4] = {x[j].x * sc, x[j].y * sc, x[j].z * sc, x[j].w * sc};
+      __half h[4], l[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        h[c] = __float2half_rn(xs[c]);
+        l[c] = __float2half_rn(xs[c] - __half2float(h[c]));
+      }
+      reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<const uint2*>(h);
+      reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<const uint2*>(l);
+    }
   }
 }
 
@@ -102,7 +144,7 @@ bool src_ok(const TensorView& t, int64_t Hn, int64_t B) {
 size_t pad256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 unsigned split_grid(unsigned long long n4) {
-  const unsigned long long g = (n4 + 255) / 256, cap = 148ull * 8;
+  const unsigned long long g = (n4 + 255) / 256, cap = 148ull * 4;
   return (unsigned)(g < cap ? (g ? g : 1) : cap);
 }
 
@@ -144,12 +186,20 @@ cudaError_t launch_fwd_split(const AttnParams& p, void* scratch, cudaStream_t st
   __half* dst[3] = {qh, kh, vh};
   const int Hn[3] = {p.H, p.Hkv, p.Hkv}, S[3] = {p.Sq, p.Skv, p.Skv};
   const size_t n[3] = {nq, nkv, nkv};
+  SplitViews vs;
+  SplitOut out;
+  unsigned long long nmax = 0;
   for (int i = 0; i < 3; ++i) {
-    SplitView v{reinterpret_cast<const float*>(src[i]->ptr), src[i]->sb, src[i]->sh, src[i]->ss, Hn[i], S[i], p.D / 4, n[i] / 4};
-    split_absmax_kernel<<<split_grid(v.n4), 256, 0, st>>>(v, amax + i);
-    split_f16_kernel<<<split_grid(v.n4), 256, 0, st>>>(v, amax + i, dst[i], dst[i] + n[i], inv + i);
-    g_launch_count += 2;
+    const bool packed_src = src[i]->ss == p.D && src[i]->sh == (int64_t)S[i] * p.D && src[i]->sb == (int64_t)Hn[i] * S[i] * p.D;
+    vs.v[i] = SplitView{reinterpret_cast<const float*>(src[i]->ptr), src[i]->sb, src[i]->sh, src[i]->ss, Hn[i], S[i], p.D / 4,
+                        packed_src ? 1 : 0, n[i] / 4};
+    out.hi[i] = dst[i];
+    nmax = vs.v[i].n4 > nmax ? vs.v[i].n4 : nmax;
   }
+  const dim3 grid(split_grid((nmax + kIlp - 1) / kIlp), 3, 1);
+  split_absmax_kernel<<<grid, 256, 0, st>>>(vs, amax);
+  split_f16_kernel<<<grid, 256, 0, st>>>(vs, amax, out, inv);
+  g_launch_count += 2;
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
   FwdTcParams prm = {};
@@ -181,7 +231,8 @@ cudaError_t launch_fwd_split(const AttnParams& p, void* scratch, cudaStream_t st
   // attention uses).  Why: tcgen05 adds every MMA into the TMEM accumulator with truncation, a bias of ~2^-24 of the accumulator
   // per MMA; O collects 24 MMAs per KV step, so one launch over N keys carries ~N * 5.6e-9 relative error (measured 1.7e-5 at
   // 4099 keys, 2.9e-5 at 4608) -- beyond the 1e-5 this path promises.  Slices of 1024 keys keep it at ~5e-6.
-  const int n_slices = (p.o_dtype == kF32 && !p.accumulate && slice_lse) ? (p.Skv + kSliceKeys - 1) / kSliceKeys : 1;
+  const int kSliceKeys = slice_keys();
+  const int n_slices = (kSliceKeys > 0 && p.o_dtype == kF32 && !p.accumulate && slice_lse) ? (p.Skv + kSliceKeys - 1) / kSliceKeys : 1;
   if (n_slices <= 1) {
     if ((e = fwd_tc_build_mask_tiles(prm, p, st)) != cudaSuccess) return e;
     e = launch_fwd_tc_kernel(prm, p.D, kFwdSplit, st, p.B);
