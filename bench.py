@@ -49,6 +49,9 @@ WORKLOADS = {
     # the reference adapters' default precision: fp32 operands, served on the tensor pipe as fp16 (hi, lo) pairs (3 MMAs / product)
     "flux_fp32": dict(B=1, H=24, Sq=4608, Skv=4608, D=128, causal=False, window=-1, dtype="fp32",
                       label="FLUX shape with fp32 operands (reference default precision) B=1 H=24 N=4608 D=128 forward"),
+    # head_dim 256 (the head dim of the reference's own headline figure): two 128-column halves of O per query block
+    "d256": dict(B=1, H=16, Sq=8192, Skv=8192, D=256, causal=False, window=-1, dtype="bf16",
+                 label="bf16 B=1 H=16 N=8192 D=256 forward"),
     "flux_causal": dict(B=1, H=24, Sq=4608, Skv=4608, D=128, causal=True, window=-1, dtype="bf16",
                         label="FLUX shape, causal"),
     "long_window": dict(B=1, H=32, Sq=32768, Skv=32768, D=128, causal=True, window=4096, dtype="bf16",
@@ -64,7 +67,7 @@ WORKLOADS = {
     "ring16k": dict(B=1, H=8, Sq=16384, Skv=16384, D=128, causal=True, window=-1, dtype="bf16", ring=True,
                     label="16k-token causal ring attention (smoke size)"),
 }
-ALL_EXTRAS = ["fwdbwd_flux", "c4_fwdbwd_heads_sharded", "int8_block", "int4_block", "fp32_flux", "ring128k"]
+ALL_EXTRAS = ["fwdbwd_flux", "c4_fwdbwd_heads_sharded", "int8_block", "int4_block", "fp32_flux", "d256_fwd", "ring128k"]
 
 
 def visible_pairs(Sq, Skv, causal, window):
@@ -380,7 +383,9 @@ def section_attention(hz, w, mode, steps, warmup, heads_sharded=False, o_dtype="
            "roofline": hz.roofline(per_rank_flops, med, note=(
                "per-GPU launch(es) of one step" if mode == "fwdbwd" else
                "algorithmic FLOPs; the fp32 path issues 3 fp16 MMAs per product (hi/lo operand pairs), so the tensor pipe does 3x this work"
-               if w["dtype"] == "fp32" else None)),
+               if w["dtype"] == "fp32" else
+               "algorithmic FLOPs; head_dim 256 runs as two 128-column halves of O per query block, Q K^T computed for each: the tensor pipe does 1.5x this work"
+               if w["D"] == 256 else None)),
            "gpu_launches": launches, "clocks": clocks}
     del sets
     hz.torch.cuda.empty_cache()
@@ -542,6 +547,8 @@ def run_extras(hz, names, args):
                 rec = section_quant(hz, min(args.steps, 10), 3, 4, "int4 block-64 codes")
             elif name == "fp32_flux":
                 rec = section_attention(hz, WORKLOADS["flux_fp32"], "fwd", min(args.steps, 10), 3)[0]
+            elif name == "d256_fwd":
+                rec = section_attention(hz, WORKLOADS["d256"], "fwd", min(args.steps, 10), 3)[0]
             elif name == "ring128k":
                 rec = section_ring(hz, WORKLOADS["ring128k"], min(args.steps, 4), 3)
             else:

@@ -334,3 +334,39 @@ def test_tc_fp16_output_tma_store(ctx, shape, causal):
     ref, _ = O.attention_forward(q.astype(np.float32), k.astype(np.float32), v.astype(np.float32), causal=causal)
     assert np.isfinite(out).all()
     assert rel_max(out.astype(np.float32), ref) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# head_dim 256 (the head dim of the reference's own headline figure, AttentionDescriptor+Parameters.swift:133-153): the kernel
+# runs it as two 128-column halves of O per query block, S over all 256 dims.
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(1, 2, 256, 256), (1, 1, 128, 128), (2, 3, 300, 777), (1, 2, 1, 1), (1, 2, 1000, 130), (1, 1, 257, 2051)])
+def test_tc_d256_shapes(ctx, dtype, shape):
+    B, H, Sq, Skv = shape
+    run_case(ctx, B, H, Sq, Skv, 256, dtype, seed=Sq + Skv)
+    assert ctx.last_kernel == f"fwd_tc_{dtype}_d256"
+
+
+@pytest.mark.parametrize("causal,window", [(True, None), (True, 300), (False, 100)])
+def test_tc_d256_causal_window(ctx, causal, window):
+    run_case(ctx, 1, 2, 1024, 1024, 256, "bf16", causal=causal, window=window, seed=5)
+    run_case(ctx, 2, 1, 333, 700, 256, "fp16", causal=causal, window=window, seed=6)
+
+
+def test_tc_d256_large_logits_rescale_path(ctx):
+    run_case(ctx, 1, 1, 512, 2048, 256, "bf16", seed=3, amp=3.0, scale=1.0)
+
+
+def test_tc_d256_external_mask(ctx):
+    import umfa
+    B, H, Sq, Skv, D = 2, 2, 256, 384, 256
+    rng = np.random.default_rng(31)
+    q, k, v = (rng.standard_normal(s).astype(np.float32) for s in ((B, H, Sq, D), (B, H, Skv, D), (B, H, Skv, D)))
+    (qa, qv), (ka, kv), (va, vv) = (to_dtype(x, "bf16") for x in (q, k, v))
+    m = (2.0 * rng.standard_normal((B, H, Sq, Skv))).astype(np.float32)
+    m[:, :, :, 128:256] = -np.inf
+    out, lse = umfa.flash_attention_forward(ctx, qa, ka, va, input_precision="bf16", output_precision="fp32", layout="bhsd",
+                                            attn_mask=m, return_lse=True)
+    assert ctx.last_kernel == "fwd_tc_bf16_d256_mask", ctx.last_kernel
+    ref, lref = O.attention_forward(qv, kv, vv, mask=m)
+    assert rel_max(out, ref) < 2e-2 and np.abs(lse - lref).max() < 2e-2

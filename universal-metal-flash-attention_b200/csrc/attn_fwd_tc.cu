@@ -60,15 +60,16 @@ struct Cfg {
   static constexpr bool kF8 = MODE == kFwdI8F8 || MODE == kFwdI4F8;  // int8 Q K^T, e4m3 P V
   static constexpr bool kI8 = MODE == kFwdI8 || kF8 || kI4;          // int8 Q K^T
   static constexpr bool kSplit = MODE == kFwdSplit;                  // fp32 operands as fp16 (hi, lo) pairs, 3 MMAs per product
+  static constexpr bool kWide = MODE == kFwdWideF16 || MODE == kFwdWideBF16;   // head_dim 256: (a, b) halves of 128 columns
   static constexpr int kChunkBytes = 128 * 128;                      // one 128-byte swizzle chunk of 128 rows
   static constexpr int kQChunks = kI8 ? 1 : D / 64;                  // chunks per Q / K tile (split: per hi / lo half)
   static constexpr int kVChunks = kF8 ? 1 : D / 64;                  // V: 16-bit, or e4m3 (128 head dims = one 128-byte row)
   static constexpr int kHalf = kQChunks * kChunkBytes;               // one K tile, or one half (hi / lo) of a split tile
-  static constexpr int kQTile = kHalf * (kSplit ? 2 : 1);            // split: Q_hi then Q_lo
+  static constexpr int kQTile = kHalf * ((kSplit || kWide) ? 2 : 1); // split: Q_hi then Q_lo; wide: Q_a then Q_b
   static constexpr int kVTile = kVChunks * kChunkBytes;
   static constexpr int kStage = kVTile;                              // ring stage (K tiles may use part of it)
-  static constexpr int kSPS = kSplit ? 4 : 2;                        // ring stages per KV step (split: K_lo, K_hi, V_hi, V_lo)
-  static constexpr int kStages = kSplit ? 3 : (D == 128 && !kF8) ? 5 : 10;   // split: 2 x 64 KB of Q leave room for 3 x 32 KB
+  static constexpr int kSPS = kSplit ? 4 : kWide ? 3 : 2;            // ring stages per KV step (split: K_lo, K_hi, V_hi, V_lo; wide: K_a, K_b, V_half)
+  static constexpr int kStages = (kSplit || kWide) ? 3 : (D == 128 && !kF8) ? 5 : 10;   // split / wide: 2 x 64 KB of Q leave room for 3 x 32 KB
   static constexpr int kBarBytes = 112 + 16 * kStages + 16 + 32 + 64; // + q_empty, o_empty, + raw-tile barriers (int4)
   // int4: raw (packed) tiles as TMA delivers them -- a 3-deep ring of K tiles + one Q tile, 128 rows x 64 bytes each -- and
   // the per-row sums of the Q codes (2 x 128 ints)
@@ -178,8 +179,8 @@ __device__ __forceinline__ void exp_phase(const float* s, float a0, float a1, fl
 template <int D, int MODE, int POLY, bool TR = false, bool MASKED = false>
 __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_constant__ FwdTcParams p) {
   using C = Cfg<D, MODE>;
-  constexpr bool I8 = C::kI8, F8 = C::kF8, SPLIT = C::kSplit, I4 = C::kI4;
-  constexpr int PF = SPLIT ? 3 : F8 ? 2 : (MODE == kFwdF16 ? 0 : 1);  // format of P (and of V): f16 / bf16 / e4m3 / f16 (hi, lo) pairs
+  constexpr bool I8 = C::kI8, F8 = C::kF8, SPLIT = C::kSplit, I4 = C::kI4, WIDE = C::kWide;
+  constexpr int PF = SPLIT ? 3 : F8 ? 2 : ((MODE == kFwdF16 || MODE == kFwdWideF16) ? 0 : 1);  // format of P (and of V): f16 / bf16 / e4m3 / f16 (hi, lo) pairs
   // e4m3 P: the exponent carries +kShift so that P' = 2^kShift P uses the format's range (max 448), and the running max
   // may lag the true one by kThr = 2 only (P' <= 2^8); 16-bit P: lag 2^8 (bf16 / fp32-range exponent, f16 P <= 256 < 65504)
   constexpr float kShift = F8 ? 6.f : 0.f;
@@ -216,10 +217,12 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
   // items: the producer then prefetches the next item's Q/K/V and the MMA warps start its first S while the softmax warps
   // are still in the epilogue of the previous one, so the per-item prologue / epilogue latency is hidden.
   const int nqb = (p.Sq + 255) / 256;
-  const int n_items = nqb * p.H * p.nbatch;
-  struct Item { int r0, h, b, hk, nt, j_lo, n, lid; };
+  const int n_items = nqb * p.H * p.nbatch * (WIDE ? 2 : 1);
+  struct Item { int r0, h, b, hk, nt, j_lo, n, lid, half; };
   auto decode = [&](int w) {
     Item it;
+    it.half = 0;
+    if constexpr (WIDE) { it.half = w & 1; w >>= 1; }           // the two O halves of a query block run next to each other
     const int x = w % nqb, hb = w / nqb;
     const int qblk = p.causal ? nqb - 1 - x : x;                                     // heavy blocks first
     it.h = hb % p.H; it.b = hb / p.H;
@@ -282,9 +285,9 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         const int r0 = im.r0, h = im.h, b = im.b, hk = im.hk, nt = im.nt, n = im.n;
         if (n == 0) continue;
         // one Q / K tile (or one hi / lo half of a split tile); the caller has armed the barrier with the bytes
-        auto load_half = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int row, int head) {
+        auto load_half = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int row, int head, int col0 = 0) {
 #pragma unroll
-          for (int c = 0; c < C::kQChunks; ++c) tma_load_4d(dst + c * CHB, m, bar, c * (I8 ? 128 : 64), row, head, b);
+          for (int c = 0; c < C::kQChunks; ++c) tma_load_4d(dst + c * CHB, m, bar, col0 + c * (I8 ? 128 : 64), row, head, b);
         };
         auto load_q = [&](int t2) {
           if constexpr (I4) {              // packed tile into the raw Q buffer; the converter warp unpacks it into sQ
@@ -298,8 +301,9 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           mbar_arrive_expect_tx(q_full(t2), QT);
           load_half(sQ + t2 * QT, &p.tq, q_full(t2), r0 + t2 * 128, h);
           if constexpr (SPLIT) load_half(sQ + t2 * QT + HT, &p.tq2, q_full(t2), r0 + t2 * 128, h);
+          if constexpr (WIDE) load_half(sQ + t2 * QT + HT, &p.tq, q_full(t2), r0 + t2 * 128, h, 128);
         };
-        auto load_k = [&](const CUtensorMap* m, int row) {
+        auto load_k = [&](const CUtensorMap* m, int row, int col0 = 0) {
           if constexpr (I4) {              // packed tile into the raw ring; its operand stage (ring index kvi) is the converter's
             const int rs = kr % NR;
             mbar_wait(raw_empty(rs), ((kr / NR) & 1) ^ 1);
@@ -311,15 +315,15 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           const int s = kvi % NS;
           mbar_wait(kv_empty(s), ((kvi / NS) & 1) ^ 1);
           mbar_arrive_expect_tx(kv_full(s), HT);
-          load_half(sKV + s * STG, m, kv_full(s), row, hk);
+          load_half(sKV + s * STG, m, kv_full(s), row, hk, col0);
           ++kvi;
         };
-        auto load_v = [&](const CUtensorMap* m, int row) {
+        auto load_v = [&](const CUtensorMap* m, int row, int col0 = 0) {
           const int s = kvi % NS;
           mbar_wait(kv_empty(s), ((kvi / NS) & 1) ^ 1);
           mbar_arrive_expect_tx(kv_full(s), VT);
 #pragma unroll
-          for (int c = 0; c < C::kVChunks; ++c) tma_load_4d(sKV + s * STG + c * CHB, m, kv_full(s), c * 64, row, hk, b);
+          for (int c = 0; c < C::kVChunks; ++c) tma_load_4d(sKV + s * STG + c * CHB, m, kv_full(s), col0 + c * 64, row, hk, b);
           ++kvi;
         };
         load_q(0);
@@ -328,11 +332,12 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           const int row = (tile_of(im, it) & (kTileNoMask - 1)) * 128;
           if constexpr (SPLIT) load_k(&p.tk2, row);         // K_lo first: its stage is released after the first MMA group
           load_k(&p.tk, row);
+          if constexpr (WIDE) load_k(&p.tk, row, 128);      // K_b: head dims 128 .. 255
           if (it == 0 && nt == 2) {
             load_q(1);
             ++qc[1];
           }
-          load_v(&p.tv, row);
+          load_v(&p.tv, row, WIDE ? 128 * im.half : 0);
           if constexpr (SPLIT) load_v(&p.tv2, row);         // V_lo last: only the closing MMA group of the step reads it
         }
       }
@@ -402,6 +407,14 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
             issue_qk(q_lo + (HT >> 4), idx + 1, true);   // Q_lo K_hi^T
             tc_commit_u(s_full(t));
             release(idx + 1);
+          } else if constexpr (WIDE) {
+            issue_qk(q_lo, idx, false);                  // Q_a K_a^T
+            release(idx);
+            wait_full(idx + 1);
+            tc_fence_after();
+            issue_qk(q_lo + (HT >> 4), idx + 1, true);   // + Q_b K_b^T
+            tc_commit_u(s_full(t));
+            release(idx + 1);
           } else {
             issue_s(idx);
             tc_commit_u(s_full(t));
@@ -414,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         do_s(kvbase);
         if (n == 1) tc_commit_u(q_empty(t));
         for (int it = 0; it < n; ++it) {
-          const int vi = kvbase + SPS * it + SPS / 2, ki = kvbase + SPS * (it + 1);
+          const int vi = kvbase + SPS * it + (SPS == 2 ? 1 : 2), ki = kvbase + SPS * (it + 1);
           wait_full(vi);
           if (TR && tr && it < 64) tr[it * 16 + 13] = clock64();
 #pragma unroll
@@ -704,7 +717,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       if constexpr (F8) { if (p.vs) inv = (l > 0.f ? 1.f / l : 0.f) * __ldg(p.vs + (size_t)b * p.Hkv + hk); }     // per-(b, head) scale of the e4m3 V
       if constexpr (SPLIT) inv *= __ldg(p.vs);
       const bool live = r < p.Sq && !p.debug_skip_store;
-      const size_t orow = (size_t)b * p.o_sb + (size_t)h * p.o_sh + (size_t)r * p.o_ss;
+      const size_t orow = (size_t)b * p.o_sb + (size_t)h * p.o_sh + (size_t)r * p.o_ss + (WIDE ? 128 * im.half : 0);   // wide: this CTA's half of O
       const size_t lrow = ((size_t)b * p.H + h) * p.lse_sh + r;
       float l_out = l > 0.f ? m + log2f(l) - kShift : -CUDART_INF_F;
       // accumulate mode (ring attention): the partial of this launch is merged in place with the (O, L) already there,
@@ -818,17 +831,17 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           if (p.o_dtype == kF32) {
 #pragma unroll
             for (int ch = 0; ch < D / 32; ++ch)
-              tma_store_4d(&p.to, base + (uint32_t)(t * (D / 32) + ch) * (128u * 128u), ch * 32, r0 + t * 128, h, b);
+              tma_store_4d(&p.to, base + (uint32_t)(t * (D / 32) + ch) * (128u * 128u), ch * 32 + (WIDE ? 128 * im.half : 0), r0 + t * 128, h, b);
           } else {
 #pragma unroll
             for (int ch = 0; ch < D / 64; ++ch)
-              tma_store_4d(&p.to, base + (uint32_t)(t * (D / 64) + ch) * (128u * 128u), ch * 64, r0 + t * 128, h, b);
+              tma_store_4d(&p.to, base + (uint32_t)(t * (D / 64) + ch) * (128u * 128u), ch * 64 + (WIDE ? 128 * im.half : 0), r0 + t * 128, h, b);
           }
           bulk_commit();
           bulk_wait_read();           // the CTA may exit (and free its shared memory) once the TMA has read the tile
         }
       }
-      if (live && p.lse) p.lse[lrow] = l_out;
+      if (live && p.lse && (!WIDE || im.half == 0)) p.lse[lrow] = l_out;
       if (TR && ct && w == (int)blockIdx.x) { ct[5] = globaltimer_ns(); ct[8] = clock64(); }
     }
     }   // items
@@ -1138,7 +1151,8 @@ cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm_in, int D, int mode, cud
   FwdTcParams prm = prm_in;
   prm.nbatch = B;
   ptx::watchdog_bind();
-  const long long items = (long long)((prm.Sq + 255) / 256) * prm.H * B;
+  const bool wide = mode == kFwdWideF16 || mode == kFwdWideBF16;
+  const long long items = (long long)((prm.Sq + 255) / 256) * prm.H * B * (wide ? 2 : 1);
   if (items <= 0 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
   // Persistent grid (one CTA per SM striding over the items) when every item costs the same -- no causal / window
   // imbalance that the hardware's dynamic CTA dispatch handles better -- and there is more than one item per SM.
@@ -1156,6 +1170,16 @@ cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm_in, int D, int mode, cud
     }
     if (prm.mask) return poly ? launch_masked_k<128, kFwdI4F8, 3>(prm, grid, st) : launch_masked_k<128, kFwdI4F8, 0>(prm, grid, st);
     return poly ? launch_k<128, kFwdI4F8, 3>(prm, grid, st) : launch_k<128, kFwdI4F8, 0>(prm, grid, st);
+  }
+  if (mode == kFwdWideF16 || mode == kFwdWideBF16) {      // D is the head dim of the problem (256); the kernel's tiles are 128 wide
+    if (D != 256) return cudaErrorInvalidValue;
+    const bool poly = poly_setting() > 0;
+    if (mode == kFwdWideBF16) {
+      if (prm.mask) return poly ? launch_masked_k<128, kFwdWideBF16, 3>(prm, grid, st) : launch_masked_k<128, kFwdWideBF16, 0>(prm, grid, st);
+      return poly ? launch_k<128, kFwdWideBF16, 3>(prm, grid, st) : launch_k<128, kFwdWideBF16, 0>(prm, grid, st);
+    }
+    if (prm.mask) return poly ? launch_masked_k<128, kFwdWideF16, 3>(prm, grid, st) : launch_masked_k<128, kFwdWideF16, 0>(prm, grid, st);
+    return poly ? launch_k<128, kFwdWideF16, 3>(prm, grid, st) : launch_k<128, kFwdWideF16, 0>(prm, grid, st);
   }
   if (mode == kFwdSplit) {        // exact exp2 only (the polynomial's 8.6e-5 would show at fp32 tolerances)
     if (D != 128) return cudaErrorInvalidValue;
@@ -1249,7 +1273,7 @@ void fwd_tc_set_out_map(FwdTcParams& prm, const AttnParams& p) {
 bool fwd_tc_eligible(const AttnParams& p) {
   if (getenv("MFA_DISABLE_TC")) return false;
   if (p.in_dtype != kBF16 && p.in_dtype != kF16) return false;
-  if (p.D != 64 && p.D != 128) return false;
+  if (p.D != 64 && p.D != 128 && !(p.D == 256 && !p.accumulate)) return false;
   if (!fwd_tc_mask_ok(p)) return false;
   if (!(p.scale > 0.f) || p.Sq <= 0 || p.Skv <= 0 || p.B <= 0 || p.H <= 0 || p.Hkv <= 0 || p.H % p.Hkv) return false;
   if (p.B > 65535 || p.H > 65535) return false;
@@ -1281,6 +1305,12 @@ cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st) {
   fwd_tc_set_mask(prm, p);
   if (cudaError_t me = fwd_tc_build_mask_tiles(prm, p, st); me != cudaSuccess) return me;
   const bool bf = p.in_dtype == kBF16;
+  if (p.D == 256) {
+    cudaError_t e = launch_fwd_tc_kernel(prm, p.D, bf ? kFwdWideBF16 : kFwdWideF16, st, p.B);
+    g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d256_mask" : "fwd_tc_fp16_d256_mask") : (bf ? "fwd_tc_bf16_d256" : "fwd_tc_fp16_d256");
+    ++g_launch_count;
+    return e;
+  }
   cudaError_t e = launch_fwd_tc_kernel(prm, p.D, bf ? kFwdBF16 : kFwdF16, st, p.B);
   if (p.D == 128) g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d128_mask" : "fwd_tc_fp16_d128_mask") : (bf ? "fwd_tc_bf16_d128" : "fwd_tc_fp16_d128");
   else g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d64_mask" : "fwd_tc_fp16_d64_mask") : (bf ? "fwd_tc_bf16_d64" : "fwd_tc_fp16_d64");

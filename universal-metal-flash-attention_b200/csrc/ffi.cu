@@ -41,7 +41,7 @@ void note_simt_route(const char* what, const AttnParams& p) {
   said[i] = true;
   const char* dt[] = {"fp16", "bf16", "fp32", "int8", "int4"};
   fprintf(stderr, "[mfa] %s of B=%d H=%d Sq=%d Skv=%d D=%d (%s operands) runs on the exact SIMT kernels, not the tensor pipe: "
-          "tensor-core routes need head_dim 64/128 (fp32 / int8 / int4: 128), unit stride along D, masks with unit key stride, "
+          "tensor-core routes need head_dim 64/128/256 forward, 64/128 backward (fp32 / int8 / int4: 128), unit stride along D, masks with unit key stride, "
           "no transposed operands\n", what, p.B, p.H, p.Sq, p.Skv, p.D, (p.in_dtype >= 0 && p.in_dtype <= 4) ? dt[p.in_dtype] : "?");
 }
 
@@ -401,7 +401,7 @@ bool forward_pipeline_ok(const FwdArgs& a, int o_dtype) {
   if (a.tq || a.tk || a.tv || a.to) return false;
   if (a.mask.type != MFA_MASK_TYPE_NONE && a.mask.ptr && a.mask.bytes) return false;
   if (a.in_dtype != kBF16 && a.in_dtype != kF16) return false;
-  if (a.D != 64 && a.D != 128) return false;
+  if (a.D != 64 && a.D != 128 && a.D != 256) return false;
   (void)o_dtype;
   const size_t per_head = ((size_t)a.Sq + 2 * (size_t)a.Skv) * a.D * 2;
   return (size_t)a.B * a.H * per_head >= 2 * pipeline_chunk_bytes();     // small problems: one shot is as fast

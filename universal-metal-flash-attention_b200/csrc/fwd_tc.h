@@ -10,7 +10,10 @@ namespace mfa {
 
 // I8: int8 Q K^T + bf16 P V; I8F8: int8 Q K^T + e4m3 P V; Split: fp32 operands as scaled fp16 (hi, lo) pairs, three MMAs per product
 // I4 / I4F8: as I8 / I8F8 with Q and K delivered as packed int4 and unpacked in shared memory (tq / tk map the packed bytes)
-enum FwdMode : int { kFwdF16 = 0, kFwdBF16 = 1, kFwdI8 = 2, kFwdI8F8 = 3, kFwdSplit = 4, kFwdI4 = 5, kFwdI4F8 = 6 };
+// WideF16 / WideBF16: head_dim 256 as two 128-column halves -- a CTA computes S over all 256 dims (two MMA groups) and ONE half of O
+// (the TMEM budget is 2 tiles x (S 128 + O 128) columns), so the grid doubles and Q K^T runs twice
+enum FwdMode : int { kFwdF16 = 0, kFwdBF16 = 1, kFwdI8 = 2, kFwdI8F8 = 3, kFwdSplit = 4, kFwdI4 = 5, kFwdI4F8 = 6,
+                     kFwdWideF16 = 7, kFwdWideBF16 = 8 };
 
 struct FwdTcParams {
   CUtensorMap tq, tk, tv;
