@@ -370,3 +370,13 @@ def test_tc_d256_external_mask(ctx):
     assert ctx.last_kernel == "fwd_tc_bf16_d256_mask", ctx.last_kernel
     ref, lref = O.attention_forward(qv, kv, vv, mask=m)
     assert rel_max(out, ref) < 2e-2 and np.abs(lse - lref).max() < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Head dims that are not 64 / 128 / 256 (the reference's tile table covers any D, AttentionDescriptor+Parameters.swift:133-153):
+# every multiple of 8 runs on the next kernel width, TMA zero-fills the missing columns on loads and clips them on stores.
+@pytest.mark.parametrize("D", [8, 40, 72, 80, 96, 112, 160, 192, 224])
+def test_tc_padded_head_dims(ctx, D):
+    run_case(ctx, 2, 2, 300, 777, D, "bf16", seed=D)
+    run_case(ctx, 1, 2, 512, 512, D, "fp16", seed=D + 1, causal=True)
+    assert ctx.last_kernel.startswith("fwd_tc_fp16_d"), ctx.last_kernel

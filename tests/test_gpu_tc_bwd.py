@@ -182,3 +182,10 @@ def test_bwd_tc_mask_tile_skipping(ctx, kind, causal, monkeypatch):
     monkeypatch.setenv("MFA_DISABLE_MASK_SKIP", "1")
     dq2, dk2, dv2, _ = umfa.flash_attention_backward(ctx, ga, qa, ka, va, o_ref, l_ref, input_precision="bf16", attn_mask=m, causal=causal)
     assert rel_max(dq, dq2) < 1e-5 and rel_max(dk, dk2) < 1e-5 and rel_max(dv, dv2) < 1e-5
+
+
+@pytest.mark.parametrize("D", [40, 80, 96, 112])
+def test_bwd_tc_padded_head_dims(ctx, D):
+    """multiples of 8 other than 64 / 128 run on the next kernel width (TMA zero-fill in, clipped gradient stores out)"""
+    run_case(ctx, 1, 2, 384, 512, D, "bf16", causal=True, seed=D)
+    assert ctx.last_kernel.startswith("bwd_tc_"), ctx.last_kernel

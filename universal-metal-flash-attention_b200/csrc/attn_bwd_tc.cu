@@ -791,7 +791,10 @@ bool bwd_tc_eligible(const AttnParams& p) {
   if (getenv("MFA_DISABLE_TC") || getenv("MFA_DISABLE_TC_BWD")) return false;
   if (p.in_dtype != kBF16 && p.in_dtype != kF16) return false;
   if (p.do_dtype != p.in_dtype) return false;
-  if (p.D != 64 && p.D != 128) return false;
+  // head dims 64 / 128 as they are; other multiples of 8 up to 128 on the next kernel width: TMA zero-fills the missing columns
+  // of Q / K / V / dO and clips the gradient stores, so those need the TMA-store epilogues
+  if (p.D < 8 || p.D > 128 || (p.D & 7)) return false;
+  if (p.D != 64 && p.D != 128 && (getenv("MFA_DISABLE_TMA_STORE") || getenv("MFA_DISABLE_TC_PADDED_D"))) return false;
   if (p.mask_kind != kMaskNone && p.mask && (p.mask_sk != 1 || getenv("MFA_DISABLE_TC_MASK"))) return false;
   if (p.Sq <= 0 || p.Skv <= 0 || p.B <= 0 || p.H <= 0 || p.Hkv <= 0 || p.H % p.Hkv) return false;
   if (p.B > 65535 || p.H > 65535) return false;
@@ -869,10 +872,12 @@ cudaError_t launch_bwd_tc(const AttnParams& p, cudaStream_t st) {
   }
   const bool want_dq = p.dq != nullptr, want_dkv = p.dk != nullptr && p.dv != nullptr;
   const bool bf = p.in_dtype == kBF16;
-  if (p.D == 128) e = bf ? launch_bwd<128, true>(prm, p.B, want_dq, want_dkv, st) : launch_bwd<128, false>(prm, p.B, want_dq, want_dkv, st);
+  const int Dk = p.D <= 64 ? 64 : 128;
+  if (Dk != p.D && !prm.g_tma) return cudaErrorNotSupported;
+  if (Dk == 128) e = bf ? launch_bwd<128, true>(prm, p.B, want_dq, want_dkv, st) : launch_bwd<128, false>(prm, p.B, want_dq, want_dkv, st);
   else e = bf ? launch_bwd<64, true>(prm, p.B, want_dq, want_dkv, st) : launch_bwd<64, false>(prm, p.B, want_dq, want_dkv, st);
-  if (prm.mask) g_last_kernel = p.D == 128 ? (bf ? "bwd_tc_bf16_d128_mask" : "bwd_tc_fp16_d128_mask") : (bf ? "bwd_tc_bf16_d64_mask" : "bwd_tc_fp16_d64_mask");
-  else g_last_kernel = p.D == 128 ? (bf ? "bwd_tc_bf16_d128" : "bwd_tc_fp16_d128") : (bf ? "bwd_tc_bf16_d64" : "bwd_tc_fp16_d64");
+  if (prm.mask) g_last_kernel = Dk == 128 ? (bf ? "bwd_tc_bf16_d128_mask" : "bwd_tc_fp16_d128_mask") : (bf ? "bwd_tc_bf16_d64_mask" : "bwd_tc_fp16_d64_mask");
+  else g_last_kernel = Dk == 128 ? (bf ? "bwd_tc_bf16_d128" : "bwd_tc_fp16_d128") : (bf ? "bwd_tc_bf16_d64" : "bwd_tc_fp16_d64");
   return e;
 }
 

@@ -1273,7 +1273,17 @@ void fwd_tc_set_out_map(FwdTcParams& prm, const AttnParams& p) {
 bool fwd_tc_eligible(const AttnParams& p) {
   if (getenv("MFA_DISABLE_TC")) return false;
   if (p.in_dtype != kBF16 && p.in_dtype != kF16) return false;
-  if (p.D != 64 && p.D != 128 && !(p.D == 256 && !p.accumulate)) return false;
+  // head dims 64 / 128 / 256 run as they are; any other multiple of 8 up to 256 runs on the next kernel width with the missing
+  // columns zero-filled by TMA on the way in (tensor extent < box extent) and clipped by the TMA store on the way out -- so it
+  // needs the TMA-store epilogue (checked below) and cannot use the accumulate mode
+  if (p.D < 8 || p.D > 256 || (p.D & 7)) return false;
+  const bool native_d = p.D == 64 || p.D == 128 || p.D == 256;
+  if ((!native_d || p.D == 256) && p.accumulate) return false;
+  if (!native_d) {
+    if (getenv("MFA_DISABLE_TMA_STORE") || getenv("MFA_FWD_PERSIST") || getenv("MFA_DISABLE_TC_PADDED_D")) return false;
+    if (p.o_dtype != kF32 && p.o_dtype != kBF16 && p.o_dtype != kF16) return false;
+    if (!tc::view_ok(p.o, p.H, p.B, dtype_bytes(p.o_dtype))) return false;
+  }
   if (!fwd_tc_mask_ok(p)) return false;
   if (!(p.scale > 0.f) || p.Sq <= 0 || p.Skv <= 0 || p.B <= 0 || p.H <= 0 || p.Hkv <= 0 || p.H % p.Hkv) return false;
   if (p.B > 65535 || p.H > 65535) return false;
@@ -1305,14 +1315,16 @@ cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st) {
   fwd_tc_set_mask(prm, p);
   if (cudaError_t me = fwd_tc_build_mask_tiles(prm, p, st); me != cudaSuccess) return me;
   const bool bf = p.in_dtype == kBF16;
-  if (p.D == 256) {
-    cudaError_t e = launch_fwd_tc_kernel(prm, p.D, bf ? kFwdWideBF16 : kFwdWideF16, st, p.B);
+  const int Dk = p.D <= 64 ? 64 : p.D <= 128 ? 128 : 256;          // kernel width (zero-padded head dims: see fwd_tc_eligible)
+  if (Dk != p.D && !prm.o_tma) return cudaErrorNotSupported;
+  if (Dk == 256) {
+    cudaError_t e = launch_fwd_tc_kernel(prm, Dk, bf ? kFwdWideBF16 : kFwdWideF16, st, p.B);
     g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d256_mask" : "fwd_tc_fp16_d256_mask") : (bf ? "fwd_tc_bf16_d256" : "fwd_tc_fp16_d256");
     ++g_launch_count;
     return e;
   }
-  cudaError_t e = launch_fwd_tc_kernel(prm, p.D, bf ? kFwdBF16 : kFwdF16, st, p.B);
-  if (p.D == 128) g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d128_mask" : "fwd_tc_fp16_d128_mask") : (bf ? "fwd_tc_bf16_d128" : "fwd_tc_fp16_d128");
+  cudaError_t e = launch_fwd_tc_kernel(prm, Dk, bf ? kFwdBF16 : kFwdF16, st, p.B);
+  if (Dk == 128) g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d128_mask" : "fwd_tc_fp16_d128_mask") : (bf ? "fwd_tc_bf16_d128" : "fwd_tc_fp16_d128");
   else g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d64_mask" : "fwd_tc_fp16_d64_mask") : (bf ? "fwd_tc_bf16_d64" : "fwd_tc_fp16_d64");
   ++g_launch_count;
   return e;

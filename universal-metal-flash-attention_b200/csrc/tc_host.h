@@ -41,8 +41,9 @@ inline bool make_map(CUtensorMap* out, const TensorView& t, int dtype, int B, in
   cuuint64_t st[3] = {(cuuint64_t)t.ss * eb, (cuuint64_t)t.sh * eb, (cuuint64_t)t.sb * eb};
   if (Hn == 1) st[1] = st[0] * (cuuint64_t)S;
   if (B == 1) st[2] = st[1] * (cuuint64_t)Hn;
+  // the box is always 128 bytes wide (one swizzle span): a head dim that is not a multiple of it leaves part of the last box out of
+  // bounds, which TMA zero-fills on loads and clips on stores
   cuuint32_t box[4] = {(cuuint32_t)(128 / eb), (cuuint32_t)box_rows, 1, 1};
-  if (box[0] > (cuuint32_t)D) box[0] = (cuuint32_t)D;
   cuuint32_t es[4] = {1, 1, 1, 1};
   const CUtensorMapDataType ty = dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                : dtype == kF16  ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
