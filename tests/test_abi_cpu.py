@@ -223,3 +223,23 @@ int main(void) {
                     "-lMFAFFI", "-Wl,-rpath," + lib_dir], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "c consumer ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_headline_forward_kernels_do_not_spill():
+    """The unmasked bf16 / fp16 / fp32-split / int8 forward instantiations must keep O and S in registers: a stack frame in them
+    cost 6 % of the headline number once (an epilogue branch indexed the O registers dynamically; round 2)."""
+    import re
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    obj = os.path.join(ROOT, "universal-metal-flash-attention_b200", "lib", "attn_fwd_tc.o")
+    if not os.path.exists(cuobjdump) or not os.path.exists(obj):
+        pytest.skip("cuobjdump or the object file is not available")
+    out = subprocess.run([cuobjdump, "-res-usage", obj], capture_output=True, text=True).stdout
+    seen = 0
+    for m in re.finditer(r"Function (\S*fwd_tc_kernelILi(\d+)ELi(\d+)ELi(\d+)ELb0ELb0E\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
+        mode, stack = int(m.group(3)), int(m.group(6))
+        if mode in (0, 1, 3, 4, 8):          # f16, bf16, int8 + e4m3, fp32 split, wide bf16
+            seen += 1
+            assert stack == 0, (m.group(1), stack)
+    assert seen >= 8

@@ -127,3 +127,10 @@ def test_fp32_tc_strided_bshd_view(ctx):
     assert ctx.last_kernel == "fwd_tc_fp32split_d128", ctx.last_kernel
     ref, _ = O.attention_forward(*(np.ascontiguousarray(x.transpose(0, 2, 1, 3)) for x in (q, k, v)))
     assert rel_max(out.transpose(0, 2, 1, 3), ref) < TOL
+
+
+@pytest.mark.parametrize("D", [64, 80, 32, 120])
+def test_fp32_tc_head_dims_below_128(ctx, D):
+    """fp32 at other head dims (multiples of 8): same kernel, the (hi, lo) scratch keeps the true head dim and TMA zero-fills"""
+    check(ctx, rand((2, 2, 300, D), D), rand((2, 2, 777, D), D + 1), rand((2, 2, 777, D), D + 2))
+    check(ctx, rand((1, 2, 1536, D), D + 3), rand((1, 2, 1536, D), D + 4), rand((1, 2, 1536, D), D + 5), causal=True)   # two key slices

@@ -380,3 +380,10 @@ def test_tc_padded_head_dims(ctx, D):
     run_case(ctx, 2, 2, 300, 777, D, "bf16", seed=D)
     run_case(ctx, 1, 2, 512, 512, D, "fp16", seed=D + 1, causal=True)
     assert ctx.last_kernel.startswith("fwd_tc_fp16_d"), ctx.last_kernel
+
+
+@pytest.mark.parametrize("D", [80, 160])
+def test_tc_padded_head_dims_direct_store_epilogue(ctx, D, monkeypatch):
+    """without the TMA-store epilogue the row-owner threads stop at the true head dim"""
+    monkeypatch.setenv("MFA_DISABLE_TMA_STORE", "1")
+    run_case(ctx, 1, 2, 300, 400, D, "bf16", seed=D)

@@ -153,7 +153,8 @@ unsigned split_grid(unsigned long long n4) {
 // fp32 operands, head_dim 128, unit stride along D with 16-byte aligned rows; masks as for the 16-bit kernel
 bool fwd_split_eligible(const AttnParams& p) {
   if (getenv("MFA_DISABLE_TC") || getenv("MFA_DISABLE_TC32")) return false;
-  if (p.in_dtype != kF32 || p.D != 128 || p.accumulate || !fwd_tc_mask_ok(p)) return false;
+  // head dims below 128 (multiples of 8) ride the same kernel: the (hi, lo) scratch tensors keep the true head dim, TMA zero-fills
+  if (p.in_dtype != kF32 || p.D < 8 || p.D > 128 || (p.D & 7) || p.accumulate || !fwd_tc_mask_ok(p)) return false;
   if (!(p.scale > 0.f) || p.Sq <= 0 || p.Skv <= 0 || p.B <= 0 || p.H <= 0 || p.Hkv <= 0 || p.H % p.Hkv) return false;
   if (p.B > 65535 || p.H > 65535) return false;
   if (!src_ok(p.q, p.H, p.B) || !src_ok(p.k, p.Hkv, p.B) || !src_ok(p.v, p.Hkv, p.B)) return false;
@@ -221,6 +222,7 @@ cudaError_t launch_fwd_split(const AttnParams& p, void* scratch, cudaStream_t st
   prm.lse_sh = p.lse_sh > 0 ? p.lse_sh : p.Sq;
   prm.accumulate = 0;
   prm.H = p.H; prm.Hkv = p.Hkv; prm.Sq = p.Sq; prm.Skv = p.Skv;
+  prm.dv = p.D;
   prm.c = p.scale * kLog2e;
   prm.causal = p.causal; prm.window = p.window;
   prm.pingpong = fwd_tc_pingpong();
@@ -235,7 +237,7 @@ cudaError_t launch_fwd_split(const AttnParams& p, void* scratch, cudaStream_t st
   const int n_slices = (kSliceKeys > 0 && p.o_dtype == kF32 && !p.accumulate && slice_lse) ? (p.Skv + kSliceKeys - 1) / kSliceKeys : 1;
   if (n_slices <= 1) {
     if ((e = fwd_tc_build_mask_tiles(prm, p, st)) != cudaSuccess) return e;
-    e = launch_fwd_tc_kernel(prm, p.D, kFwdSplit, st, p.B);
+    e = launch_fwd_tc_kernel(prm, 128, kFwdSplit, st, p.B);
     if (e != cudaSuccess) return e;
     ++g_launch_count;
   } else {
@@ -246,7 +248,7 @@ cudaError_t launch_fwd_split(const AttnParams& p, void* scratch, cudaStream_t st
       prm.kv_begin = i * kSliceKeys;
       prm.kv_end = min(p.Skv, (i + 1) * kSliceKeys);
       if (i == 1) { prm.accumulate = 1; prm.o_tma = 0; }
-      e = launch_fwd_tc_kernel(prm, p.D, kFwdSplit, st, p.B);
+      e = launch_fwd_tc_kernel(prm, 128, kFwdSplit, st, p.B);
       if (e != cudaSuccess) return e;
       ++g_launch_count;
     }

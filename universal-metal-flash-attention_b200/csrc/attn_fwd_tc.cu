@@ -717,6 +717,9 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       if constexpr (F8) { if (p.vs) inv = (l > 0.f ? 1.f / l : 0.f) * __ldg(p.vs + (size_t)b * p.Hkv + hk); }     // per-(b, head) scale of the e4m3 V
       if constexpr (SPLIT) inv *= __ldg(p.vs);
       const bool live = r < p.Sq && !p.debug_skip_store;
+      // zero-padded head dims: the columns past the true head dim p.dv are not written
+      const bool padded_d = p.dv > 0 && p.dv < (WIDE ? 256 : D);
+      const int dv_tile = p.dv - (WIDE ? 128 * im.half : 0);
       const size_t orow = (size_t)b * p.o_sb + (size_t)h * p.o_sh + (size_t)r * p.o_ss + (WIDE ? 128 * im.half : 0);   // wide: this CTA's half of O
       const size_t lrow = ((size_t)b * p.H + h) * p.lse_sh + r;
       float l_out = l > 0.f ? m + log2f(l) - kShift : -CUDART_INF_F;
@@ -779,6 +782,22 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
             const int unit = (ch & 1) * 4 + i;
             st_shared_v4(line + (uint32_t)((unit ^ (row & 7)) << 4), __uint_as_float(w[0]), __uint_as_float(w[1]),
                          __uint_as_float(w[2]), __uint_as_float(w[3]));
+          }
+        } else if (live && padded_d) {
+          // zero-padded head dim without the TMA-store epilogue (rare: accumulate mode, views TMA cannot describe): element-wise,
+          // stopping at the true head dim
+          const int nv = dv_tile - ch * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {         // fully unrolled: the registers of O must keep static indices
+            if (i >= nv) continue;
+            const float val = __uint_as_float(ou[i]) * inv;
+            if (p.o_dtype == kF32) {
+              float* dst = reinterpret_cast<float*>(p.o) + orow + ch * 32 + i;
+              *dst = acc_mode ? fmaf(*dst, c_old, val) : val;
+            } else {
+              uint16_t* dst = reinterpret_cast<uint16_t*>(p.o) + orow + ch * 32 + i;
+              *dst = (uint16_t)((p.o_dtype == kBF16 ? pack_bf16(val, 0.f) : pack_f16(val, 0.f)) & 0xffffu);
+            }
           }
         } else if (live) {
           if (p.o_dtype == kF32) {
@@ -1274,16 +1293,12 @@ bool fwd_tc_eligible(const AttnParams& p) {
   if (getenv("MFA_DISABLE_TC")) return false;
   if (p.in_dtype != kBF16 && p.in_dtype != kF16) return false;
   // head dims 64 / 128 / 256 run as they are; any other multiple of 8 up to 256 runs on the next kernel width with the missing
-  // columns zero-filled by TMA on the way in (tensor extent < box extent) and clipped by the TMA store on the way out -- so it
-  // needs the TMA-store epilogue (checked below) and cannot use the accumulate mode
+  // columns zero-filled by TMA on the way in (tensor extent < box extent) and left out on the way out (the TMA store clips
+  // them, the direct stores stop at FwdTcParams::dv)
   if (p.D < 8 || p.D > 256 || (p.D & 7)) return false;
   const bool native_d = p.D == 64 || p.D == 128 || p.D == 256;
-  if ((!native_d || p.D == 256) && p.accumulate) return false;
-  if (!native_d) {
-    if (getenv("MFA_DISABLE_TMA_STORE") || getenv("MFA_FWD_PERSIST") || getenv("MFA_DISABLE_TC_PADDED_D")) return false;
-    if (p.o_dtype != kF32 && p.o_dtype != kBF16 && p.o_dtype != kF16) return false;
-    if (!tc::view_ok(p.o, p.H, p.B, dtype_bytes(p.o_dtype))) return false;
-  }
+  if (p.D > 128 && p.accumulate) return false;
+  if (!native_d && getenv("MFA_DISABLE_TC_PADDED_D")) return false;
   if (!fwd_tc_mask_ok(p)) return false;
   if (!(p.scale > 0.f) || p.Sq <= 0 || p.Skv <= 0 || p.B <= 0 || p.H <= 0 || p.Hkv <= 0 || p.H % p.Hkv) return false;
   if (p.B > 65535 || p.H > 65535) return false;
@@ -1316,7 +1331,7 @@ cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st) {
   if (cudaError_t me = fwd_tc_build_mask_tiles(prm, p, st); me != cudaSuccess) return me;
   const bool bf = p.in_dtype == kBF16;
   const int Dk = p.D <= 64 ? 64 : p.D <= 128 ? 128 : 256;          // kernel width (zero-padded head dims: see fwd_tc_eligible)
-  if (Dk != p.D && !prm.o_tma) return cudaErrorNotSupported;
+  prm.dv = p.D;
   if (Dk == 256) {
     cudaError_t e = launch_fwd_tc_kernel(prm, Dk, bf ? kFwdWideBF16 : kFwdWideF16, st, p.B);
     g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d256_mask" : "fwd_tc_fp16_d256_mask") : (bf ? "fwd_tc_bf16_d256" : "fwd_tc_fp16_d256");

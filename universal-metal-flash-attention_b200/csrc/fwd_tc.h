@@ -27,6 +27,7 @@ struct FwdTcParams {
   int accumulate;          // merge this launch's partial (O, L) with what lse / o already hold (fp32 O, lse required)
   int o_dtype;
   int H, Hkv, Sq, Skv;
+  int dv;                  // true head dim when it is smaller than the kernel's tile width (0 = the full width): direct stores stop there
   int nbatch;              // set by launch_fwd_tc_kernel (work items = query blocks x H x nbatch)
   float c;                 // softmax_scale * log2(e)
   int causal, window;
