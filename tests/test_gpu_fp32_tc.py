@@ -134,3 +134,13 @@ def test_fp32_tc_head_dims_below_128(ctx, D):
     """fp32 at other head dims (multiples of 8): same kernel, the (hi, lo) scratch keeps the true head dim and TMA zero-fills"""
     check(ctx, rand((2, 2, 300, D), D), rand((2, 2, 777, D), D + 1), rand((2, 2, 777, D), D + 2))
     check(ctx, rand((1, 2, 1536, D), D + 3), rand((1, 2, 1536, D), D + 4), rand((1, 2, 1536, D), D + 5), causal=True)   # two key slices
+
+
+def test_fp32_tc_same_sign_values_long_keys(ctx):
+    """V >= 0 makes the O accumulator grow monotonically -- the worst case for the truncating accumulation of tcgen05.mma that the
+    1024-key slices bound (attn_fwd_split.cu); 4608 keys like config 2"""
+    rng = np.random.default_rng(33)
+    q, k = rand((1, 2, 512, 128), 34), rand((1, 2, 4608, 128), 35)
+    v = rng.random((1, 2, 4608, 128)).astype(np.float32) + 0.5
+    check(ctx, q, k, v)
+    check(ctx, q, k, -v, causal=False, softmax_scale=0.02)      # nearly uniform attention: every key contributes

@@ -36,8 +36,8 @@ int slice_keys() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MFA_FP32_SLICE_KEYS");
-    v = e ? atoi(e) : 1024;
-    if (v < 0 || (v & 127)) v = 1024;
+    v = e ? atoi(e) : 768;
+    if (v < 0 || (v & 127)) v = 768;
   }
   return v;
 }
@@ -231,8 +231,9 @@ cudaError_t launch_fwd_split(const AttnParams& p, void* scratch, cudaStream_t st
   fwd_tc_set_mask(prm, p);
   // Long key ranges run as slices of kSliceKeys keys, one launch each, merged in fp32 by the accumulate epilogue (the one ring
   // attention uses).  Why: tcgen05 adds every MMA into the TMEM accumulator with truncation, a bias of ~2^-24 of the accumulator
-  // per MMA; O collects 24 MMAs per KV step, so one launch over N keys carries ~N * 5.6e-9 relative error (measured 1.7e-5 at
-  // 4099 keys, 2.9e-5 at 4608) -- beyond the 1e-5 this path promises.  Slices of 1024 keys keep it at ~5e-6.
+  // per MMA; O collects 24 MMAs per KV step, so one launch over N keys carries a relative error of N * 4e-9 (zero-mean V) to
+  // N * 9e-9 (same-sign V, the accumulator grows monotonically): 1.7e-5 .. 4.2e-5 at 4608 keys -- beyond the 1e-5 this path
+  // promises.  Slices of 768 keys keep the worst case at ~7e-6 (2048: 1.7e-5, 1024: ~9e-6; tests/test_gpu_fp32_tc.py).
   const int kSliceKeys = slice_keys();
   const int n_slices = (kSliceKeys > 0 && p.o_dtype == kF32 && !p.accumulate && slice_lse) ? (p.Skv + kSliceKeys - 1) / kSliceKeys : 1;
   if (n_slices <= 1) {
