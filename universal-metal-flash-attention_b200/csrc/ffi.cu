@@ -41,7 +41,7 @@ void note_simt_route(const char* what, const AttnParams& p) {
   said[i] = true;
   const char* dt[] = {"fp16", "bf16", "fp32", "int8", "int4"};
   fprintf(stderr, "[mfa] %s of B=%d H=%d Sq=%d Skv=%d D=%d (%s operands) runs on the exact SIMT kernels, not the tensor pipe: "
-          "tensor-core routes need a head_dim that is a multiple of 8 (<= 256 forward, <= 128 backward; fp32 / int8 / int4: 128), unit stride along D, masks with unit key stride, "
+          "tensor-core routes need a head_dim that is a multiple of 8 (<= 256 forward, <= 128 backward and fp32; int8 / int4: 128), unit stride along D, masks with unit key stride, "
           "no transposed operands\n", what, p.B, p.H, p.Sq, p.Skv, p.D, (p.in_dtype >= 0 && p.in_dtype <= 4) ? dt[p.in_dtype] : "?");
 }
 
