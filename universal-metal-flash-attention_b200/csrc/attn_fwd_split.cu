@@ -31,7 +31,7 @@ namespace mfa {
 namespace {
 
 constexpr float kLog2e = 1.4426950408889634f;
-// keys per launch (see launch_fwd_split); MFA_FP32_SLICE_KEYS overrides it (a multiple of 128; 0 = one launch over all keys)
+// keys per accumulator lifetime (see launch_fwd_split); MFA_FP32_SLICE_KEYS overrides it (a multiple of 128; 0 = no flush)
 int slice_keys() {
   static int v = -1;
   if (v < 0) {
@@ -168,7 +168,9 @@ bool fwd_split_eligible(const AttnParams& p) {
 // scratch: (hi, lo) fp16 copies of Q, K, V + three abs-max words + three inverse scales
 size_t fwd_split_scratch_bytes(const AttnParams& p) {
   const size_t nq = (size_t)p.B * p.H * p.Sq * p.D, nkv = (size_t)p.B * p.Hkv * p.Skv * p.D;
-  return pad256(nq * 4) + 2 * pad256(nkv * 4) + 512 + (size_t)p.B * p.H * p.Sq * 4 + 256;
+  // + the running L of launch-wise slices, + the flush tiles of the in-kernel slices (128 KB per 256-row work item)
+  const size_t items = (size_t)((p.Sq + 255) / 256) * p.H * p.B;
+  return pad256(nq * 4) + 2 * pad256(nkv * 4) + 512 + pad256((size_t)p.B * p.H * p.Sq * 4) + items * 2 * 128 * 128 * 4 + 256;
 }
 
 cudaError_t launch_fwd_split(const AttnParams& p, void* scratch, cudaStream_t st) {
@@ -234,8 +236,16 @@ cudaError_t launch_fwd_split(const AttnParams& p, void* scratch, cudaStream_t st
   // per MMA; O collects 24 MMAs per KV step, so one launch over N keys carries a relative error of N * 4e-9 (zero-mean V) to
   // N * 9e-9 (same-sign V, the accumulator grows monotonically): 1.7e-5 .. 4.2e-5 at 4608 keys -- beyond the 1e-5 this path
   // promises.  Slices of 768 keys keep the worst case at ~7e-6 (2048: 1.7e-5, 1024: ~9e-6; tests/test_gpu_fp32_tc.py).
+  // Two ways to bound the accumulator's lifetime: the kernel hands O over to its fp32 output row every kSliceKeys / 128 steps
+  // (default: one launch, no re-read of Q, no extra prologues), or -- MFA_FP32_SLICE_LAUNCHES=1, the first implementation, kept
+  // for A/B -- one launch per slice merged by the accumulate epilogue.
   const int kSliceKeys = slice_keys();
-  const int n_slices = (kSliceKeys > 0 && p.o_dtype == kF32 && !p.accumulate && slice_lse) ? (p.Skv + kSliceKeys - 1) / kSliceKeys : 1;
+  const bool by_launch = getenv("MFA_FP32_SLICE_LAUNCHES") != nullptr;
+  if (!by_launch && kSliceKeys > 0 && !p.accumulate && p.Skv > kSliceKeys) {
+    prm.flush_steps = kSliceKeys / 128;
+    prm.flush_buf = reinterpret_cast<float*>(sc + pad256(nq * 4) + 2 * pad256(nkv * 4) + 512 + pad256((size_t)p.B * p.H * p.Sq * 4));
+  }
+  const int n_slices = (by_launch && kSliceKeys > 0 && p.o_dtype == kF32 && !p.accumulate && slice_lse) ? (p.Skv + kSliceKeys - 1) / kSliceKeys : 1;
   if (n_slices <= 1) {
     if ((e = fwd_tc_build_mask_tiles(prm, p, st)) != cudaSuccess) return e;
     e = launch_fwd_tc_kernel(prm, 128, kFwdSplit, st, p.B);

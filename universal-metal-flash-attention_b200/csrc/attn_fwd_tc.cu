@@ -388,6 +388,8 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
       }
     };
     int kvbase = 0, qc = 0, pc = 0;                // ring index at the start of the item; items / KV steps done by this tile
+    int oe = 0;                                    // o_empty phases consumed: one per O hand-over (flush or end of item)
+    const int F = SPLIT ? p.flush_steps : 0;       // fp32 split mode: O leaves TMEM every F steps (see the softmax warps)
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const Item im = decode(w);
       const int nt = im.nt, n = im.n;
@@ -433,11 +435,13 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
 #pragma unroll
           for (int part = 0; part < kParts; ++part) {
             mbar_wait(p_part(t, part), pc & 1);
-            // first P V of an item overwrites O: the epilogue of the previous item must have read it out of TMEM
-            if (part == 0 && it == 0 && qc > 0) mbar_wait(o_empty(t), (qc - 1) & 1);
+            // the first P V of an item (and, split mode, of a flush period) overwrites O: the softmax warps must have read the
+            // previous contents out of TMEM (epilogue of the previous item / flush) -- one o_empty phase per hand-over
+            const bool fresh = F > 0 ? (it % F == 0) : (it == 0);
+            if (part == 0 && fresh && (it > 0 || qc > 0)) { mbar_wait(o_empty(t), oe & 1); ++oe; }
             tc_fence_after();
             if (TR && tr && it < 64) tr[it * 16 + 8 + part] = clock64();
-            issue_o_part(vi, part, it > 0);
+            issue_o_part(vi, part, !fresh);
           }
           release(vi);
           if constexpr (SPLIT) {                         // closing group of the step: P_hi V_lo over all 128 keys
@@ -493,6 +497,9 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     // split mode: the operands were scaled by powers of two into fp16's range (qs / ks / vs point at the inverse scales)
     if constexpr (SPLIT) qsc = p.c * __ldg(p.qs) * __ldg(p.ks);
     float sb_row = p.s_bias;                               // offset of the widened integer score of this row (int4: set at step 0)
+    float m_flush = -CUDART_INF_F;                         // split mode: running max the flushed part of O (in global memory) is scaled by
+    int nflush = 0;
+    const int dv_row = p.dv > 0 ? p.dv : D;                // head dims this row holds in global memory
     const bool v_blocks = I8 && !F8 && vsp != nullptr;     // (e4m3 V carries one scale per (b, head): applied in the epilogue)
     const bool pingpong = nt == 2 && p.pingpong;
 
@@ -538,6 +545,39 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         mbar_wait(s_full(t), pc & 1);
         ++pc;
         tc_fence_after();
+        if constexpr (SPLIT) {
+          // fp32 split mode, every flush_steps steps: O leaves TMEM for an fp32 scratch tile in global memory,
+          //   O_flushed = O_flushed 2^(m_flush - m) + O_tmem,
+          // and the next P V starts a fresh accumulator.  tcgen05.mma adds into TMEM with truncation (~2^-24 of the accumulator per
+          // MMA, 24 MMAs per step): bounded accumulator lifetimes keep that bias at ~7e-6 of O; the sums across periods are
+          // round-to-nearest FMAs in registers.  S of this step being ready means the P V of the step before has retired.
+          if (p.flush_steps > 0 && it > 0 && it % p.flush_steps == 0) {
+            const float fs = (nflush > 0 && m_flush != -CUDART_INF_F) ? ex2(m_flush - m) : 0.f;
+            // the flushed part lives in a scratch tile private to this (item, tile), laid out [column / 4][row][4]: the 32 rows
+            // of a warp touch consecutive 16-byte units, so every access is a fully coalesced 512-byte request (row-major rows
+            // of the output would cost 32 sectors in 32 lines per request)
+            float4* fbuf = reinterpret_cast<float4*>(p.flush_buf) + ((size_t)w * 2 + t) * (size_t)(D / 4) * 128 + row;
+#pragma unroll
+            for (int ch = 0; ch < D / 32; ++ch) {
+              uint32_t ou[32];
+              tmem_ld_x32(tO + ch * 32, ou);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4* dst = fbuf + (size_t)(ch * 8 + i) * 128;
+                float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (nflush > 0) o4 = *dst;
+                *dst = make_float4(fmaf(o4.x, fs, __uint_as_float(ou[4 * i])), fmaf(o4.y, fs, __uint_as_float(ou[4 * i + 1])),
+                                   fmaf(o4.z, fs, __uint_as_float(ou[4 * i + 2])), fmaf(o4.w, fs, __uint_as_float(ou[4 * i + 3])));
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_empty(t));
+            m_flush = m;
+            ++nflush;
+          }
+        }
         if constexpr (I4) {
           // unsigned K nibbles: S_true = S_mma - 8 sum_d q[row][d]; the row constant joins the widening offset (both exact integers
           // in fp32).  The converter wrote the sums before it published Q, S of this item was computed from that Q.
@@ -753,6 +793,20 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(o_empty(t));
+        if constexpr (SPLIT) {
+          if (nflush > 0) {        // + what the flushes left in the scratch tile, brought to the final running max
+            const float fs = m_flush != -CUDART_INF_F ? ex2(m_flush - m) : 0.f;
+            const float4* src = reinterpret_cast<const float4*>(p.flush_buf) + ((size_t)w * 2 + t) * (size_t)(D / 4) * 128 + row;
+#pragma unroll
+            for (int i = 0; i < D / 4; ++i) {
+              const float4 g4 = src[(size_t)i * 128];
+              oall[4 * i] = __float_as_uint(fmaf(g4.x, fs, __uint_as_float(oall[4 * i])));
+              oall[4 * i + 1] = __float_as_uint(fmaf(g4.y, fs, __uint_as_float(oall[4 * i + 1])));
+              oall[4 * i + 2] = __float_as_uint(fmaf(g4.z, fs, __uint_as_float(oall[4 * i + 2])));
+              oall[4 * i + 3] = __float_as_uint(fmaf(g4.w, fs, __uint_as_float(oall[4 * i + 3])));
+            }
+          }
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < D; ++i) oall[i] = 0u;

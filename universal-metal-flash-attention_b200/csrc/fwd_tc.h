@@ -33,6 +33,8 @@ struct FwdTcParams {
   int causal, window;
   int kv_begin, kv_end;    // kv_end > 0: this launch attends to keys [kv_begin, kv_end) only (kv_begin a multiple of 128); the fp32
                            // split mode covers long key ranges in slices merged by the accumulate epilogue
+  int flush_steps;         // kFwdSplit: O leaves TMEM for an fp32 scratch tile every flush_steps KV steps (0 = never)
+  float* flush_buf;        // [work items][2 tiles][D / 4][128 rows][4] floats
   // kFwdI8 only: symmetric scales of the int8 codes (value = code * scale)
   const float* qs; const float* ks; const float* vs;   // per-block scale arrays (device) or nullptr
   float qs1, ks1, vs1;                                  // per-tensor scales when the array is null
