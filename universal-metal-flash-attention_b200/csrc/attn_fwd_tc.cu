@@ -589,24 +589,13 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
         }
         if (TR && tr) tr[0] = clock64();
         if (TR && ct && it == 0 && w == (int)blockIdx.x) ct[2] = globaltimer_ns();
-        // Reading 128 fp32 columns out of TMEM takes ~500 clk (64 B / clk per lane quarter) and sits on the per-tile chain.  Where
-        // nothing has to touch the scores before the row max (no int8 widening, no external mask) the read is split: the maximum
-        // of the first 64 columns is taken while the other 64 are still on their way.
-        constexpr bool kSplitLd = !I8 && !MASKED && !TR;
         uint32_t su[128];
         tmem_ld_x32(tS, su);
         tmem_ld_x32(tS + 32, su + 32);
-        if constexpr (kSplitLd) tmem_wait_ld();
         tmem_ld_x32(tS + 64, su + 64);
         tmem_ld_x32(tS + 96, su + 96);
-        float* s = reinterpret_cast<float*>(su);
-        float mxa = 0.f, mxb = 0.f;
-        if constexpr (kSplitLd) {
-          mxa = s[0]; mxb = s[1];
-#pragma unroll
-          for (int i = 2; i < 64; i += 2) { mxa = fmaxf(mxa, s[i]); mxb = fmaxf(mxb, s[i + 1]); }
-        }
         tmem_wait_ld();
+        float* s = reinterpret_cast<float*>(su);
         if (TR && tr) tr[1] = clock64();
         if (it + 1 < n) { jt_next = tile_of(im, it + 1); fetch_scales(jt_next); }
         if constexpr (I8) {
@@ -701,14 +690,11 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
 #pragma unroll
           for (int i = 0; i < 128; ++i) s[i] = (i < lo_i || i > hi_i) ? -CUDART_INF_F : s[i];
         }
-        float mxc = s[64], mxd = s[65];
-        if (!kSplitLd || any_mask) {           // (split read: the early maximum of the first half saw columns the range rule hides)
-          mxa = s[0]; mxb = s[1];
+        float mxa = s[0], mxb = s[1], mxc = s[64], mxd = s[65];
 #pragma unroll
-          for (int i = 2; i < 64; i += 2) { mxa = fmaxf(mxa, s[i]); mxb = fmaxf(mxb, s[i + 1]); }
+        for (int i = 2; i < 64; i += 2) {
+          mxa = fmaxf(mxa, s[i]); mxb = fmaxf(mxb, s[i + 1]); mxc = fmaxf(mxc, s[64 + i]); mxd = fmaxf(mxd, s[65 + i]);
         }
-#pragma unroll
-        for (int i = 2; i < 64; i += 2) { mxc = fmaxf(mxc, s[64 + i]); mxd = fmaxf(mxd, s[65 + i]); }
         // per-half maxima to scaled log2 units; a_h > 0 so the max commutes with the scaling (-inf if all masked)
         float mx;
         if constexpr (I8) mx = fmaxf(fmaf(fmaxf(mxa, mxb), a0, cb0), fmaf(fmaxf(mxc, mxd), a1, cb1));
