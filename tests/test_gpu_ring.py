@@ -249,3 +249,114 @@ def test_ring_native_world1(tmp_path):
              o_hi=o_hi.cpu().numpy(), l_hi=l_hi.cpu().numpy())
     runner.close()
     _check(tmp_path, 1, 1024)
+
+
+# ---------------------------------------------------------------------------------------------------- ring backward
+@pytest.mark.parametrize("world", [2, 4])
+def test_ring_backward_emulated_on_one_gpu(world):
+    """All ranks of a ring as threads on one GPU (the hops are queues between the threads): step_plan rectangles through the
+    tensor-core backward kernels with the forward's final O / L, dQ accumulated locally, dK / dV travelling with their K / V
+    and arriving home after `world` hops -- against the oracle's full causal backward."""
+    import queue
+    import threading
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "universal-metal-flash-attention_b200"))
+    import umfa
+    from umfa import ring
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(23)
+    B, H, D, N = 1, 2, 128, 256 * 2 * world
+    q, k, v, g = (O.round_bf16(rng.standard_normal((B, H, N, D)).astype(np.float32))[0] for _ in range(4))
+    o_ref, l_ref = O.attention_forward(q, k, v, causal=True)
+    rq, rk, rv, _ = O.attention_backward(q, k, v, g, causal=True)
+    ctx = umfa.MFAContext()
+    links = [queue.Queue() for _ in range(world)]           # links[r]: what rank r receives from rank r - 1
+
+    class Threaded(ring.CudaBackend):
+        def __init__(self, rank):
+            super().__init__(ctx, None, dev, "bf16")
+            self.rank = rank
+
+        def sendrecv(self, buf, dst, src):
+            torch.cuda.synchronize(dev)
+            links[dst].put(buf.clone())
+            return links[self.rank].get(timeout=120)
+
+    results, errors = {}, []
+
+    def run(r):
+        try:
+            with torch.cuda.device(dev):
+                be = Threaded(r)
+                sh16 = lambda x: tuple(_bf16_dev(c, dev) for c in ring.shard_sequence(x, r, world))
+                sh32 = lambda x: tuple(torch.from_numpy(np.ascontiguousarray(c, np.float32)).to(dev) for c in ring.shard_sequence(x, r, world))
+                results[r] = ring.ring_attention_backward(be, sh16(q), sh16(k), sh16(v), sh32(o_ref), sh32(l_ref), sh16(g), r, world,
+                                                          1.0 / np.sqrt(D))
+                torch.cuda.synchronize(dev)
+        except Exception as e:                                   # noqa: BLE001 -- reported by the main thread
+            errors.append((r, repr(e)))
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    c = N // (2 * world)
+    for r in range(world):
+        lo, hi = ring.chunk_ids(r, world)
+        for pair, ref, name in zip(results[r], (rq, rk, rv), ("dq", "dk", "dv")):
+            for part, cid in zip(pair, (lo, hi)):
+                want = ref[:, :, cid * c:(cid + 1) * c]
+                err = np.abs(part.cpu().numpy() - want).max() / np.abs(ref).max()
+                assert err < 2e-2, (r, name, cid, err)
+    ctx.close()
+
+
+def _run_rank_bwd(rank, world, port, N, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "universal-metal-flash-attention_b200"))
+    os.environ["MFA_CUDA_DEVICE"] = str(rank)
+    torch.cuda.set_device(rank)
+    import umfa
+    from umfa import ring
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dev = torch.device("cuda", rank)
+    rng = np.random.default_rng(29)
+    B, H, D = 1, 2, 128
+    q, k, v, g = (O.round_bf16(rng.standard_normal((B, H, N, D)).astype(np.float32))[0] for _ in range(4))
+    ctx = umfa.MFAContext()
+    be = ring.CudaBackend(ctx, dist, dev, "bf16")
+    sh16 = lambda x: tuple(_bf16_dev(c, dev) for c in ring.shard_sequence(x, rank, world))
+    (o_lo, l_lo), (o_hi, l_hi) = ring.ring_attention_forward(be, sh16(q), sh16(k), sh16(v), rank, world, 1.0 / np.sqrt(D))
+    dq, dk, dv = ring.ring_attention_backward(be, sh16(q), sh16(k), sh16(v), (o_lo, o_hi), (l_lo, l_hi), sh16(g), rank, world,
+                                              1.0 / np.sqrt(D))
+    torch.cuda.synchronize(dev)
+    np.savez(os.path.join(out_dir, f"bwd{rank}.npz"), **{f"{n}_{s}": t.cpu().numpy() for n, pair in (("dq", dq), ("dk", dk), ("dv", dv))
+                                                         for s, t in zip(("lo", "hi"), pair)})
+    dist.destroy_process_group()
+
+
+def test_ring_forward_backward_world2_nccl(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from umfa import ring
+    world, N = 2, 2048
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_run_rank_bwd, args=(world, port, N, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(29)
+    q, k, v, g = (O.round_bf16(rng.standard_normal((1, 2, N, 128)).astype(np.float32))[0] for _ in range(4))
+    rq, rk, rv, _ = O.attention_backward(q, k, v, g, causal=True)
+    c = N // (2 * world)
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"bwd{r}.npz"))
+        lo, hi = ring.chunk_ids(r, world)
+        for name, ref in (("dq", rq), ("dk", rk), ("dv", rv)):
+            for s_, cid in (("lo", lo), ("hi", hi)):
+                err = np.abs(got[f"{name}_{s_}"] - ref[:, :, cid * c:(cid + 1) * c]).max() / np.abs(ref).max()
+                assert err < 2e-2, (r, name, s_, err)

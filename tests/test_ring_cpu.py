@@ -126,3 +126,59 @@ def test_ring_attention_gloo_matches_single_device(tmp_path, world, N):
         np.testing.assert_allclose(got["o_hi"], o_ref[:, :, hi * c:(hi + 1) * c], rtol=2e-5, atol=2e-6)
         np.testing.assert_allclose(got["l_lo"], l_ref[:, :, lo * c:(lo + 1) * c], rtol=2e-5, atol=2e-5)
         np.testing.assert_allclose(got["l_hi"], l_ref[:, :, hi * c:(hi + 1) * c], rtol=2e-5, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------------- ring backward
+def test_block_backward_is_an_exact_partial_sum():
+    """the rectangle rule the ring backward rests on: with the final L and O, block gradients add up to the full backward"""
+    rng = np.random.default_rng(3)
+    q, k, v, g = (rng.standard_normal((1, 2, 48, 16)).astype(np.float32) for _ in range(4))
+    scale = 0.25
+    o, l = O.attention_forward(q, k, v, scale=scale)
+    rq, rk, rv, _ = O.attention_backward(q, k, v, g, scale=scale)
+    dq = np.zeros_like(q)
+    dk, dv = np.zeros_like(k), np.zeros_like(v)
+    for k0, k1 in ((0, 20), (20, 48)):
+        a, b, c = ring.block_backward_numpy(q, k[:, :, k0:k1], v[:, :, k0:k1], o, l, g, False, scale)
+        dq += a
+        dk[:, :, k0:k1] += b
+        dv[:, :, k0:k1] += c
+    for got, ref in ((dq, rq), (dk, rk), (dv, rv)):
+        np.testing.assert_allclose(got, ref, rtol=2e-4, atol=2e-5)
+
+
+def _worker_bwd(rank, world, port, N, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(9)
+        B, H, D = 1, 2, 32
+        q, k, v, g = (rng.standard_normal((B, H, N, D)).astype(np.float32) for _ in range(4))
+        scale = 1.0 / np.sqrt(D)
+        o, l = O.attention_forward(q, k, v, causal=True, scale=scale)
+        be = ring.HostBackend(None, dist)
+        sh = lambda x: ring.shard_sequence(np.asarray(x, np.float32), rank, world)
+        dq, dk, dv = ring.ring_attention_backward(be, sh(q), sh(k), sh(v), sh(o), sh(l), sh(g), rank, world, scale)
+        np.savez(os.path.join(out_dir, f"bwd{rank}.npz"), dq_lo=dq[0], dq_hi=dq[1], dk_lo=dk[0], dk_hi=dk[1], dv_lo=dv[0], dv_hi=dv[1])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,N", [(2, 96), (4, 128)])
+def test_ring_backward_gloo_matches_single_device(tmp_path, world, N):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker_bwd, args=(world, port, N, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(9)
+    B, H, D = 1, 2, 32
+    q, k, v, g = (rng.standard_normal((B, H, N, D)).astype(np.float32) for _ in range(4))
+    rq, rk, rv, _ = O.attention_backward(q, k, v, g, causal=True)
+    c = N // (2 * world)
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"bwd{r}.npz"))
+        lo, hi = ring.chunk_ids(r, world)
+        for name, ref in (("dq", rq), ("dk", rk), ("dv", rv)):
+            np.testing.assert_allclose(got[f"{name}_lo"], ref[:, :, lo * c:(lo + 1) * c], rtol=3e-4, atol=3e-5)
+            np.testing.assert_allclose(got[f"{name}_hi"], ref[:, :, hi * c:(hi + 1) * c], rtol=3e-4, atol=3e-5)

@@ -109,6 +109,56 @@ def ring_attention_forward(backend, q_pair, k_pair, v_pair, rank: int, world: in
     return (o[:, :, :C], l[:, :, :C]), (o[:, :, C:], l[:, :, C:])
 
 
+def ring_attention_backward(backend, q_pair, k_pair, v_pair, o_pair, l_pair, do_pair, rank: int, world: int, scale: float):
+    """Backward of `ring_attention_forward` ("ring backward").  Inputs are this rank's (low, high) chunks of Q, K, V,
+    of the forward's O (fp32) and L (log2 units) and of the upstream gradient dO; returns ((dq_lo, dq_hi), (dk_lo, dk_hi),
+    (dv_lo, dv_hi)), fp32.
+
+    With the FINAL L and D = scale * rowsum(dO * O) of a query row, the flash backward of a (query block, key block) rectangle
+    is an exact partial sum (P = exp2(S c - L), dS = P (dP - D)): the same rectangles as the forward (`step_plan`) are visited,
+    dQ accumulates locally, and dK / dV accumulators TRAVEL WITH their K / V round the ring -- one more hop than the forward
+    brings them home.  One backward launch pair (dK/dV + dQ kernel) per step through `backend.backward`."""
+    C = q_pair[0].shape[2]
+    q_all, o_all, do_all = backend.cat_seq(q_pair), backend.cat_seq(o_pair), backend.cat_seq(do_pair)
+    l_all = backend.cat_seq(l_pair)
+    kv_cur = backend.pack_kv(k_pair, v_pair)             # [2, B, H, 2C, D]
+    dq = backend.zeros_f32(q_all)
+    dkv_cur = backend.zeros_f32(kv_cur)                  # gradient accumulators of the K / V on hand, fp32
+    nxt, prv = (rank + 1) % world, (rank - 1) % world
+    for step in range(world):
+        k_all, v_all = backend.unpack_kv(kv_cur)
+        (q0, qn), (k0, kn), causal = step_plan(rank, world, step)
+        sq, sk = slice(q0 * C, (q0 + qn) * C), slice(k0 * C, (k0 + kn) * C)
+        dq_p, dk_p, dv_p = backend.backward(q_all[:, :, sq], k_all[:, :, sk], v_all[:, :, sk], o_all[:, :, sq], l_all[:, :, sq],
+                                            do_all[:, :, sq], causal, scale)
+        dq[:, :, sq] += dq_p
+        dkv_cur[0][:, :, sk] += dk_p
+        dkv_cur[1][:, :, sk] += dv_p
+        if world > 1:
+            if step + 1 < world:
+                kv_cur = backend.sendrecv(kv_cur, nxt, prv)
+            dkv_cur = backend.sendrecv(dkv_cur, nxt, prv)        # after the last step this hop delivers dK / dV to their owner
+    backend.finish()
+    dk, dv = dkv_cur[0], dkv_cur[1]
+    return (dq[:, :, :C], dq[:, :, C:]), (dk[:, :, :C], dk[:, :, C:]), (dv[:, :, :C], dv[:, :, C:])
+
+
+def block_backward_numpy(q, k, v, o, l, do, causal, scale):
+    """fp64 reference of one rectangle of the ring backward: gradients of a (query block, key block) pair given the FINAL L (log2
+    units) and O of the query rows.  causal = rows and keys share their local origin (the ring's step 0)."""
+    q, k, v, o, l, do = (np.asarray(x, np.float64) for x in (q, k, v, o, l, do))
+    s = np.einsum("bhqd,bhkd->bhqk", q, k) * scale
+    p = np.exp2(s * LOG2E - l[..., None])
+    if causal:
+        Sq, Sk = s.shape[-2:]
+        p = np.where(np.arange(Sk)[None, :] > np.arange(Sq)[:, None], 0.0, p)
+    dterm = (do * o).sum(-1)
+    dp = np.einsum("bhqd,bhkd->bhqk", do, v)
+    ds = p * (dp - dterm[..., None]) * scale
+    return (np.einsum("bhqk,bhkd->bhqd", ds, k).astype(np.float32), np.einsum("bhqk,bhqd->bhkd", ds, q).astype(np.float32),
+            np.einsum("bhqk,bhqd->bhkd", p, do).astype(np.float32))
+
+
 def merge_partials_numpy(o_acc, l_acc, o_part, l_part):
     """Reference merge (numpy, in place) of the rule in the module docstring; -inf rows contribute nothing."""
     m = np.maximum(l_acc, l_part)
@@ -163,6 +213,20 @@ class HostBackend:
     def exchange_finish(self, handle, step):
         reqs, recv, _send = handle
         for r in reqs:
+            r.wait()
+        return recv.numpy()
+
+    def zeros_f32(self, like):
+        return np.zeros(like.shape, np.float32)
+
+    def backward(self, q, k, v, o, l, do, causal, scale):
+        return block_backward_numpy(q, k, v, o, l, do, causal, scale)
+
+    def sendrecv(self, buf, dst, src):
+        import torch
+        send = torch.from_numpy(np.ascontiguousarray(buf))
+        recv = torch.empty_like(send)
+        for r in [self.dist.isend(send, dst), self.dist.irecv(recv, src)]:
             r.wait()
         return recv.numpy()
 
@@ -284,6 +348,37 @@ class CudaBackend:
         self.cur ^= 1
         return nxt
 
+    def zeros_f32(self, like):
+        return self.torch.zeros(like.shape, device=self.device, dtype=self.torch.float32)
+
+    def backward(self, q, k, v, o, l, do, causal, scale):
+        """one rectangle through mfa_attention_backward_ex (tensor-core dK/dV + dQ kernels); windows are made contiguous"""
+        torch = self.torch
+        q, k, v, do = (t.contiguous() for t in (q, k, v, do))
+        o, l = o.contiguous(), l.contiguous()
+        B, H, S, D = q.shape
+        Skv = k.shape[2]
+        dq = torch.empty(B, H, S, D, device=self.device, dtype=torch.float32)
+        dk = torch.empty(B, H, Skv, D, device=self.device, dtype=torch.float32)
+        dv = torch.empty(B, H, Skv, D, device=self.device, dtype=torch.float32)
+        bufs = [self._buf(t) for t in (do, q, k, v, o, l, dq, dk, dv)]
+        rc = self.lib.mfa_attention_backward_ex(self.ctx.handle, *[b.handle for b in bufs], None, B, S, Skv, H, D, scale, causal,
+                                                -1, self.prec, None, 0, None, None, 0, 0, 0, self.stream_ptr)
+        for b in bufs:
+            b.close()
+        if rc != 0:
+            raise RuntimeError(f"mfa_attention_backward_ex failed: {rc}")
+        self.launches += 1
+        return dq, dk, dv
+
+    def sendrecv(self, buf, dst, src):
+        torch, dist = self.torch, self.dist
+        buf = buf.contiguous()
+        recv = torch.empty_like(buf)
+        for r in dist.batch_isend_irecv([dist.P2POp(dist.isend, buf, dst), dist.P2POp(dist.irecv, recv, src)]):
+            r.wait()
+        return recv
+
     def finish(self):
         pass
 
@@ -304,6 +399,9 @@ class PythonRingRunner:
 
     def forward(self, q_pair, k_pair, v_pair, scale):
         return ring_attention_forward(self.be, q_pair, k_pair, v_pair, self.rank, self.world, scale)
+
+    def backward(self, q_pair, k_pair, v_pair, o_pair, l_pair, do_pair, scale):
+        return ring_attention_backward(self.be, q_pair, k_pair, v_pair, o_pair, l_pair, do_pair, self.rank, self.world, scale)
 
     def pack(self, q_pair, k_pair, v_pair):
         return (q_pair, k_pair, v_pair)
