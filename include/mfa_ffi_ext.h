@@ -194,6 +194,15 @@ mfa_error_t mfa_ring_attention_forward(
     uint32_t batch_size, uint32_t chunk_rows, uint32_t num_heads, uint16_t head_dim, float softmax_scale,
     mfa_precision_t precision, void* stream);
 
+/* Backward of the ring forward (collective; NCCL transport: the ring must own or have been given a communicator).  out / lse: the
+ * forward's results of this rank; dout in `precision` [B, H, 2 * chunk_rows, D]; dq / dk / dv fp32 [B, H, 2 * chunk_rows, D],
+ * overwritten.  Same rectangles as the forward; dQ accumulates locally, the dK / dV of a visiting pair go straight back to its owner. */
+mfa_error_t mfa_ring_attention_backward(
+    mfa_ring_t ring, mfa_buffer_t q, mfa_buffer_t k, mfa_buffer_t v, mfa_buffer_t out, mfa_buffer_t lse, mfa_buffer_t dout,
+    mfa_buffer_t dq, mfa_buffer_t dk, mfa_buffer_t dv,
+    uint32_t batch_size, uint32_t chunk_rows, uint32_t num_heads, uint16_t head_dim, float softmax_scale,
+    mfa_precision_t precision, void* stream);
+
 /* Backward twin of the above (mask and window honoured; the reference's backward takes neither). */
 mfa_error_t mfa_attention_backward_ex(
     mfa_context_t context,

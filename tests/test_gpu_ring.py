@@ -360,3 +360,78 @@ def test_ring_forward_backward_world2_nccl(tmp_path):
             for s_, cid in (("lo", lo), ("hi", hi)):
                 err = np.abs(got[f"{name}_{s_}"] - ref[:, :, cid * c:(cid + 1) * c]).max() / np.abs(ref).max()
                 assert err < 2e-2, (r, name, s_, err)
+
+
+def _run_native_rank_bwd(rank, world, port, N, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "universal-metal-flash-attention_b200"))
+    os.environ["MFA_CUDA_DEVICE"] = str(rank)
+    torch.cuda.set_device(rank)
+    import umfa
+    from umfa import ring
+    if world > 1:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dev = torch.device("cuda", rank)
+    rng = np.random.default_rng(31)
+    q, k, v, g = (O.round_bf16(rng.standard_normal((1, 2, N, 128)).astype(np.float32))[0] for _ in range(4))
+    ctx = umfa.MFAContext()
+    os.environ["MFA_RING_TRANSPORT"] = "nccl"
+    runner = ring.make_runner(ctx, dist if world > 1 else None, dev, "bf16", rank, world)
+    assert runner.kind.startswith("native"), runner.kind
+    sh = lambda x: tuple(_bf16_dev(c, dev) for c in ring.shard_sequence(x, rank, world))
+    pk = runner.pack(sh(q), sh(k), sh(v))
+    runner.forward_packed(pk, 1.0 / np.sqrt(128))
+    for _ in range(2):                                 # repeated: the second call reuses the work space and the events
+        dq, dk, dv = runner.backward_packed(pk, sh(g), 1.0 / np.sqrt(128))
+    torch.cuda.synchronize(dev)
+    np.savez(os.path.join(out_dir, f"bwd{rank}.npz"), **{f"{n}_{s}": t.cpu().numpy() for n, pair in (("dq", dq), ("dk", dk), ("dv", dv))
+                                                         for s, t in zip(("lo", "hi"), pair)})
+    runner.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _check_bwd(tmp_path, world, N, seed):
+    from umfa import ring
+    rng = np.random.default_rng(seed)
+    q, k, v, g = (O.round_bf16(rng.standard_normal((1, 2, N, 128)).astype(np.float32))[0] for _ in range(4))
+    rq, rk, rv, _ = O.attention_backward(q, k, v, g, causal=True)
+    c = N // (2 * world)
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"bwd{r}.npz"))
+        lo, hi = ring.chunk_ids(r, world)
+        for name, ref in (("dq", rq), ("dk", rk), ("dv", rv)):
+            for s_, cid in (("lo", lo), ("hi", hi)):
+                err = np.abs(got[f"{name}_{s_}"] - ref[:, :, cid * c:(cid + 1) * c]).max() / np.abs(ref).max()
+                assert err < 2e-2, (r, name, s_, err)
+
+
+def test_ring_native_backward_world1(tmp_path):
+    """mfa_ring_attention_backward with a world of one: the causal dK/dV + dQ launches through the ring entry point"""
+    _run_native_rank_bwd(0, 1, 0, 1024, str(tmp_path))
+    _check_bwd(tmp_path, 1, 1024, 31)
+
+
+def test_ring_native_backward_world2(tmp_path):
+    """csrc/ring.cu backward over NVLink (NCCL): K / V exchange, per-step rectangles, dK / dV sent straight back to their owner"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_run_native_rank_bwd, args=(2, port, 2048, str(tmp_path)), nprocs=2, join=True)
+    _check_bwd(tmp_path, 2, 2048, 31)
+
+
+def test_ring_native_backward_world4(tmp_path):
+    """four ranks: every kind of step (source below / above the rank, wrap-around) and the reuse of the two send sets"""
+    import torch
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_run_native_rank_bwd, args=(4, port, 4096, str(tmp_path)), nprocs=4, join=True)
+    _check_bwd(tmp_path, 4, 4096, 31)

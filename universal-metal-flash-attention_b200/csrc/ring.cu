@@ -10,7 +10,8 @@
 //     step 0           mfa_attention_forward_ex            causal 2C x 2C on local indices
 //     source < rank    mfa_attention_forward_accumulate    2C x C  (both local query chunks see the visitor's low chunk)
 //     source > rank    mfa_attention_forward_accumulate     C x 2C (the high query chunk sees both chunks of the visitor)
-// the partial (O, L) of a step being merged into the running result inside the attention epilogue.
+// the partial (O, L) of a step being merged into the running result inside the attention epilogue.  The backward
+// (mfa_ring_attention_backward, end of this file) visits the same rectangles with the dK/dV + dQ kernels.
 //
 // B200-first shape of the exchange: a B200 has memory to spare (180 GB), so every visiting pair lands in its own slot (no
 // double-buffer hand-shake inside a forward), and NVSwitch gives every pair of GPUs full bandwidth, so step s is a DIRECT
@@ -140,8 +141,31 @@ struct Ring {
   bool peers_ready = false;
   unsigned int epoch = 0;
   unsigned long long launches = 0;
+  // backward (mfa_ring_attention_backward): its own visiting K/V slots + fp32 work space, NCCL transport
+  char* bwd_ws = nullptr;
+  size_t bwd_ws_bytes = 0;
+  cudaEvent_t ev_part[2] = {nullptr, nullptr}, ev_sent[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> ev_kv_bwd, ev_grad;          // visiting pair s has landed / the gradients of slot s have landed
   std::mutex mu;
 };
+
+// dst[bh][row0 + r][:] += src[bh][r][:]  (fp32, D % 4 == 0): gradient partials of a row window into the running gradient
+__global__ void add_rows_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n4, long long rows_d4,
+                                long long dst_bh_d4, long long row0_d4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long bh = i / rows_d4, j = i - bh * rows_d4;
+    float4* d = reinterpret_cast<float4*>(dst) + bh * dst_bh_d4 + row0_d4 + j;
+    const float4 a = *d, b = reinterpret_cast<const float4*>(src)[i];
+    *d = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+void add_rows(float* dst, const float* src, long long BH, long long T, long long row0, long long rows, long long D, cudaStream_t st) {
+  const long long n4 = BH * rows * D / 4;
+  if (n4 <= 0) return;
+  long long g = (n4 + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  add_rows_kernel<<<(unsigned)g, 256, 0, st>>>(dst, src, n4, rows * D / 4, T * D / 4, row0 * D / 4);
+}
 
 bool debug_on() { const char* d = getenv("MFA_DEBUG"); return d && d[0] && d[0] != '0'; }
 #define RDBG(...) do { if (debug_on()) { fprintf(stderr, "[mfa ring] " __VA_ARGS__); fputc('\n', stderr); } } while (0)
@@ -278,6 +302,11 @@ void mfa_ring_destroy(mfa_ring_t ring) {
   if (r->k_visit) cudaFree(r->k_visit);
   if (r->v_visit) cudaFree(r->v_visit);
   if (r->flags) cudaFree(r->flags);
+  if (r->bwd_ws) cudaFree(r->bwd_ws);
+  for (cudaEvent_t e : r->ev_part) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : r->ev_sent) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : r->ev_kv_bwd) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : r->ev_grad) if (e) cudaEventDestroy(e);
   if (r->ev_ready) cudaEventDestroy(r->ev_ready);
   if (r->ev_done) cudaEventDestroy(r->ev_done);
   for (cudaEvent_t e : r->ev_arrived) if (e) cudaEventDestroy(e);
@@ -459,6 +488,166 @@ mfa_error_t mfa_ring_attention_forward(mfa_ring_t ring, mfa_buffer_t q, mfa_buff
     cudaStreamDestroy(own);
   }
   return rc;
+}
+
+// Backward of mfa_ring_attention_forward.  q, k, v as in the forward; out / lse are the forward's results of this
+// rank; dout is the upstream gradient in `precision`, contiguous [B, H, 2C, D]; dq, dk, dv fp32 [B, H, 2C, D] (overwritten).
+// The same rectangles as the forward: with the final L and D = scale * rowsum(dO * O) of a query row the flash backward of a
+// (query block, key block) pair is an exact partial sum, so step s runs the dK/dV + dQ kernels on (local rows, visiting pair),
+// adds its dQ into the local gradient and sends the pair's dK / dV DIRECTLY back to its owner (rank - s), which adds them into
+// its own -- the mirror image of the forward's direct exchange.  NCCL transport (the ring needs a communicator); the K / V
+// exchange and the gradient returns run on the side stream behind events, the backward kernels on `stream`.
+mfa_error_t mfa_ring_attention_backward(mfa_ring_t ring, mfa_buffer_t q, mfa_buffer_t k, mfa_buffer_t v, mfa_buffer_t out,
+                                        mfa_buffer_t lse, mfa_buffer_t dout, mfa_buffer_t dq, mfa_buffer_t dk, mfa_buffer_t dv,
+                                        uint32_t batch_size, uint32_t chunk_rows, uint32_t num_heads, uint16_t head_dim,
+                                        float softmax_scale, mfa_precision_t precision, void* stream) {
+  if (!ring || !q || !k || !v || !out || !lse || !dout || !dq || !dk || !dv) return MFA_ERROR_INVALID_ARGS;
+  if (precision != MFA_PRECISION_BF16 && precision != MFA_PRECISION_FP16) return MFA_ERROR_INVALID_ARGS;
+  Ring* r = reinterpret_cast<Ring*>(ring);
+  std::lock_guard<std::mutex> lock(r->mu);
+  const int64_t B = batch_size, H = num_heads, C = chunk_rows, T = 2 * C, D = head_dim, BH = B * H;
+  const size_t n = (size_t)BH * T * D, esz = 2, bytes = n * esz, gbytes = n * 4, half16 = n / 2 * esz, half32 = n / 2 * 4;
+  if (n == 0) return MFA_SUCCESS;
+  if (D % 4) return MFA_ERROR_INVALID_ARGS;
+  char* qd = reinterpret_cast<char*>(mfa_buffer_contents(q));
+  char* kd = reinterpret_cast<char*>(mfa_buffer_contents(k));
+  char* vd = reinterpret_cast<char*>(mfa_buffer_contents(v));
+  char* od = reinterpret_cast<char*>(mfa_buffer_contents(out));
+  char* ld = reinterpret_cast<char*>(mfa_buffer_contents(lse));
+  char* gd = reinterpret_cast<char*>(mfa_buffer_contents(dout));
+  float* dqd = reinterpret_cast<float*>(mfa_buffer_contents(dq));
+  float* dkd = reinterpret_cast<float*>(mfa_buffer_contents(dk));
+  float* dvd = reinterpret_cast<float*>(mfa_buffer_contents(dv));
+  if (!qd || !kd || !vd || !od || !ld || !gd || !dqd || !dkd || !dvd) return MFA_ERROR_INVALID_ARGS;
+  DeviceScope ds(r->device);
+  const int W = r->world;
+  if (W > 1 && (!r->comm || !nccl().ok)) return MFA_ERROR_DEVICE_NOT_SUPPORTED;
+  cudaStream_t cs = reinterpret_cast<cudaStream_t>(stream);
+  const bool blocking = stream == nullptr;
+  cudaStream_t own = nullptr;
+  if (blocking) { if (cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking) != cudaSuccess) return MFA_ERROR_EXECUTION_FAILED; cs = own; }
+  mfa_error_t rc = MFA_SUCCESS;
+  auto done = [&](mfa_error_t e) {
+    if (blocking) { if (cudaStreamSynchronize(cs) != cudaSuccess) { cudaGetLastError(); if (e == MFA_SUCCESS) e = MFA_ERROR_EXECUTION_FAILED; } cudaStreamDestroy(own); }
+    return e;
+  };
+
+  // step 0: the rank's own pair, causal on local indices, straight into dq / dk / dv
+  rc = mfa_attention_backward_ex(r->ctx, dout, q, k, v, out, lse, dq, dk, dv, nullptr, batch_size, (uint32_t)T, (uint32_t)T, num_heads,
+                                 head_dim, softmax_scale, true, -1, precision, nullptr, 0, nullptr, nullptr, 0, MFA_MASK_TYPE_NONE,
+                                 MFA_MASK_SCALAR_BYTE, cs);
+  ++r->launches;
+  if (W == 1 || rc != MFA_SUCCESS) return done(rc);
+
+  // ---- work space: visiting K / V slots, the gathered high-chunk windows, gradient partials (two send sets, W - 1 receive sets)
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t o_kv = 0, o_win = o_kv + 2 * (size_t)(W - 1) * up(bytes);
+  const size_t o_qh = o_win, o_gh = o_qh + up(half16), o_oh = o_gh + up(half16), o_lh = o_oh + up(half32);
+  const size_t o_dqp = o_lh + up((size_t)BH * C * 4), o_send = o_dqp + up(gbytes), o_recv = o_send + 4 * up(gbytes);
+  const size_t total = o_recv + 2 * (size_t)(W - 1) * up(gbytes);
+  if (r->bwd_ws_bytes < total) {
+    cudaDeviceSynchronize();
+    if (r->bwd_ws) cudaFree(r->bwd_ws);
+    r->bwd_ws = nullptr; r->bwd_ws_bytes = 0;
+    if (cudaMalloc(&r->bwd_ws, total) != cudaSuccess) { cudaGetLastError(); return done(MFA_ERROR_MEMORY_ALLOCATION); }
+    r->bwd_ws_bytes = total;
+  }
+  if (r->ev_kv_bwd.empty()) {
+    bool ok = true;
+    r->ev_kv_bwd.assign((size_t)W, nullptr); r->ev_grad.assign((size_t)W, nullptr);
+    for (int s = 1; s < W && ok; ++s)
+      ok = cudaEventCreateWithFlags(&r->ev_kv_bwd[s], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&r->ev_grad[s], cudaEventDisableTiming) == cudaSuccess;
+    for (int j = 0; j < 2 && ok; ++j)
+      ok = cudaEventCreateWithFlags(&r->ev_part[j], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&r->ev_sent[j], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); return done(MFA_ERROR_EXECUTION_FAILED); }
+  }
+  char* ws = r->bwd_ws;
+  auto kslot = [&](int s) { return ws + o_kv + (size_t)(2 * (s - 1)) * up(bytes); };
+  auto vslot = [&](int s) { return ws + o_kv + (size_t)(2 * (s - 1) + 1) * up(bytes); };
+  auto send_dk = [&](int j) { return reinterpret_cast<float*>(ws + o_send + (size_t)(2 * j) * up(gbytes)); };
+  auto send_dv = [&](int j) { return reinterpret_cast<float*>(ws + o_send + (size_t)(2 * j + 1) * up(gbytes)); };
+  auto recv_dk = [&](int s) { return reinterpret_cast<float*>(ws + o_recv + (size_t)(2 * (s - 1)) * up(gbytes)); };
+  auto recv_dv = [&](int s) { return reinterpret_cast<float*>(ws + o_recv + (size_t)(2 * (s - 1) + 1) * up(gbytes)); };
+  float* dq_part = reinterpret_cast<float*>(ws + o_dqp);
+  NcclApi& nc = nccl();
+
+  // ---- K / V exchange: all hops queued now on the side stream (they only read the rank's own pair)
+  cudaEventRecord(r->ev_ready, cs);
+  cudaStreamWaitEvent(r->comm_stream, r->ev_ready, 0);
+  for (int s = 1; s < W && rc == MFA_SUCCESS; ++s) {
+    const int dst = (r->rank + s) % W, src = (r->rank - s + W) % W;
+    ncclResult_t e = nc.GroupStart();
+    if (e == 0) e = nc.Send(kd, bytes, 0, dst, r->comm, r->comm_stream);
+    if (e == 0) e = nc.Send(vd, bytes, 0, dst, r->comm, r->comm_stream);
+    if (e == 0) e = nc.Recv(kslot(s), bytes, 0, src, r->comm, r->comm_stream);
+    if (e == 0) e = nc.Recv(vslot(s), bytes, 0, src, r->comm, r->comm_stream);
+    const ncclResult_t e2 = nc.GroupEnd();
+    if (e != 0 || e2 != 0) rc = MFA_ERROR_EXECUTION_FAILED;
+    cudaEventRecord(r->ev_kv_bwd[s], r->comm_stream);
+  }
+  if (rc != MFA_SUCCESS) return done(rc);
+
+  // ---- the high query chunk as contiguous operands (rows C .. 2C of every (b, h)): used by every step whose source rank > rank
+  const size_t rq = (size_t)T * D * esz, ro = (size_t)T * D * 4, rl = (size_t)T * 4;
+  cudaMemcpy2DAsync(ws + o_qh, rq / 2, qd + rq / 2, rq, rq / 2, (size_t)BH, cudaMemcpyDeviceToDevice, cs);
+  cudaMemcpy2DAsync(ws + o_gh, rq / 2, gd + rq / 2, rq, rq / 2, (size_t)BH, cudaMemcpyDeviceToDevice, cs);
+  cudaMemcpy2DAsync(ws + o_oh, ro / 2, od + ro / 2, ro, ro / 2, (size_t)BH, cudaMemcpyDeviceToDevice, cs);
+  cudaMemcpy2DAsync(ws + o_lh, rl / 2, ld + rl / 2, rl, rl / 2, (size_t)BH, cudaMemcpyDeviceToDevice, cs);
+  struct Dev { mfa_buffer_t h = nullptr; Dev(mfa_context_t c, void* p, size_t b) { mfa_buffer_from_mtl_buffer(c, p, b, &h); } ~Dev() { if (h) mfa_destroy_buffer(h); } };
+  Dev h_qh(r->ctx, ws + o_qh, half16), h_gh(r->ctx, ws + o_gh, half16), h_oh(r->ctx, ws + o_oh, half32), h_lh(r->ctx, ws + o_lh, (size_t)BH * C * 4);
+  Dev h_dqp(r->ctx, dq_part, gbytes);
+  if (!h_qh.h || !h_gh.h || !h_oh.h || !h_lh.h || !h_dqp.h) return done(MFA_ERROR_MEMORY_ALLOCATION);
+
+  for (int step = 1; step < W && rc == MFA_SUCCESS; ++step) {
+    const int j = step & 1;
+    const int src = (r->rank - step + W) % W, from = (r->rank + step) % W;      // owner of the visiting pair / whose gradients come back
+    const Plan pl = step_plan(r->rank, W, step);
+    cudaStreamWaitEvent(cs, r->ev_kv_bwd[step], 0);
+    if (step > 2) cudaStreamWaitEvent(cs, r->ev_sent[j], 0);                   // send set j is free again
+    {
+      Handle hk(r->ctx, kslot(step), (size_t)pl.k0 * C * D, esz, B, H, (int64_t)pl.kn * C, D, T);
+      Handle hv(r->ctx, vslot(step), (size_t)pl.k0 * C * D, esz, B, H, (int64_t)pl.kn * C, D, T);
+      Dev h_dk(r->ctx, send_dk(j), gbytes), h_dv(r->ctx, send_dv(j), gbytes);
+      if (!hk.h || !hv.h || !h_dk.h || !h_dv.h) { rc = MFA_ERROR_MEMORY_ALLOCATION; break; }
+      const bool all_rows = pl.qn == 2;
+      rc = mfa_attention_backward_ex(r->ctx, all_rows ? dout : h_gh.h, all_rows ? q : h_qh.h, hk.h, hv.h, all_rows ? out : h_oh.h,
+                                     all_rows ? lse : h_lh.h, h_dqp.h, h_dk.h, h_dv.h, nullptr, batch_size, (uint32_t)(pl.qn * C),
+                                     (uint32_t)(pl.kn * C), num_heads, head_dim, softmax_scale, false, -1, precision, nullptr, 0,
+                                     nullptr, nullptr, 0, MFA_MASK_TYPE_NONE, MFA_MASK_SCALAR_BYTE, cs);
+      ++r->launches;
+      if (rc != MFA_SUCCESS) break;
+    }
+    add_rows(dqd, dq_part, BH, T, (long long)pl.q0 * C, (long long)pl.qn * C, D, cs);
+    cudaEventRecord(r->ev_part[j], cs);
+    // gradients of the visiting pair go home; the pair this rank lent to rank + step comes back with what that rank computed:
+    // it saw the low chunk only when it is the higher rank, both chunks otherwise
+    const size_t send_bytes = (size_t)BH * pl.kn * C * D * 4;
+    const int back_kn = from > r->rank ? 1 : 2;
+    const size_t recv_bytes = (size_t)BH * back_kn * C * D * 4;
+    cudaStreamWaitEvent(r->comm_stream, r->ev_part[j], 0);
+    ncclResult_t e = nc.GroupStart();
+    if (e == 0) e = nc.Send(send_dk(j), send_bytes, 0, src, r->comm, r->comm_stream);
+    if (e == 0) e = nc.Send(send_dv(j), send_bytes, 0, src, r->comm, r->comm_stream);
+    if (e == 0) e = nc.Recv(recv_dk(step), recv_bytes, 0, from, r->comm, r->comm_stream);
+    if (e == 0) e = nc.Recv(recv_dv(step), recv_bytes, 0, from, r->comm, r->comm_stream);
+    const ncclResult_t e2 = nc.GroupEnd();
+    if (e != 0 || e2 != 0) { rc = MFA_ERROR_EXECUTION_FAILED; break; }
+    cudaEventRecord(r->ev_sent[j], r->comm_stream);
+    cudaEventRecord(r->ev_grad[step], r->comm_stream);
+  }
+  // ---- what the other ranks computed for this rank's K / V
+  for (int step = 1; step < W && rc == MFA_SUCCESS; ++step) {
+    const int from = (r->rank + step) % W;
+    const int back_kn = from > r->rank ? 1 : 2;
+    cudaStreamWaitEvent(cs, r->ev_grad[step], 0);
+    add_rows(dkd, recv_dk(step), BH, T, 0, (long long)back_kn * C, D, cs);
+    add_rows(dvd, recv_dv(step), BH, T, 0, (long long)back_kn * C, D, cs);
+  }
+  if (cudaGetLastError() != cudaSuccess && rc == MFA_SUCCESS) rc = MFA_ERROR_EXECUTION_FAILED;
+  // the side stream's last sends read the send sets: the next call may not reuse them before (same stream order on comm_stream)
+  return done(rc);
 }
 
 }  // extern "C"

@@ -143,6 +143,7 @@ SIGNATURES = {
     "mfa_ring_import_handles": (_i32, [_vp, _vp, _sz]),
     "mfa_ring_launch_count": (_u64, [_vp]),
     "mfa_ring_attention_forward": (_i32, [_vp, _buf, _buf, _buf, _buf, _buf, _u32, _u32, _u32, _u16, _f32, _i32, _vp]),
+    "mfa_ring_attention_backward": (_i32, [_vp] + [_buf] * 9 + [_u32, _u32, _u32, _u16, _f32, _i32, _vp]),
     "mfa_set_quantized_pv_precision": (_i32, [_ctx, _i32]),
     "mfa_get_quantized_pv_precision": (_i32, [_ctx]),
     "mfa_set_device": (_i32, [_i32]),

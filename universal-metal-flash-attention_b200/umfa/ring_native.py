@@ -13,7 +13,7 @@ from .core import MFABuffer
 
 
 class NativeRingRunner:
-    kind = "native driver (csrc/ring.cu: mfa_ring_attention_forward, one launch per ring step, merge in the epilogue)"
+    kind = "native driver (csrc/ring.cu: mfa_ring_attention_forward / _backward, one launch per ring step, merge in the epilogue)"
 
     def __init__(self, ctx, dist, device, dtype, rank, world, transport=None):
         import torch
@@ -92,6 +92,28 @@ class NativeRingRunner:
             raise RuntimeError(f"mfa_ring_attention_forward failed: {rc}")
         o, l = pk["t"][3], pk["t"][4]
         return (o[:, :, :C], l[:, :, :C]), (o[:, :, C:], l[:, :, C:])
+
+    def backward_packed(self, pk, do_pair, scale):
+        """mfa_ring_attention_backward on the operands / results of a forward_packed call: do_pair = (low, high) chunks of the
+        upstream gradient in the operands' precision.  Returns ((dq_lo, dq_hi), (dk_lo, dk_hi), (dv_lo, dv_hi)), fp32."""
+        torch = self.torch
+        B, H, C, D = pk["dims"]
+        do = torch.cat([do_pair[0], do_pair[1]], dim=2).contiguous()
+        grads = [torch.empty(B, H, 2 * C, D, device=self.device, dtype=torch.float32) for _ in range(3)]
+        extra = [MFABuffer(self.ctx, device_ptr=t.data_ptr(), size=t.numel() * t.element_size()) for t in [do] + grads]
+        qb, kb, vb, ob, lb = pk["b"]
+        stream_ptr = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        try:
+            rc = self.lib.mfa_ring_attention_backward(self.handle, qb.handle, kb.handle, vb.handle, ob.handle, lb.handle,
+                                                      extra[0].handle, extra[1].handle, extra[2].handle, extra[3].handle,
+                                                      B, C, H, D, scale, self.prec, stream_ptr)
+            if rc != 0:
+                raise RuntimeError(f"mfa_ring_attention_backward failed: {rc}")
+            torch.cuda.current_stream(self.device).synchronize()       # `do` and the handles die with this call
+        finally:
+            for b in extra:
+                b.close()
+        return tuple((g[:, :, :C], g[:, :, C:]) for g in grads)
 
     def forward(self, q_pair, k_pair, v_pair, scale):
         """Convenience form on chunk pairs: packs (three device copies) on every call; hot loops pack once and call
