@@ -21,8 +21,12 @@ Printed JSON (rank 0, one line):
                fwdbwd_flux              config 2 shape, forward + backward per step (weak replicas)
                c4_fwdbwd_heads_sharded  config 4: 32k causal + window 4096, fwd+bwd, the 32 heads SPLIT over the N ranks (strong)
                int8_block / int4_block  config 3: runtime-quantised forward (block-64 scales), against the bf16 launch
-               ring128k                 config 5: 128k causal, sequence split over the N ranks, K/V ring over NCCL (strong);
+               fp32_flux                config 2 shape with fp32 operands (the reference adapters' default precision): tensor pipe
+                                        through fp16 (hi, lo) operand pairs
+               d256_fwd                 head_dim 256 (the head dim of the reference's own headline figure), bf16 N=8192 H=16
+               ring128k                 config 5: 128k causal, sequence split over the N ranks, K/V ring over NVLink (strong);
                                         at N=1 it is the single causal launch the efficiency is measured against
+               ring128k_fwdbwd          the same with the native ring backward behind every forward
 
 --impl reference times that CPU oracle alone (the reference's Metal path cannot run on Linux).
 """
@@ -67,7 +71,7 @@ WORKLOADS = {
     "ring16k": dict(B=1, H=8, Sq=16384, Skv=16384, D=128, causal=True, window=-1, dtype="bf16", ring=True,
                     label="16k-token causal ring attention (smoke size)"),
 }
-ALL_EXTRAS = ["fwdbwd_flux", "c4_fwdbwd_heads_sharded", "int8_block", "int4_block", "fp32_flux", "d256_fwd", "ring128k"]
+ALL_EXTRAS = ["fwdbwd_flux", "c4_fwdbwd_heads_sharded", "int8_block", "int4_block", "fp32_flux", "d256_fwd", "ring128k", "ring128k_fwdbwd"]
 
 
 def visible_pairs(Sq, Skv, causal, window):
@@ -481,7 +485,7 @@ def section_quant(hz, steps, warmup, target, label):
     return rec
 
 
-def section_ring(hz, w, steps, warmup):
+def section_ring(hz, w, steps, warmup, mode="fwd"):
     """Config 5: causal ring attention over `world` GPUs, total sequence fixed (strong scaling)."""
     import numpy as np
     torch = hz.torch
@@ -496,8 +500,15 @@ def section_ring(hz, w, steps, warmup):
     qp, kp, vp = (mk(), mk()), (mk(), mk()), (mk(), mk())
     runner = ring.make_runner(hz.ctx, hz.dist, dev, w["dtype"], rank, world)
     pk = runner.pack(qp, kp, vp)                   # the [low | high] operand layout is the API's input contract: built once
-    for _ in range(warmup):
+    fwdbwd = mode == "fwdbwd" and hasattr(runner, "backward_packed")
+    dop = (mk(), mk()) if fwdbwd else None
+
+    def one_step():
         runner.forward_packed(pk, scale)
+        if fwdbwd:
+            runner.backward_packed(pk, dop, scale)     # (synchronises the stream at its end: the gradients are returned)
+    for _ in range(warmup):
+        one_step()
     hz.barrier()
     l0 = runner.launches
     sampler = ClockSampler(hz.local_rank, interval=0.25)
@@ -507,18 +518,18 @@ def section_ring(hz, w, steps, warmup):
     hz.barrier()
     e0.record(hz.stream)
     for _ in range(steps):
-        runner.forward_packed(pk, scale)
+        one_step()
     e1.record(hz.stream)
     hz.barrier()
     ms = hz.max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
-    flops = 4.0 * B * H * ring.visible_pairs_causal(N) * D
+    flops = (14.0 if fwdbwd else 4.0) * B * H * ring.visible_pairs_causal(N) * D      # fwd 4, bwd 10 FLOP per pair per d (FA convention)
     value = flops * steps / (ms * 1e-3) / 1e12
     kv_hop_bytes = 4 * B * H * C * D * 2
-    rec = {"metric": "attention forward TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world,
-           "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+    rec = {"metric": "attention forward+backward TFLOP/s" if fwdbwd else "attention forward TFLOP/s", "value": value, "unit": "TFLOP/s",
+           "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
            "scaling": "strong", "dtype": w["dtype"],
-           "config": {"workload": w["label"], "total_seq": N, "per_gpu_rows": 2 * C, "H": H, "D": D,
+           "config": {"workload": w["label"] + (" forward + backward (mfa_ring_attention_backward)" if fwdbwd else ""), "total_seq": N, "per_gpu_rows": 2 * C, "H": H, "D": D,
                       "parallelism": f"context parallel x{world}, zig-zag ring, {runner.transport} of K/V ({kv_hop_bytes / 1e6:.0f} MB per hop) on a side stream",
                       "driver": runner.kind,
                       "cache": "per-rank K/V + O working set >> 126 MB L2" if B * H * C * D * 2 * 6 > 126e6 else "small"},
@@ -551,6 +562,8 @@ def run_extras(hz, names, args):
                 rec = section_attention(hz, WORKLOADS["d256"], "fwd", min(args.steps, 10), 3)[0]
             elif name == "ring128k":
                 rec = section_ring(hz, WORKLOADS["ring128k"], min(args.steps, 4), 3)
+            elif name == "ring128k_fwdbwd":
+                rec = section_ring(hz, WORKLOADS["ring128k"], min(args.steps, 3), 2, mode="fwdbwd")
             else:
                 rec = {"error": f"unknown extra {name}"}
         except Exception as e:                                    # an extra never takes the headline down
@@ -560,7 +573,7 @@ def run_extras(hz, names, args):
             except Exception:
                 pass
         out[name] = rec
-        if ok == 0.0 and hz.dist is not None and name == "ring128k":
+        if ok == 0.0 and hz.dist is not None and name.startswith("ring128k"):
             break                                                 # peers may be stuck in the ring: stop issuing collectives
     return out
 
