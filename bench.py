@@ -71,7 +71,8 @@ WORKLOADS = {
     "ring16k": dict(B=1, H=8, Sq=16384, Skv=16384, D=128, causal=True, window=-1, dtype="bf16", ring=True,
                     label="16k-token causal ring attention (smoke size)"),
 }
-ALL_EXTRAS = ["fwdbwd_flux", "c4_fwdbwd_heads_sharded", "int8_block", "int4_block", "fp32_flux", "d256_fwd", "ring128k", "ring128k_fwdbwd"]
+ALL_EXTRAS = ["fwdbwd_flux", "c4_fwdbwd_heads_sharded", "int8_block", "int4_block", "fp32_flux", "d256_fwd", "mask_bf16_dense", "ring128k",
+              "ring128k_fwdbwd"]
 
 
 def visible_pairs(Sq, Skv, causal, window):
@@ -330,9 +331,15 @@ def make_attention_sets(hz, w, H, mode, o_dtype="fp32", seed=1234):
     return sets, in_bytes, out_bytes
 
 
-def attention_enqueue(hz, w, H, mode, sets, o_prec=2):
+def attention_enqueue(hz, w, H, mode, sets, o_prec=2, mask=None):
+    """mask: optional device tensor [1, H, Sq, Skv] (bf16 additive terms), handed over in place with its strides"""
     import numpy as np
     lib, ctx = hz.lib, hz.ctx
+    margs = [None, 0, None, None, 0, 0, 0]
+    if mask is not None:
+        i64 = ctypes.c_int64
+        margs = [ctypes.c_void_p(mask.data_ptr()), mask.numel() * mask.element_size(), (i64 * mask.dim())(*mask.shape),
+                 (i64 * mask.dim())(*mask.stride()), mask.dim(), 2, 2]              # additive, bf16 scalars
     B, Sq, Skv, D = w["B"], w["Sq"], w["Skv"], w["D"]
     scale = 1.0 / float(np.sqrt(D))
     prec = {"bf16": 1, "fp16": 0, "fp32": 2}[w["dtype"]]
@@ -343,20 +350,20 @@ def attention_enqueue(hz, w, H, mode, sets, o_prec=2):
         lse = b[4].handle if mode == "fwdbwd" else None
         rc = lib.mfa_attention_forward_ex(ctx.handle, b[0].handle, b[1].handle, b[2].handle, b[3].handle, lse,
                                           B, Sq, Skv, H, D, scale, w["causal"], w["window"], prec, o_prec,
-                                          None, 0, None, None, 0, 0, 0, hz.stream_ptr)
+                                          *margs, hz.stream_ptr)
         if rc != 0:
             raise RuntimeError(f"mfa_attention_forward_ex failed: {rc}")
         if mode == "fwdbwd":
             rc = lib.mfa_attention_backward_ex(ctx.handle, b[5].handle, b[0].handle, b[1].handle, b[2].handle, b[3].handle,
                                                b[4].handle, b[6].handle, b[7].handle, b[8].handle, b[9].handle,
                                                B, Sq, Skv, H, D, scale, w["causal"], w["window"], prec,
-                                               None, 0, None, None, 0, 0, 0, hz.stream_ptr)
+                                               *margs, hz.stream_ptr)
             if rc != 0:
                 raise RuntimeError(f"mfa_attention_backward_ex failed: {rc}")
     return enqueue
 
 
-def section_attention(hz, w, mode, steps, warmup, heads_sharded=False, o_dtype="fp32"):
+def section_attention(hz, w, mode, steps, warmup, heads_sharded=False, o_dtype="fp32", dense_mask=False):
     """Dense attention section: weak replicas (every rank the whole workload) or -- heads_sharded -- the workload's heads
     split over the ranks (strong scaling, no collective: heads are independent, MultiHeadAttention.swift:373-377)."""
     import numpy as np
@@ -367,7 +374,11 @@ def section_attention(hz, w, mode, steps, warmup, heads_sharded=False, o_dtype="
         H = H // hz.world
     o_prec = {"fp32": 2, "bf16": 1, "fp16": 0}[o_dtype]
     sets, in_bytes, out_bytes = make_attention_sets(hz, w, H, mode, o_dtype)
-    enqueue = attention_enqueue(hz, w, H, mode, sets, o_prec)
+    mask = None
+    if dense_mask:       # dense additive bias, one row of bf16 terms per (head, query): [1, H, Sq, Skv], read once per launch
+        g = hz.torch.Generator(device=hz.dev).manual_seed(99 + hz.rank)
+        mask = hz.torch.randn(1, H, w["Sq"], w["Skv"], device=hz.dev, dtype=hz.torch.float32, generator=g).to(hz.torch.bfloat16)
+    enqueue = attention_enqueue(hz, w, H, mode, sets, o_prec, mask)
     total_ms, per, clocks, launches = hz.timed(enqueue, steps, warmup)
     kernel = hz.ctx.last_kernel
     per_rank_flops = fwd_flops(dict(w, H=H)) * (3.5 if mode == "fwdbwd" else 1.0)   # fwd 4, bwd 10 FLOP per pair per d
@@ -391,7 +402,19 @@ def section_attention(hz, w, mode, steps, warmup, heads_sharded=False, o_dtype="
                "algorithmic FLOPs; head_dim 256 runs as two 128-column halves of O per query block, Q K^T computed for each: the tensor pipe does 1.5x this work"
                if w["D"] == 256 else None)),
            "gpu_launches": launches, "clocks": clocks}
-    del sets
+    if mask is not None:
+        mb = mask.numel() * mask.element_size()
+        rec["config"]["mask"] = f"dense additive bf16 [1, {H}, {w['Sq']}, {w['Skv']}] = {mb / 1e6:.0f} MB, device-resident, read in place"
+        hbm_peak = 6650.0
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_peak = float(json.load(f)["hbm_gbs"])
+        except (OSError, KeyError, ValueError):
+            pass
+        gbs = mb / (med * 1e-3) / 1e9
+        rec["mask_hbm"] = {"bytes_per_launch": mb, "GB/s": gbs, "peak": hbm_peak, "frac": gbs / hbm_peak,
+                           "note": "the mask alone is this much HBM traffic per launch (it cannot stay in the 126 MB L2)"}
+    del sets, mask
     hz.torch.cuda.empty_cache()
     return rec, in_bytes, out_bytes, per_rank_flops
 
@@ -558,6 +581,8 @@ def run_extras(hz, names, args):
                 rec = section_quant(hz, min(args.steps, 10), 3, 4, "int4 block-64 codes")
             elif name == "fp32_flux":
                 rec = section_attention(hz, WORKLOADS["flux_fp32"], "fwd", min(args.steps, 10), 3)[0]
+            elif name == "mask_bf16_dense":
+                rec = section_attention(hz, WORKLOADS["flux"], "fwd", min(args.steps, 10), 3, dense_mask=True)[0]
             elif name == "d256_fwd":
                 rec = section_attention(hz, WORKLOADS["d256"], "fwd", min(args.steps, 10), 3)[0]
             elif name == "ring128k":

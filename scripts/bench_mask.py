@@ -46,6 +46,8 @@ cases = {
     "bool_key_padding_[B,1,1,S]_last_512_hidden": (torch.cat([torch.ones(S - 512, dtype=torch.bool, device=dev), torch.zeros(512, dtype=torch.bool, device=dev)]).view(1, 1, 1, S), 1, 0),
     "bool_packing_8_segments_[1,1,S,S]": ((seg[:, None] == seg[None, :]).view(1, 1, S, S), 1, 0),
     "additive_fp32_dense_[1,1,S,S]": (torch.randn(1, 1, S, S, device=dev), 2, 3),
+    "additive_bf16_dense_[1,1,S,S]": (torch.randn(1, 1, S, S, device=dev).to(torch.bfloat16), 2, 2),
+    "bool_dense_random_half_[1,H,S,S]": (torch.rand(1, H, S, S, device=dev) > 0.5, 1, 0),
     "additive_bf16_dense_[1,H,S,S]": (torch.randn(1, H, S, S, device=dev).to(torch.bfloat16), 2, 2),
     "additive_fp32_dense_[1,H,S,S]": (torch.randn(1, H, S, S, device=dev), 2, 3),
 }
@@ -62,6 +64,10 @@ for name, (mask, mt, ms) in cases.items():
     res[name] = {"ms": t * 1e3, "kernel": ctx.last_kernel, "visible_fraction": vis,
                  "tflops_of_visible_pairs": 4.0 * B * H * S * S * D * vis / t / 1e12,
                  "mask_mb": 0 if mask is None else mask.numel() * mask.element_size() / 1e6}
+if os.environ.get("MFA_BENCH_MASK_FWD_ONLY"):
+    print(json.dumps({"workload": "FLUX.1-schnell shape B=1 H=24 N=4608 D=128 bf16 forward under external masks",
+                      "timing": "mfa_get_gpu_latency, median of %d" % steps, **res}))
+    sys.exit(0)
 # backward under the same masks (dO random, O / L from the forward just run)
 do = torch.randn(B, H, S, D, device=dev, generator=g).to(torch.bfloat16)
 dq, dk, dv = (torch.empty(B, H, S, D, device=dev, dtype=torch.float32) for _ in range(3))

@@ -237,7 +237,7 @@ def test_headline_forward_kernels_do_not_spill():
         pytest.skip("cuobjdump or the object file is not available")
     out = subprocess.run([cuobjdump, "-res-usage", obj], capture_output=True, text=True).stdout
     seen = 0
-    for m in re.finditer(r"Function (\S*fwd_tc_kernelILi(\d+)ELi(\d+)ELi(\d+)ELb0ELb0E\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
+    for m in re.finditer(r"Function (\S*fwd_tc_kernelILi(\d+)ELi(\d+)ELi(\d+)ELb0ELi0E\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
         mode, stack = int(m.group(3)), int(m.group(6))
         if mode in (0, 1, 3, 4, 8):          # f16, bf16, int8 + e4m3, fp32 split, wide bf16
             seen += 1

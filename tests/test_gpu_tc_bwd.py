@@ -139,6 +139,53 @@ def test_bwd_tc_external_masks(ctx, kind, shape):
     assert max(errs.values()) < 2e-2, errs
 
 
+@pytest.mark.parametrize("kind", ["bool_bcast_heads", "bool_rows_empty", "add_fp16", "add_bf16"])
+@pytest.mark.parametrize("shape", [(2, 2, 300, 400, 128, "bf16"), (1, 3, 520, 656, 64, "fp16"), (1, 1, 900, 1152, 128, "fp16")])
+def test_bwd_tc_external_masks_staged(ctx, kind, shape):
+    """dense 1- / 2-byte masks with 16-byte-multiple rows: both backward kernels read TMA-staged 128 x 128 mask tiles from shared
+    memory (dQ: row owner; dK / dV: column owner); ragged query / key counts, several steps per CTA"""
+    import umfa
+    B, H, Sq, Skv, D, dtype = shape
+    rng = np.random.default_rng(41)
+    q, k, v, g = (rng.standard_normal(s).astype(np.float32) for s in
+                  ((B, H, Sq, D), (B, H, Skv, D), (B, H, Skv, D), (B, H, Sq, D)))
+    (qa, qf), (ka, kf), (va, vf), (ga, gf) = (to_dtype(x, dtype) for x in (q, k, v, g))
+    m, om, kw = _mask_for(kind, rng, B, H, Sq, Skv)
+    o_ref, l_ref = O.attention_forward(qf, kf, vf, mask=om)
+    dq, dk, dv, dt = umfa.flash_attention_backward(ctx, ga, qa, ka, va, o_ref, l_ref, input_precision=dtype, attn_mask=m, **kw)
+    assert ctx.last_kernel.startswith("bwd_tc_") and ctx.last_kernel.endswith("_tma_mask"), ctx.last_kernel
+    rq, rk, rv, rt = O.attention_backward(qf, kf, vf, gf, mask=om)
+    errs = {}
+    for name, got, ref in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+        assert np.isfinite(got).all(), name
+        errs[name] = rel_max(got, ref)
+    assert max(errs.values()) < 2e-2, errs
+
+
+def test_bwd_tc_staged_mask_matches_in_place_reads(ctx, monkeypatch):
+    """staged tiles and in-place mask reads feed the same arithmetic: bit-identical gradients (also with causal)"""
+    import umfa
+    B, H, Sq, Skv, D = 1, 3, 640, 896, 128
+    rng = np.random.default_rng(42)
+    q, g = (rng.standard_normal((B, H, Sq, D)).astype(np.float32) for _ in range(2))
+    k, v = (rng.standard_normal((B, H, Skv, D)).astype(np.float32) for _ in range(2))
+    (qa, qf), (ka, kf), (va, vf), (ga, gf) = (to_dtype(x, "bf16") for x in (q, k, v, g))
+    add = (2.0 * rng.standard_normal((1, H, Sq, Skv))).astype(np.float16)
+    keep = rng.random((Sq, Skv)) > 0.5
+    keep[:, 0] = True
+    for m, causal in ((add, False), (keep, False), (keep, True)):
+        o_ref, l_ref = O.attention_forward(qf, kf, vf, mask=m.astype(np.float32) if m.dtype == np.float16 else m, causal=causal)
+        kw = dict(input_precision="bf16", attn_mask=m, causal=causal)
+        a = umfa.flash_attention_backward(ctx, ga, qa, ka, va, o_ref, l_ref, **kw)
+        assert ctx.last_kernel.endswith("_tma_mask"), ctx.last_kernel
+        monkeypatch.setenv("MFA_DISABLE_MASK_TMA", "1")
+        b = umfa.flash_attention_backward(ctx, ga, qa, ka, va, o_ref, l_ref, **kw)
+        assert ctx.last_kernel.endswith("_mask") and not ctx.last_kernel.endswith("_tma_mask"), ctx.last_kernel
+        monkeypatch.delenv("MFA_DISABLE_MASK_TMA")
+        for x, y in zip(a[:3], b[:3]):
+            assert np.array_equal(x, y)
+
+
 def test_bwd_tc_mask_with_causal_gqa_free(ctx):
     """mask + causal together, gradients against the oracle"""
     import umfa

@@ -55,6 +55,9 @@ struct BwdTcParams {
   const void* mask;
   int mask_kind, mask_scalar;
   long long mask_sb, mask_sh, mask_sq;
+  // dense 1- / 2-byte masks: 128 x 128 tiles staged in shared memory by TMA (tm over [MB, MH, Sq, Skv], tc::make_mask_map)
+  CUtensorMap tm;
+  int mask_tma;
   // visible-tile lists under an external mask (null = walk the whole causal / window range):
   //   dQ kernel:  per (mask batch, mask head, 256-row query block) the KV tiles with a visible element   [lists][m_nkt]
   //   dK/dV kernel (H == Hkv only): per (mask batch, mask head, KV tile) the 128-row query tiles           [listsT][2 m_nqb]
@@ -137,15 +140,77 @@ __device__ __forceinline__ void mask_terms32(const BwdTcParams& p, long long off
   }
 }
 
-template <int D>
+template <int D, bool STAGED = false>
 struct BCfg {
   static constexpr int kTile = 128 * D * 2;
   static constexpr int kChunks = D / 64;
   static constexpr int kChunkBytes = 128 * 128;
-  static constexpr int kRA = 3, kRB = 2;                         // ring depths: A = operand used last (Q / K), B = dO / V
+  // ring depths: A = operand used last (Q / K), B = dO / V.  STAGED (external mask tiles in shared memory): the 32 KB mask tile
+  // takes the place of the second B stage at D = 128 (dO_i / V_j have one reader group per step and a whole step to reload)
+  static constexpr int kRA = 3, kRB = (STAGED && D == 128) ? 1 : 2;
+  static constexpr int kMaskBytes = STAGED ? 128 * 128 * 2 : 0;  // one 128 x 128 tile of 16-bit terms (bool bytes use half)
   static constexpr int kStatBytes = 2 * 2 * 128 * 4;             // [slot][L|D][128], own 2-deep ring
-  static constexpr int kSmem = (2 + kRA + kRB) * kTile + kStatBytes + 256 + 512;   // D = 128: 232192 of 232448 B
+  static constexpr int kSmem = (2 + kRA + kRB) * kTile + kMaskBytes + kStatBytes + 256 + 512;   // D = 128: 232192 of 232448 B
+  static_assert(kSmem <= 232448, "shared memory budget of one CTA");
 };
+
+// Mask terms (log2 units, -inf = hidden) of one staged tile.  The tile sits in shared memory as TMA delivered it: rows = queries,
+// 128 bytes of keys per row and chunk (16-bit terms: two chunks of 64 keys, 16 KB apart; bool bytes: one chunk of 128 keys),
+// 16-byte unit j of row r at j ^ (r & 7).
+// row-owner read (dQ kernel): the 64 keys [64 half, 64 half + 64) of query row `row`
+__device__ __forceinline__ void staged_terms_row(const BwdTcParams& p, uint32_t tile, int row, int half, float* mt) {
+  const uint32_t sw = (uint32_t)(row & 7);
+  if (p.mask_kind == kMaskBool) {
+    const uint32_t line = tile + (uint32_t)row * 128u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f0, f1, f2, f3;
+      ptx::ld_shared_v4(line + (((uint32_t)(4 * half + j) ^ sw) << 4), f0, f1, f2, f3);
+      const uint32_t w4[4] = {__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)};
+#pragma unroll
+      for (int k = 0; k < 16; ++k) mt[16 * j + k] = ((w4[k >> 2] >> (8 * (k & 3))) & 0xffu) ? 0.f : -CUDART_INF_F;
+    }
+  } else {
+    const uint32_t line = tile + (uint32_t)half * 16384u + (uint32_t)row * 128u;
+    const bool bf = p.mask_scalar == kMaskBF16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f0, f1, f2, f3;
+      ptx::ld_shared_v4(line + (((uint32_t)j ^ sw) << 4), f0, f1, f2, f3);
+      const uint32_t w4[4] = {__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float lo, hi;
+        if (bf) { lo = __uint_as_float(w4[k] << 16); hi = __uint_as_float(w4[k] & 0xffff0000u); }
+        else { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[k])); lo = f.x; hi = f.y; }
+        mt[8 * j + 2 * k] = lo * kLog2e;
+        mt[8 * j + 2 * k + 1] = hi * kLog2e;
+      }
+    }
+  }
+}
+// column-owner read (dK/dV kernel): key column `col` of the 64 query rows [64 half, 64 half + 64); the 32 lanes of a warp read 32
+// neighbouring keys of one row per request (64 or 32 consecutive bytes: no bank conflicts)
+__device__ __forceinline__ void staged_terms_col(const BwdTcParams& p, uint32_t tile, int col, int half, float* mt) {
+  if (p.mask_kind == kMaskBool) {
+    const uint32_t unit = (uint32_t)(col >> 4), byte = (uint32_t)(col & 15);
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      const uint32_t q = (uint32_t)(64 * half + i);
+      mt[i] = ptx::ld_shared_u8(tile + q * 128u + ((unit ^ (q & 7u)) << 4) + byte) ? 0.f : -CUDART_INF_F;
+    }
+  } else {
+    const uint32_t chunk = tile + (uint32_t)(col >> 6) * 16384u;
+    const uint32_t unit = (uint32_t)((col & 63) >> 3), byte = (uint32_t)(col & 7) * 2u;
+    const bool bf = p.mask_scalar == kMaskBF16;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      const uint32_t q = (uint32_t)(64 * half + i);
+      const uint32_t raw = ptx::ld_shared_u16(chunk + q * 128u + ((unit ^ (q & 7u)) << 4) + byte);
+      mt[i] = (bf ? __uint_as_float(raw << 16) : __half2float(__ushort_as_half((unsigned short)raw))) * kLog2e;
+    }
+  }
+}
 
 
 __device__ __forceinline__ void load_tile_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int row, int head, int b,
@@ -154,9 +219,10 @@ __device__ __forceinline__ void load_tile_4d(uint32_t dst, const CUtensorMap* m,
 }
 
 // ================================================================================================ dK / dV
-template <int D, bool BF16, bool MASKED = false>
+template <int D, bool BF16, int MASKED = 0>      // MASKED: 0 no external mask, 1 read in place, 2 tiles staged by TMA
 __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_constant__ BwdTcParams p) {
-  using C = BCfg<D>;
+  using C = BCfg<D, MASKED == 2>;
+  constexpr bool MT = MASKED == 2;
   constexpr int TILE = C::kTile, CHB = C::kChunkBytes;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -165,7 +231,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
   constexpr int RA = C::kRA, RB = C::kRB;
   auto sQ = [&](int s) { return base + (2 + s) * TILE; };            // ring A: Q_i (read by S^T_i first, dK_i last)
   auto sdO = [&](int s) { return base + (2 + RA + s) * TILE; };      // ring B: dO_i (dP^T_i, dV_i)
-  const uint32_t sStat = base + (2 + RA + RB) * TILE;
+  const uint32_t sMask = base + (2 + RA + RB) * TILE;                // MT: the staged mask tile of the current step
+  const uint32_t sStat = sMask + C::kMaskBytes;
   float* stat = reinterpret_cast<float*>(smem_raw + (sStat - raw));     // [stage][0: L, 1: D][128]
   const uint32_t sBar = sStat + C::kStatBytes;
   const uint32_t kv_full = sBar, s_full = sBar + 8, dp_full = sBar + 16, p_full = sBar + 24, ds_full = sBar + 32,
@@ -177,6 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
   auto stat_full = [&](int s) { return sBar + 144 + 8 * s; };
   auto stat_empty = [&](int s) { return sBar + 160 + 8 * s; };
   const uint32_t tmem_slot = sBar + 176;
+  const uint32_t mk_full = sBar + 184, mk_empty = sBar + 192;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
   const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
@@ -203,6 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
     for (int s = 0; s < RA; ++s) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
     for (int s = 0; s < RB; ++s) { mbar_init(do_full(s), 1); mbar_init(do_empty(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(stat_full(s), 2); mbar_init(stat_empty(s), 8); }
+    if constexpr (MT) { mbar_init(mk_full, 1); mbar_init(mk_empty, 8); }
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -223,12 +292,30 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
       mbar_arrive_expect_tx(kv_full, 2 * TILE);
       load_tile_4d(sK, &p.tk, kv_full, c0, hk, b, C::kChunks, CHB);
       load_tile_4d(sV, &p.tv, kv_full, c0, hk, b, C::kChunks, CHB);
+      int mc = 0;                                        // staged mask tiles requested
       for (int it = 0; it < n_it; ++it) {
         const int sa = it % RA, sb = it % RB;
         const int head = hk * group + it / nq, q0 = qtile_of(it) * 128;
         mbar_wait(q_empty(sa), ((it / RA) & 1) ^ 1);
         mbar_arrive_expect_tx(q_full(sa), TILE);
         load_tile_4d(sQ(sa), &p.tq, q_full(sa), q0, head, b, C::kChunks, CHB);
+        if constexpr (MT) {
+          // mask tile [queries of Q_i] x [this CTA's keys]: its buffer is free once the elementwise warps have read the previous
+          // one (at the start of their step), a whole step before this one is needed
+          if (!(qlist && (__ldg(qlist + it) & kTileNoMask))) {
+            if (mc > 0) mbar_wait(mk_empty, (mc - 1) & 1);
+            const int mh = p.mask_sh ? head : 0, mb = p.mask_sb ? b : 0;
+            if (p.mask_kind == kMaskBool) {
+              mbar_arrive_expect_tx(mk_full, 16384);
+              tma_load_4d(sMask, &p.tm, mk_full, c0, q0, mh, mb);
+            } else {
+              mbar_arrive_expect_tx(mk_full, 32768);
+              tma_load_4d(sMask, &p.tm, mk_full, c0, q0, mh, mb);
+              tma_load_4d(sMask + 16384, &p.tm, mk_full, c0 + 64, q0, mh, mb);
+            }
+            ++mc;
+          }
+        }
         mbar_wait(do_empty(sb), ((it / RB) & 1) ^ 1);
         mbar_arrive_expect_tx(do_full(sb), TILE);
         load_tile_4d(sdO(sb), &p.tdo, do_full(sb), q0, head, b, C::kChunks, CHB);
@@ -324,6 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
     const float c = p.c, scale = p.scale;
     const int qlo_r = p.causal ? key : 0;
     const int qhi_r = p.window >= 0 ? min(key + p.window, 1 << 30) : (1 << 30);
+    int mkc = 0;                                           // staged mask tiles consumed
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1;
       const int q0 = qtile_of(it) * 128 + half * 64;
@@ -339,6 +427,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
         if (qlist && (__ldg(qlist + it) & kTileNoMask)) {          // the mask is a no-op on this tile: nothing to load
 #pragma unroll
           for (int i = 0; i < 64; ++i) pv[i] = 0.f;
+        } else if constexpr (MT) {
+          // staged tile: rows past Sq / keys past Skv arrive as zeros (bool: hidden; additive: + 0 on rows whose L is +inf)
+          mbar_wait(mk_full, mkc & 1);
+          ++mkc;
+          staged_terms_col(p, sMask, row, half, pv);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(mk_empty);
         } else {
           const int head = hk * group + it / nq;
 #pragma unroll
@@ -472,9 +567,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_tc_kernel(const __grid_co
 }
 
 // ================================================================================================ dQ
-template <int D, bool BF16, bool MASKED = false>
+template <int D, bool BF16, int MASKED = 0>
 __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_constant__ BwdTcParams p) {
-  using C = BCfg<D>;
+  using C = BCfg<D, MASKED == 2>;
+  constexpr bool MT = MASKED == 2;
   constexpr int TILE = C::kTile, CHB = C::kChunkBytes;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -483,7 +579,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
   constexpr int RA = C::kRA, RB = C::kRB;
   auto sK = [&](int s) { return base + (2 + s) * TILE; };            // ring A: K_j (S_j first, dQ_j last)
   auto sV = [&](int s) { return base + (2 + RA + s) * TILE; };       // ring B: V_j (dP_j only)
-  const uint32_t sBar = base + (2 + RA + RB) * TILE;
+  const uint32_t sMask = base + (2 + RA + RB) * TILE;                // MT: the staged mask tile of the current step
+  const uint32_t sBar = sMask + C::kMaskBytes;
   const uint32_t q_full = sBar, dp_full = sBar + 8, ds_full = sBar + 16, acc_full = sBar + 24;
   auto s_full = [&](int u) { return sBar + 32 + 8 * u; };
   auto k_full = [&](int s) { return sBar + 48 + 8 * s; };
@@ -491,6 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
   auto v_full = [&](int s) { return sBar + 112 + 8 * s; };
   auto v_empty = [&](int s) { return sBar + 128 + 8 * s; };
   const uint32_t tmem_slot = sBar + 144;
+  const uint32_t mk_full = sBar + 152, mk_empty = sBar + 160;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
   const int it_q = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;     // heavy tiles first
@@ -516,6 +614,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
     for (int s = 0; s < 2; ++s) mbar_init(s_full(s), 1);
     for (int s = 0; s < RA; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
     for (int s = 0; s < RB; ++s) { mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+    if constexpr (MT) { mbar_init(mk_full, 1); mbar_init(mk_empty, 8); }
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -535,11 +634,27 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
       mbar_arrive_expect_tx(q_full, 2 * TILE);
       load_tile_4d(sQ, &p.tq, q_full, r0, h, b, C::kChunks, CHB);
       load_tile_4d(sdO, &p.tdo, q_full, r0, h, b, C::kChunks, CHB);
+      int mc = 0;                                        // staged mask tiles requested
       for (int it = 0; it < n; ++it) {
         const int sa = it % RA, sb = it % RB;
         mbar_wait(k_empty(sa), ((it / RA) & 1) ^ 1);
         mbar_arrive_expect_tx(k_full(sa), TILE);
         load_tile_4d(sK(sa), &p.tk, k_full(sa), ktile_of(it) * 128, hk, b, C::kChunks, CHB);
+        if constexpr (MT) {
+          if (!(klist && (__ldg(klist + it) & kTileNoMask))) {       // mask tile [this CTA's queries] x [keys of K_j]
+            if (mc > 0) mbar_wait(mk_empty, (mc - 1) & 1);
+            const int mh = p.mask_sh ? h : 0, mb = p.mask_sb ? b : 0, kc0 = ktile_of(it) * 128;
+            if (p.mask_kind == kMaskBool) {
+              mbar_arrive_expect_tx(mk_full, 16384);
+              tma_load_4d(sMask, &p.tm, mk_full, kc0, r0, mh, mb);
+            } else {
+              mbar_arrive_expect_tx(mk_full, 32768);
+              tma_load_4d(sMask, &p.tm, mk_full, kc0, r0, mh, mb);
+              tma_load_4d(sMask + 16384, &p.tm, mk_full, kc0 + 64, r0, mh, mb);
+            }
+            ++mc;
+          }
+        }
         mbar_wait(v_empty(sb), ((it / RB) & 1) ^ 1);
         mbar_arrive_expect_tx(v_full(sb), TILE);
         load_tile_4d(sV(sb), &p.tv, v_full(sb), ktile_of(it) * 128, hk, b, C::kChunks, CHB);
@@ -610,6 +725,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
     }
     const int chi = p.causal ? min(p.Skv - 1, r) : p.Skv - 1;      // visible keys of this row: [clo, chi]
     const int clo = p.window >= 0 ? max(0, r - p.window) : 0;
+    int mkc = 0;                                           // staged mask tiles consumed
     for (int it = 0; it < n; ++it) {
       const int u = it & 1;
       const int k0 = ktile_of(it) * 128 + half * 64;
@@ -621,6 +737,12 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_tc_kernel(const __grid_con
         if (klist && (__ldg(klist + it) & kTileNoMask)) {
 #pragma unroll
           for (int i = 0; i < 64; ++i) pv[i] = 0.f;
+        } else if constexpr (MT) {
+          mbar_wait(mk_full, mkc & 1);
+          ++mkc;
+          staged_terms_row(p, sMask, row, half, pv);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(mk_empty);
         } else {
 #pragma unroll
           for (int ch = 0; ch < 2; ++ch) {
@@ -758,21 +880,22 @@ cudaError_t ensure_smem(K kern, int bytes, bool& done) {
   return e;
 }
 
-template <int D, bool BF16, bool MASKED>
+template <int D, bool BF16, int MASKED>
 cudaError_t launch_bwd_m(const BwdTcParams& prm, int B, bool want_dq, bool want_dkv, cudaStream_t st) {
   static bool a_set = false, b_set = false;
+  constexpr int kSmem = BCfg<D, MASKED == 2>::kSmem;
   cudaError_t e;
   if (want_dkv) {
-    if ((e = ensure_smem(bwd_dkv_tc_kernel<D, BF16, MASKED>, BCfg<D>::kSmem, a_set)) != cudaSuccess) return e;
+    if ((e = ensure_smem(bwd_dkv_tc_kernel<D, BF16, MASKED>, kSmem, a_set)) != cudaSuccess) return e;
     dim3 grid((prm.Skv + 127) / 128, prm.Hkv, B);
-    bwd_dkv_tc_kernel<D, BF16, MASKED><<<grid, kThreads, BCfg<D>::kSmem, st>>>(prm);
+    bwd_dkv_tc_kernel<D, BF16, MASKED><<<grid, kThreads, kSmem, st>>>(prm);
     ++g_launch_count;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   if (want_dq) {
-    if ((e = ensure_smem(bwd_dq_tc_kernel<D, BF16, MASKED>, BCfg<D>::kSmem, b_set)) != cudaSuccess) return e;
+    if ((e = ensure_smem(bwd_dq_tc_kernel<D, BF16, MASKED>, kSmem, b_set)) != cudaSuccess) return e;
     dim3 grid((prm.Sq + 127) / 128, prm.H, B);
-    bwd_dq_tc_kernel<D, BF16, MASKED><<<grid, kThreads, BCfg<D>::kSmem, st>>>(prm);
+    bwd_dq_tc_kernel<D, BF16, MASKED><<<grid, kThreads, kSmem, st>>>(prm);
     ++g_launch_count;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
@@ -781,8 +904,9 @@ cudaError_t launch_bwd_m(const BwdTcParams& prm, int B, bool want_dq, bool want_
 
 template <int D, bool BF16>
 cudaError_t launch_bwd(const BwdTcParams& prm, int B, bool want_dq, bool want_dkv, cudaStream_t st) {
-  return prm.mask ? launch_bwd_m<D, BF16, true>(prm, B, want_dq, want_dkv, st)
-                  : launch_bwd_m<D, BF16, false>(prm, B, want_dq, want_dkv, st);
+  if (prm.mask && prm.mask_tma) return launch_bwd_m<D, BF16, 2>(prm, B, want_dq, want_dkv, st);
+  return prm.mask ? launch_bwd_m<D, BF16, 1>(prm, B, want_dq, want_dkv, st)
+                  : launch_bwd_m<D, BF16, 0>(prm, B, want_dq, want_dkv, st);
 }
 
 }  // namespace
@@ -844,6 +968,7 @@ cudaError_t launch_bwd_tc(const AttnParams& p, cudaStream_t st) {
     prm.mask = p.mask; prm.mask_kind = p.mask_kind; prm.mask_scalar = p.mask_scalar;
     prm.mask_sb = p.mask_sb; prm.mask_sh = p.mask_sh; prm.mask_sq = p.mask_sq;
   }
+  prm.mask_tma = (prm.mask && tc::make_mask_map(&prm.tm, p)) ? 1 : 0;    // dense 1- / 2-byte masks: tiles staged by TMA
   prm.ktiles = prm.kcounts = prm.qtiles = prm.qcounts = nullptr; prm.m_nqb = prm.m_nkt = 0;
   cudaError_t e;
   if (prm.mask && p.mask_tile_scratch && bwd_tc_mask_scratch_bytes(p)) {
@@ -876,7 +1001,8 @@ cudaError_t launch_bwd_tc(const AttnParams& p, cudaStream_t st) {
   if (Dk != p.D && !prm.g_tma) return cudaErrorNotSupported;
   if (Dk == 128) e = bf ? launch_bwd<128, true>(prm, p.B, want_dq, want_dkv, st) : launch_bwd<128, false>(prm, p.B, want_dq, want_dkv, st);
   else e = bf ? launch_bwd<64, true>(prm, p.B, want_dq, want_dkv, st) : launch_bwd<64, false>(prm, p.B, want_dq, want_dkv, st);
-  if (prm.mask) g_last_kernel = Dk == 128 ? (bf ? "bwd_tc_bf16_d128_mask" : "bwd_tc_fp16_d128_mask") : (bf ? "bwd_tc_bf16_d64_mask" : "bwd_tc_fp16_d64_mask");
+  if (prm.mask && prm.mask_tma) g_last_kernel = Dk == 128 ? (bf ? "bwd_tc_bf16_d128_tma_mask" : "bwd_tc_fp16_d128_tma_mask") : (bf ? "bwd_tc_bf16_d64_tma_mask" : "bwd_tc_fp16_d64_tma_mask");
+  else if (prm.mask) g_last_kernel = Dk == 128 ? (bf ? "bwd_tc_bf16_d128_mask" : "bwd_tc_fp16_d128_mask") : (bf ? "bwd_tc_bf16_d64_mask" : "bwd_tc_fp16_d64_mask");
   else g_last_kernel = Dk == 128 ? (bf ? "bwd_tc_bf16_d128" : "bwd_tc_fp16_d128") : (bf ? "bwd_tc_bf16_d64" : "bwd_tc_fp16_d64");
   return e;
 }

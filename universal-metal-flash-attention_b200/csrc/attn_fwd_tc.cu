@@ -50,11 +50,12 @@ using namespace ptx;
 
 constexpr int kThreads = 384;           // warpgroups: softmax 0, softmax 1, {MMA 0, TMA, MMA 1, idle}
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.f;     // log2 units
 constexpr int kTileNoMask = 1 << 30;          // flag bit in a visible-tile list entry
 constexpr int kParts = 4;                    // P hand-off granularity: 32 keys = 16 packed TMEM columns
 
-template <int D, int MODE>
+template <int D, int MODE, int MASKED = 0>      // MASKED: 0 no external mask, 1 read in place, 2 staged in shared memory
 struct Cfg {
   static constexpr bool kI4 = MODE == kFwdI4 || MODE == kFwdI4F8;    // Q / K arrive as packed int4 and are unpacked in shared memory
   static constexpr bool kF8 = MODE == kFwdI8F8 || MODE == kFwdI4F8;  // int8 Q K^T, e4m3 P V
@@ -69,13 +70,29 @@ struct Cfg {
   static constexpr int kVTile = kVChunks * kChunkBytes;
   static constexpr int kStage = kVTile;                              // ring stage (K tiles may use part of it)
   static constexpr int kSPS = kSplit ? 4 : kWide ? 3 : 2;            // ring stages per KV step (split: K_lo, K_hi, V_hi, V_lo; wide: K_a, K_b, V_half)
-  static constexpr int kStages = (kSplit || kWide) ? 3 : (D == 128 && !kF8) ? 5 : 10;   // split / wide: 2 x 64 KB of Q leave room for 3 x 32 KB
-  static constexpr int kBarBytes = 112 + 16 * kStages + 16 + 32 + 64; // + q_empty, o_empty, + raw-tile barriers (int4)
+  // MASKED == 2 (16-bit operand modes only: the quantised entry points take fp32 masks): the external mask is staged in shared
+  // memory, two 32 KB tiles fed by TMA (see the mask producer in warp 11).
+  // Every masked kernel except the int4 ones runs on a shallow ring -- 96 KB instead of 160 KB: the unmasked kernel loses
+  // nothing with it (0.216 vs 0.2145 ms, profiles/r02bb_*), the staged tiles need the room, and the in-place mask reads gain
+  // 64 KB of L1 (dense fp32 [1, 1, S, S] mask: 0.58 -> 0.49 ms)
+  static constexpr bool kMaskTma = MASKED == 2 && (MODE == kFwdF16 || MODE == kFwdBF16);
+  static constexpr int kMaskTile = 128 * 128 * 2;                    // one query tile x 128 keys of 16-bit terms (bool bytes use half)
+  static constexpr bool kShallow = MASKED != 0 && !kI4;
+#ifdef MFA_FORCE_NS3                                                 // experiment: the unmasked kernel on the shallow ring
+  static constexpr int kDeep = 3;
+#else
+  static constexpr int kDeep = 5;
+#endif
+  static constexpr int kStages = (kSplit || kWide) ? 3               // split / wide: 2 x 64 KB of Q leave room for 3 x 32 KB
+                               : (D == 128 && !kF8) ? (kShallow ? 3 : kDeep) : (kShallow ? 6 : 10);
+  static constexpr int kBarBytes = 112 + 16 * kStages + 16 + 32 + 64 + 32; // + q_empty, o_empty, + raw-tile barriers (int4), + mask tile barriers
   // int4: raw (packed) tiles as TMA delivers them -- a 3-deep ring of K tiles + one Q tile, 128 rows x 64 bytes each -- and
   // the per-row sums of the Q codes (2 x 128 ints)
   static constexpr int kRawTile = 128 * 64, kRawStages = 3;
   static constexpr int kRawBytes = kI4 ? (kRawStages + 1) * kRawTile + 1024 + 128 : 0;
-  static constexpr int kSmem = 2 * kQTile + kStages * kStage + kBarBytes + kRawBytes + 1024;
+  static constexpr int kMaskBytes = kMaskTma ? 2 * kMaskTile + 1024 : 0;
+  static constexpr int kSmem = 2 * kQTile + kStages * kStage + kBarBytes + kRawBytes + kMaskBytes + 1024;
+  static_assert(kSmem <= 232448, "shared memory budget of one CTA");
 };
 
 // 2^x for a pair of x <= ~8 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max rel err 8.6e-5),
@@ -84,7 +101,9 @@ struct Cfg {
 __device__ __forceinline__ f32x2 exp2_poly2(f32x2 x) {
   float x0, x1;
   unpack2(x, x0, x1);
-  x = pack2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  // clamp at -127: a hidden element (x = -inf) gets r = -127, f = 0, p = 1.0 exactly, and 0x3F800000 + (-127 << 23) wraps to +0.0 --
+  // an EXACT zero weight, so rows that are hidden completely keep l == 0; x in (-127, -126) gives a harmless denormal
+  x = pack2(fmaxf(x0, -127.f), fmaxf(x1, -127.f));
   const f32x2 magic = pack2(12582912.f, 12582912.f);                  // 1.5 * 2^23: low mantissa bits = floor(x)
   const f32x2 xr = add2_rm(x, magic);
   const f32x2 f = sub2(x, sub2(xr, magic));                           // [0, 1)
@@ -171,15 +190,32 @@ __device__ __forceinline__ void exp_phase(const float* s, float a0, float a1, fl
   unpack2(add2(acc[1][0], acc[1][1]), x0, x1); sum_hi = x0 + x1;
 }
 
-// POLY = n in 0..4: n of every 8 element pairs go through exp2_poly2 instead of MUFU.EX2 (only on tiles without masking,
-// so masked elements always get an exact zero weight).
+// Additive 16-bit mask terms of two neighbouring keys (one 32-bit word) onto their scores, in natural-log units:
+//   s <- s * cn + m,   cn = softmax scale (the exponent's multiplier becomes log2 e for the rest of the step)
+// one packed FMA per pair plus the two ALU ops that widen the terms (the first version spent 3 instructions per element on
+// fmaf(s, a, fmaf(m, log2 e, 0)) and a per-element format select; the softmax warps' issue slots are what bounds this kernel)
+template <bool BF>
+__device__ __forceinline__ void add_mask_pair(float& s0, float& s1, uint32_t w, f32x2 cn2) {
+  float lo, hi;
+  if constexpr (BF) {
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xffff0000u);
+  } else {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = f.x; hi = f.y;
+  }
+  unpack2(fma2(pack2(s0, s1), cn2, pack2(lo, hi)), s0, s1);
+}
+
+// POLY = n in 0..4: n of every 8 element pairs go through exp2_poly2 instead of MUFU.EX2 (on masked tiles too: the polynomial
+// returns an exact zero for hidden elements, see its clamp).
 // MASKED: an external mask (bool or additive, SURVEY A4 with the PyTorch placement softmax(scale * QK^T + mask)) is read by
 // the softmax warps straight from global memory -- each thread owns one row, so it reads the 128 mask values of its row
 // and tile with 32-byte (one sector) loads; no dense fp32 expansion pass like the reference's mfa_prepare_mask (MFABridge.swift:153-243).
-template <int D, int MODE, int POLY, bool TR = false, bool MASKED = false>
+template <int D, int MODE, int POLY, bool TR = false, int MASKED = 0>      // MASKED: 0 none, 1 read in place, 2 staged by TMA
 __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_constant__ FwdTcParams p) {
-  using C = Cfg<D, MODE>;
-  constexpr bool I8 = C::kI8, F8 = C::kF8, SPLIT = C::kSplit, I4 = C::kI4, WIDE = C::kWide;
+  using C = Cfg<D, MODE, MASKED>;
+  constexpr bool I8 = C::kI8, F8 = C::kF8, SPLIT = C::kSplit, I4 = C::kI4, WIDE = C::kWide, MT = C::kMaskTma;
   constexpr int PF = SPLIT ? 3 : F8 ? 2 : ((MODE == kFwdF16 || MODE == kFwdWideF16) ? 0 : 1);  // format of P (and of V): f16 / bf16 / e4m3 / f16 (hi, lo) pairs
   // e4m3 P: the exponent carries +kShift so that P' = 2^kShift P uses the format's range (max 448), and the running max
   // may lag the true one by kThr = 2 only (P' <= 2^8); 16-bit P: lag 2^8 (bf16 / fp32-range exponent, f16 P <= 256 < 65504)
@@ -207,6 +243,10 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
   auto raw_empty = [&](int s) { return sBar + 112 + 16 * NS + 72 + 8 * s; };
   const uint32_t qraw_full = sBar + 112 + 16 * NS + 96, qraw_empty = sBar + 112 + 16 * NS + 104;
   const uint32_t sRawK = (sBar + C::kBarBytes + 127u) & ~127u, sRawQ = sRawK + NR * RAW, sQsum = sRawQ + RAW;
+  // staged external mask (MT): one 128 x 128 tile per query tile, 128-byte swizzled like the operand tiles
+  auto mk_full = [&](int t) { return sBar + 112 + 16 * NS + 112 + 8 * t; };
+  auto mk_empty = [&](int t) { return sBar + 112 + 16 * NS + 128 + 8 * t; };
+  const uint32_t sMask = (sBar + C::kBarBytes + 1023u) & ~1023u;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
   // MFA_FWD_CTATRACE (debug build of the launch only): per-CTA wall-clock stamps written by thread 0
@@ -259,6 +299,9 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     if constexpr (I4) {
       for (int r = 0; r < NR; ++r) { mbar_init(raw_full(r), 1); mbar_init(raw_empty(r), 1); }
       mbar_init(qraw_full, 1); mbar_init(qraw_empty, 1);
+    }
+    if constexpr (MT) {
+      for (int t = 0; t < 2; ++t) { mbar_init(mk_full(t), 1); mbar_init(mk_empty(t), 4); }
     }
     fence_mbar_init();
   }
@@ -475,6 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     const uint32_t tS = tmem + lane_base + t * 128;
     const uint32_t tO = tmem + lane_base + 256 + t * D;
     int pc = 0, qc = 0;                                    // KV steps / items done by this tile (barrier phases)
+    int mkc = 0;                                           // staged mask tiles consumed by this tile
     if (p.pingpong && t == 1) named_bar_arrive(2, 256);    // the first turn belongs to tile 0
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
     const Item im = decode(w);
@@ -612,7 +656,52 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           for (int i = 0; i < 128; ++i) su[i] = su[i] * smul + sadd;
         }
         if (TR && tr) tr[15] = clock64();
-        if (MASKED && !mask_noop) {
+        if (MT && !mask_noop) {
+          if constexpr (MT) {
+            // the mask tile of this (step, query tile) is in shared memory (TMA, 128-byte swizzle: 16-byte unit j of row r sits
+            // at j ^ (r & 7), so the eight rows of a quarter warp read eight different units -- no bank conflicts); rows / keys
+            // past the tensor's extent arrive as zeros (bool: hidden; additive: + 0, the range rule below hides them)
+            mbar_wait(mk_full(t), mkc & 1);
+            ++mkc;
+            const uint32_t mrow = sMask + (uint32_t)t * C::kMaskTile + (uint32_t)row * 128u;
+            const uint32_t sw = (uint32_t)(row & 7);
+            if (p.mask_kind == kMaskBool) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {                         // 16 keys per unit
+                float f0, f1, f2, f3;
+                ld_shared_v4(mrow + (((uint32_t)j ^ sw) << 4), f0, f1, f2, f3);
+                const uint32_t w4[4] = {__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)};
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                  if (((w4[k >> 2] >> (8 * (k & 3))) & 0xffu) == 0) s[16 * j + k] = -CUDART_INF_F;
+              }
+            } else {
+              // (staged masks exist for the 16-bit operand modes only: a0 == a1 == scale * log2 e, no integer offsets)
+              const float cn = a0 * kLn2;
+              const f32x2 cn2 = pack2(cn, cn);
+              auto apply = [&](auto is_bf) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {                       // 64-key half = one 16 KB chunk
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {                     // 8 keys per unit
+                    float f0, f1, f2, f3;
+                    ld_shared_v4(mrow + (uint32_t)g * 16384u + (((uint32_t)j ^ sw) << 4), f0, f1, f2, f3);
+                    const uint32_t w4[4] = {__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      const int i = 64 * g + 8 * j + 2 * k;
+                      add_mask_pair<decltype(is_bf)::value>(s[i], s[i + 1], w4[k], cn2);
+                    }
+                  }
+                }
+              };
+              if (p.mask_scalar == kMaskBF16) apply(std::true_type{}); else apply(std::false_type{});
+              a0 = a1 = kLog2e;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(mk_empty(t));                // the producer may refill this tile's buffer
+          }
+        } else if (!MT && MASKED && !mask_noop) {
           const int rq = min(r, p.Sq - 1);
           const long long eoff = (long long)b * p.mask_sb + (long long)h * p.mask_sh + (long long)rq * p.mask_sq + c0;
           const int ncol = min(128, p.Skv - c0);
@@ -634,9 +723,22 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
             }
           } else {
             // additive: fold the scale now (s <- s a_h + mask log2 e), the multipliers become 1 for the rest of the step
+            bool mask_folded = false;
             if (p.mask_scalar == kMaskF32) {
               const float* mp = reinterpret_cast<const float*>(p.mask) + eoff;
-              if (ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 31) == 0) {
+              if (!I8 && ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 31) == 0) {
+                const float cn = a0 * kLn2;                       // s <- s * scale + m, one FMA per element (see add_mask_pair)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {                    // 32 bytes = one sector per request
+                  uint32_t w[8];
+                  ldg256(mp + 8 * c, w);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) s[8 * c + k] = fmaf(s[8 * c + k], cn, __uint_as_float(w[k]));
+                }
+                a0 = a1 = kLog2e;
+                cb0 = cb1 = 0.f;
+                mask_folded = true;
+              } else if (ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 31) == 0) {
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {                    // 32 bytes = one sector per request
                   uint32_t w[8];
@@ -656,7 +758,29 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
               auto widen = [&](uint32_t bits) {
                 return bf ? __uint_as_float(bits << 16) : __half2float(__ushort_as_half((unsigned short)bits));
               };
-              if (ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 31) == 0) {
+              if (!I8 && ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 31) == 0) {
+                // same arithmetic as the staged route (bit-identical results): s <- s * scale + m in natural-log units
+                const float cn = a0 * kLn2;
+                const f32x2 cn2 = pack2(cn, cn);
+                auto apply = [&](auto is_bf) {
+#pragma unroll
+                  for (int g = 0; g < 2; ++g) {                   // 4 requests of 32 bytes in flight, then their 64 terms
+                    uint32_t w[4][8];
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) ldg256(mp + 16 * (4 * g + k4), w[k4]);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                      const int c = 4 * g + k4;
+#pragma unroll
+                      for (int k = 0; k < 8; ++k) add_mask_pair<decltype(is_bf)::value>(s[16 * c + 2 * k], s[16 * c + 2 * k + 1], w[k4][k], cn2);
+                    }
+                  }
+                };
+                if (bf) apply(std::true_type{}); else apply(std::false_type{});
+                a0 = a1 = kLog2e;
+                cb0 = cb1 = 0.f;
+                mask_folded = true;
+              } else if (ncol == 128 && (reinterpret_cast<uintptr_t>(mp) & 31) == 0) {
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {                     // 4 requests of 32 bytes in flight, then their 64 terms
                   uint32_t w[4][8];
@@ -679,8 +803,10 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
                   s[i] = fmaf(s[i], i < 64 ? a0 : a1, fmaf(i < ncol ? widen(__ldg(mp + i)) : 0.f, kLog2e, i < 64 ? cb0 : cb1));
               }
             }
-            a0 = a1 = 1.f;
-            cb0 = cb1 = 0.f;
+            if (!mask_folded) {
+              a0 = a1 = 1.f;
+              cb0 = cb1 = 0.f;
+            }
           }
         }
         const bool need_mask = (c0 < clo) || (c0 + 127 > chi);
@@ -737,7 +863,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
           else named_bar_sync(3, 256);
         }
         if (TR && tr) tr[2] = clock64();
-        if (POLY > 0 && !any_mask && (!MASKED || mask_noop)) exp_phase<PF, POLY, TR>(s, a0, a1, nk0, nk1, tS, p_part(t, 0), lane, sum_lo, sum_hi, tr);
+        if (POLY > 0) exp_phase<PF, POLY, TR>(s, a0, a1, nk0, nk1, tS, p_part(t, 0), lane, sum_lo, sum_hi, tr);
         else exp_phase<PF, 0, TR>(s, a0, a1, nk0, nk1, tS, p_part(t, 0), lane, sum_lo, sum_hi, tr);
         if (pingpong) {
           if (t == 0) named_bar_arrive(3, 256);
@@ -921,7 +1047,49 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_tc_kernel(const __grid_consta
     if (p.pingpong && t == 0) named_bar_sync(2, 256);      // take the credit nobody will use: the barriers end balanced
   }
   else {
-    reg_dealloc<kWg2Regs>();      // warp 11 (setmaxnreg is warpgroup-wide): idle, or the int4 converter
+    reg_dealloc<kWg2Regs>();      // warp 11 (setmaxnreg is warpgroup-wide): idle, the mask producer, or the int4 converter
+    if constexpr (MT) {
+      // ---------------------------------------------------------------- external mask through shared memory: dense masks
+      // ([., ., Sq, Skv] with 1- or 2-byte elements) come in by TMA, one 128 x 128 tile per (KV step, query tile), instead of
+      // being read row by row by the softmax warps (32 lines per warp request straight to L2: the L1 tag stage, one line per
+      // clock, bounded the masked forward at 2.7x the unmasked time -- profiles/r01p_bench_mask_fwd_bwd.json).  The buffer of
+      // a tile is refilled as soon as its four softmax warps have applied it, a whole KV step before it is needed again.
+      if (lane == 0) {
+        prefetch_tmap(&p.tm);
+        // the mask streams through once (up to GBs): evict-first keeps it from pushing the K / V tiles the other CTAs of a
+        // head re-read out of L2
+#ifdef MFA_MASK_NO_HINT
+        const uint64_t pol = l2_policy_evict_normal();
+#else
+        const uint64_t pol = l2_policy_evict_first();
+#endif
+        const bool one_byte = p.mask_kind == kMaskBool;
+        int mc[2] = {0, 0};
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+          const Item im = decode(w);
+          if (im.n == 0) continue;
+          const int mb = p.mask_sb ? im.b : 0, mh = p.mask_sh ? im.h : 0;
+          for (int it = 0; it < im.n; ++it) {
+            const int jt = tile_of(im, it);
+            if (jt & kTileNoMask) continue;
+            const int c0 = (jt & (kTileNoMask - 1)) * 128;
+            for (int t = 0; t < im.nt; ++t) {
+              if (mc[t] > 0) mbar_wait(mk_empty(t), (mc[t] - 1) & 1);
+              const uint32_t dst = sMask + (uint32_t)t * C::kMaskTile;
+              if (one_byte) {
+                mbar_arrive_expect_tx(mk_full(t), 16384);
+                tma_load_4d_hint(dst, &p.tm, mk_full(t), c0, im.r0 + t * 128, mh, mb, pol);
+              } else {
+                mbar_arrive_expect_tx(mk_full(t), 32768);
+                tma_load_4d_hint(dst, &p.tm, mk_full(t), c0, im.r0 + t * 128, mh, mb, pol);
+                tma_load_4d_hint(dst + 16384, &p.tm, mk_full(t), c0 + 64, im.r0 + t * 128, mh, mb, pol);
+              }
+              ++mc[t];
+            }
+          }
+        }
+      }
+    }
     if constexpr (I4) {
       // ---------------------------------------------------------------- int4 -> int8 in shared memory (north_star item 2;
       // the reference dequantises on load as well: MFA/GEMM/GEMMHeaders.swift:757-772).  TMA delivers the packed tile (128 rows x
@@ -1157,17 +1325,27 @@ cudaError_t launch_traced(FwdTcParams prm, dim3 grid, cudaStream_t st, const cha
   return e;
 }
 
-template <int D, int MODE, int POLY>
-cudaError_t launch_masked_k(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
+template <int D, int MODE, int POLY, int MASKED>
+cudaError_t launch_masked_v(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = fwd_tc_kernel<D, MODE, POLY, false, true>;
+  auto kern = fwd_tc_kernel<D, MODE, POLY, false, MASKED>;
+  constexpr int kSmem = Cfg<D, MODE, MASKED>::kSmem;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D, MODE>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<grid, kThreads, Cfg<D, MODE>::kSmem, st>>>(prm);
+  kern<<<grid, kThreads, kSmem, st>>>(prm);
   return cudaGetLastError();
+}
+
+// dense 1- / 2-byte masks take the instantiation that stages mask tiles in shared memory (where the mode has one)
+template <int D, int MODE, int POLY>
+cudaError_t launch_masked_k(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
+  if constexpr (Cfg<D, MODE, 2>::kMaskTma) {
+    if (prm.mask_tma) return launch_masked_v<D, MODE, POLY, 2>(prm, grid, st);
+  }
+  return launch_masked_v<D, MODE, POLY, 1>(prm, grid, st);
 }
 
 // masked kernels come in two exp2 flavours only: all MUFU, or the default polynomial share on tiles the mask leaves alone
@@ -1178,8 +1356,8 @@ cudaError_t launch_masked(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
 
 template <int D, int MODE>
 cudaError_t launch(const FwdTcParams& prm, dim3 grid, cudaStream_t st) {
-#ifdef MFA_DEV_ONE        // compile-time experiment builds: one instantiation only
-  if constexpr (D == 128 && MODE == kFwdBF16) return launch_k<D, MODE, 3>(prm, grid, st);
+#ifdef MFA_DEV_ONE        // compile-time experiment builds: the D = 128 bf16 kernel (plain + masked) only
+  if constexpr (D == 128 && MODE == kFwdBF16) return prm.mask ? launch_masked_k<D, MODE, 3>(prm, grid, st) : launch_k<D, MODE, 3>(prm, grid, st);
   else return cudaErrorNotSupported;
 #else
   if (prm.mask) return launch_masked<D, MODE>(prm, grid, st);
@@ -1235,6 +1413,9 @@ cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm_in, int D, int mode, cud
                        !prm.causal && prm.window < 0 && items > sm_count() && !prm.trace;
   if (persist) prm.o_tma = 0;                    // the staging tile of the TMA-store epilogue aliases the operand ring
   dim3 grid((unsigned)(persist ? sm_count() : items), 1, 1);
+#ifdef MFA_DEV_ONE
+  return (D == 128 && mode == kFwdBF16) ? launch<128, kFwdBF16>(prm, grid, st) : cudaErrorNotSupported;
+#else
   if (mode == kFwdI8) return D == 128 ? launch<128, kFwdI8>(prm, grid, st) : cudaErrorInvalidValue;
   if (mode == kFwdI8F8) return D == 128 ? launch<128, kFwdI8F8>(prm, grid, st) : cudaErrorInvalidValue;
   if (mode == kFwdI4 || mode == kFwdI4F8) {       // packed int4 Q / K: default exp2 mix, or all-MUFU when the polynomial is off
@@ -1264,6 +1445,7 @@ cudaError_t launch_fwd_tc_kernel(const FwdTcParams& prm_in, int D, int mode, cud
   if (D == 128) return mode == kFwdBF16 ? launch<128, kFwdBF16>(prm, grid, st) : launch<128, kFwdF16>(prm, grid, st);
   if (D == 64) return mode == kFwdBF16 ? launch<64, kFwdBF16>(prm, grid, st) : launch<64, kFwdF16>(prm, grid, st);
   return cudaErrorInvalidValue;
+#endif
 }
 
 // external masks the tensor-core forward reads itself: keys contiguous (the row of a tile is one 128-element run)
@@ -1274,9 +1456,14 @@ bool fwd_tc_mask_ok(const AttnParams& p) {
 }
 
 void fwd_tc_set_mask(FwdTcParams& prm, const AttnParams& p) {
+  prm.mask_tma = 0;
   if (p.mask_kind == kMaskNone || !p.mask) return;
   prm.mask = p.mask; prm.mask_kind = p.mask_kind; prm.mask_scalar = p.mask_scalar;
   prm.mask_sb = p.mask_sb; prm.mask_sh = p.mask_sh; prm.mask_sq = p.mask_sq;
+  // dense masks (one row of terms per query row) with 1- or 2-byte elements are staged through shared memory by TMA
+  // (tc::make_mask_map); masks broadcast over the rows (key padding) and fp32 terms (64 KB per tile) keep the in-place reads
+  if (tc::make_mask_map(&prm.tm, p))
+    prm.mask_tma = 1;
 }
 
 namespace {
@@ -1396,7 +1583,9 @@ cudaError_t launch_fwd_tc(const AttnParams& p, cudaStream_t st) {
     return e;
   }
   cudaError_t e = launch_fwd_tc_kernel(prm, Dk, bf ? kFwdBF16 : kFwdF16, st, p.B);
-  if (Dk == 128) g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d128_mask" : "fwd_tc_fp16_d128_mask") : (bf ? "fwd_tc_bf16_d128" : "fwd_tc_fp16_d128");
+  if (prm.mask && prm.mask_tma)       // dense 1- / 2-byte mask staged in shared memory by TMA
+    g_last_kernel = Dk == 128 ? (bf ? "fwd_tc_bf16_d128_tma_mask" : "fwd_tc_fp16_d128_tma_mask") : (bf ? "fwd_tc_bf16_d64_tma_mask" : "fwd_tc_fp16_d64_tma_mask");
+  else if (Dk == 128) g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d128_mask" : "fwd_tc_fp16_d128_mask") : (bf ? "fwd_tc_bf16_d128" : "fwd_tc_fp16_d128");
   else g_last_kernel = prm.mask ? (bf ? "fwd_tc_bf16_d64_mask" : "fwd_tc_fp16_d64_mask") : (bf ? "fwd_tc_bf16_d64" : "fwd_tc_fp16_d64");
   ++g_launch_count;
   return e;

@@ -409,35 +409,61 @@ cudaError_t launch_fwd_simt(const AttnParams& p, cudaStream_t st) {
 
 // Vector path: O fp32 and dO 16-bit, unit inner strides, D % 4 == 0, 16-byte aligned rows.  Each lane owns 4 adjacent
 // elements per 128-wide slice (float4 of O, 8 bytes of dO); HBM-bound: 6 bytes per element in, 4 bytes per row out.
-template <bool BF16>
-__global__ void dterm_vec_kernel(AttnParams p) {
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// A warp owns R consecutive rows and issues the loads of all of them before the first use: 24 R bytes in flight per lane
+// (one row per warp left the memory system at 0.53 of the HBM rate, profiles/r01f_*; 4 rows per warp: 0.84).
+template <bool BF16, int R>
+__global__ void __launch_bounds__(256) dterm_vec_kernel(AttnParams p) {
+  // grid = (row blocks of one (b, h), B * H): no 64-bit divisions on the way to the row pointers
+  const int s0 = (int)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R);
   const int lane = threadIdx.x & 31;
-  const int64_t rows = (int64_t)p.B * p.H * p.Sq;
-  if (row >= rows) return;
-  const int s = (int)(row % p.Sq);
-  const int64_t bh = row / p.Sq;
-  const int h = (int)(bh % p.H), b = (int)(bh / p.H);
-  const float* o = reinterpret_cast<const float*>(p.o.ptr) + b * p.o.sb + h * p.o.sh + s * p.o.ss;
-  const uint16_t* g = reinterpret_cast<const uint16_t*>(p.d_o.ptr) + b * p.d_o.sb + h * p.d_o.sh + s * p.d_o.ss;
-  float acc = 0.f;
+  if (s0 >= p.Sq) return;
+  const int h = (int)(blockIdx.y % (unsigned)p.H), b = (int)(blockIdx.y / (unsigned)p.H);
+  const int64_t row0 = ((int64_t)b * p.H + h) * p.Sq + s0;
+  const int64_t rows = row0 - s0 + p.Sq;                     // end of this (b, h)
+  const float* o[R];
+  const uint16_t* g[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int s = min(s0 + i, p.Sq - 1);                     // rows past the end repeat the last one (not written)
+    o[i] = reinterpret_cast<const float*>(p.o.ptr) + b * p.o.sb + h * p.o.sh + s * p.o.ss;
+    g[i] = reinterpret_cast<const uint16_t*>(p.d_o.ptr) + b * p.d_o.sb + h * p.d_o.sh + s * p.d_o.ss;
+  }
+  float acc[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) acc[i] = 0.f;
   for (int d = lane * 4; d < p.D; d += 128) {
-    const float4 ov = *reinterpret_cast<const float4*>(o + d);
-    const uint2 gv = *reinterpret_cast<const uint2*>(g + d);
-    float g0, g1, g2, g3;
-    if (BF16) {
-      g0 = __uint_as_float(gv.x << 16); g1 = __uint_as_float(gv.x & 0xffff0000u);
-      g2 = __uint_as_float(gv.y << 16); g3 = __uint_as_float(gv.y & 0xffff0000u);
-    } else {
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&gv.x));
-      const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&gv.y));
-      g0 = a.x; g1 = a.y; g2 = c.x; g3 = c.y;
+    float4 ov[R];
+    uint2 gv[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      ov[i] = *reinterpret_cast<const float4*>(o[i] + d);
+      gv[i] = *reinterpret_cast<const uint2*>(g[i] + d);
     }
-    acc = fmaf(ov.x, g0, acc); acc = fmaf(ov.y, g1, acc); acc = fmaf(ov.z, g2, acc); acc = fmaf(ov.w, g3, acc);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float g0, g1, g2, g3;
+      if (BF16) {
+        g0 = __uint_as_float(gv[i].x << 16); g1 = __uint_as_float(gv[i].x & 0xffff0000u);
+        g2 = __uint_as_float(gv[i].y << 16); g3 = __uint_as_float(gv[i].y & 0xffff0000u);
+      } else {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&gv[i].x));
+        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&gv[i].y));
+        g0 = a.x; g1 = a.y; g2 = c.x; g3 = c.y;
+      }
+      acc[i] = fmaf(ov[i].x, g0, acc[i]); acc[i] = fmaf(ov[i].y, g1, acc[i]);
+      acc[i] = fmaf(ov[i].z, g2, acc[i]); acc[i] = fmaf(ov[i].w, g3, acc[i]);
+    }
   }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (lane == 0) p.dterm[row] = acc * p.scale;
+  for (int i = 0; i < R; ++i) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+      if (row0 + i < rows) p.dterm[row0 + i] = acc[i] * p.scale;
+  }
 }
 
 cudaError_t launch_dterm(const AttnParams& p, cudaStream_t st) {
@@ -446,9 +472,17 @@ cudaError_t launch_dterm(const AttnParams& p, cudaStream_t st) {
   const bool vec = p.o_dtype == kF32 && (p.do_dtype == kBF16 || p.do_dtype == kF16) && p.o.sd == 1 && p.d_o.sd == 1 &&
                    (p.D % 4) == 0 && !(reinterpret_cast<uintptr_t>(p.o.ptr) & 15) && !(reinterpret_cast<uintptr_t>(p.d_o.ptr) & 7) &&
                    !((p.o.ss | p.o.sh | p.o.sb) & 3) && !((p.d_o.ss | p.d_o.sh | p.d_o.sb) & 3);
-  if (vec) {
-    if (p.do_dtype == kBF16) dterm_vec_kernel<true><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(p);
-    else dterm_vec_kernel<false><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(p);
+  if (vec && (int64_t)p.B * p.H <= 65535) {
+    // rows per warp (8 warps per block): 4 by default -- FLUX shape, 85 MB in: 24.0 us with 1 row per warp, 20.0 with 2,
+    // 15.5 us = 5.5 TB/s = 0.84 of the measured copy rate with 4 (profiles/r02be_launches_dterm*.csv); MFA_DTERM_ROWS = 1 | 2 | 4 | 8
+    static int kr = 0;
+    if (!kr) { const char* e = getenv("MFA_DTERM_ROWS"); kr = e ? atoi(e) : 4; if (kr != 1 && kr != 2 && kr != 4 && kr != 8) kr = 4; }
+    const dim3 nb((unsigned)((p.Sq + 8 * kr - 1) / (8 * kr)), (unsigned)(p.B * p.H));
+    const bool bf = p.do_dtype == kBF16;
+    if (kr == 8) { if (bf) dterm_vec_kernel<true, 8><<<nb, 256, 0, st>>>(p); else dterm_vec_kernel<false, 8><<<nb, 256, 0, st>>>(p); }
+    else if (kr == 4) { if (bf) dterm_vec_kernel<true, 4><<<nb, 256, 0, st>>>(p); else dterm_vec_kernel<false, 4><<<nb, 256, 0, st>>>(p); }
+    else if (kr == 2) { if (bf) dterm_vec_kernel<true, 2><<<nb, 256, 0, st>>>(p); else dterm_vec_kernel<false, 2><<<nb, 256, 0, st>>>(p); }
+    else { if (bf) dterm_vec_kernel<true, 1><<<nb, 256, 0, st>>>(p); else dterm_vec_kernel<false, 1><<<nb, 256, 0, st>>>(p); }
   } else {
     dterm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(p);
   }

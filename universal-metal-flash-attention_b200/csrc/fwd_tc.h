@@ -48,6 +48,10 @@ struct FwdTcParams {
   const void* mask;
   int mask_kind, mask_scalar;
   long long mask_sb, mask_sh, mask_sq;
+  // dense 1- / 2-byte masks: tiles staged in shared memory by TMA (tm over [MB, MH, Sq, Skv], box 128 bytes x 128 rows); only
+  // read by the MASKED instantiations of the modes that have the room (not int4 / split / wide)
+  CUtensorMap tm;
+  int mask_tma;
   // tile skipping under an external mask: per (mask batch, mask head, query block) a compacted list of the KV tiles that
   // hold at least one visible element (built by mask_tiles_kernel right before the launch), or null
   const int* mtiles;       // [lists][m_nkt]

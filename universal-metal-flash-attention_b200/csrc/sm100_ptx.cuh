@@ -119,6 +119,25 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap
       : "memory");
 }
 
+// the same load with an L2 eviction policy (streams that are read once: evict-first)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_4d_hint(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                                 int c3, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+      : "memory");
+}
+
 // 5-D tiled load (ring attention: c4 = visiting slot)
 __device__ __forceinline__ void tma_load_5d(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
@@ -169,6 +188,16 @@ __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
 __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_shared_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_shared_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
 

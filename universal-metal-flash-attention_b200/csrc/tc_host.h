@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.h"
@@ -96,6 +97,31 @@ inline bool view_ok(const TensorView& t, int64_t Hn, int64_t B, int elem_bytes =
   if (Hn > 1 && (t.sh <= 0 || (t.sh % q))) return false;
   if (B > 1 && (t.sb <= 0 || (t.sb % q))) return false;
   return true;
+}
+
+// Dense external mask (unit key stride, one row of terms per query row) with 1-byte (bool) or 2-byte (fp16 / bf16 additive) elements
+// -> 4-D tensor map over [MB, MH, Sq, Skv] (broadcast dims have extent 1), box = 128 bytes x 128 rows, 128-byte swizzle: the kernels
+// stage 128 x 128 mask tiles in shared memory instead of reading them row by row.  False when the mask does not qualify (row
+// broadcast, fp32 terms, rows that are not 16-byte multiples, MFA_DISABLE_MASK_TMA): the kernels then read it in place.
+inline bool make_mask_map(CUtensorMap* out, const AttnParams& p) {
+  if (p.mask_kind == kMaskNone || !p.mask || getenv("MFA_DISABLE_MASK_TMA") || p.mask_sq <= 0 || p.mask_sk != 1) return false;
+  const bool one_byte = p.mask_kind == kMaskBool;
+  if (!one_byte && p.mask_scalar != kMaskBF16 && p.mask_scalar != kMaskF16) return false;
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const long long eb = one_byte ? 1 : 2, q = 16 / eb;
+  if ((reinterpret_cast<uintptr_t>(p.mask) & 15) || (p.mask_sq % q) || (p.mask_sh % q) || (p.mask_sb % q) || p.mask_sh < 0 || p.mask_sb < 0)
+    return false;
+  const int MH = p.mask_sh ? p.H : 1, MB = p.mask_sb ? p.B : 1;
+  cuuint64_t dims[4] = {(cuuint64_t)p.Skv, (cuuint64_t)p.Sq, (cuuint64_t)MH, (cuuint64_t)MB};
+  cuuint64_t st[3] = {(cuuint64_t)(p.mask_sq * eb), (cuuint64_t)(p.mask_sh * eb), (cuuint64_t)(p.mask_sb * eb)};
+  if (MH == 1) st[1] = st[0] * (cuuint64_t)p.Sq;
+  if (MB == 1) st[2] = st[1] * (cuuint64_t)MH;
+  cuuint32_t box[4] = {(cuuint32_t)(128 / eb), 128, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return fn(out, one_byte ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(p.mask), dims, st, box,
+            es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace tc
