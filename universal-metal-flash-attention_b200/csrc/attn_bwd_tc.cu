@@ -147,7 +147,11 @@ struct BCfg {
   static constexpr int kChunkBytes = 128 * 128;
   // ring depths: A = operand used last (Q / K), B = dO / V.  STAGED (external mask tiles in shared memory): the 32 KB mask tile
   // takes the place of the second B stage at D = 128 (dO_i / V_j have one reader group per step and a whole step to reload)
+#if defined(MFA_BWD_RA) && defined(MFA_BWD_RB)                  // ring-depth experiments (unmasked kernels, D = 128)
+  static constexpr int kRA = (!STAGED && D == 128) ? MFA_BWD_RA : 3, kRB = (STAGED && D == 128) ? 1 : (D == 128 ? MFA_BWD_RB : 2);
+#else
   static constexpr int kRA = 3, kRB = (STAGED && D == 128) ? 1 : 2;
+#endif
   static constexpr int kMaskBytes = STAGED ? 128 * 128 * 2 : 0;  // one 128 x 128 tile of 16-bit terms (bool bytes use half)
   static constexpr int kStatBytes = 2 * 2 * 128 * 4;             // [slot][L|D][128], own 2-deep ring
   static constexpr int kSmem = (2 + kRA + kRB) * kTile + kMaskBytes + kStatBytes + 256 + 512;   // D = 128: 232192 of 232448 B

@@ -51,7 +51,8 @@ __device__ __forceinline__ float make_scale(float amax, int bits, float floor_v)
 // apply pass of a 28 MB bf16 tensor 19.2 -> 17.2 us without the division, -> 14.0 us with the magic-number rounding and the
 // byte-permute packing below (round 2); the read-only abs-max pass takes 7.6 us, so the rest of the gap is still the
 // per-element convert / round / clamp / pack arithmetic, not memory.  A register-resident single-trip block variant was tried
-// and was slower than the two-trip one: 24.4 vs 21 us; a four-rows-per-warp D-term kernel was slower too: 36.6 vs 24 us.)
+// and was slower than the two-trip one: 24.4 vs 21 us.  A four-rows-per-warp D-term kernel first measured slower as well, 36.6 vs
+// 24 us -- its 64-bit row / head divisions were the cost; with those moved into the grid shape it runs in 15.5 us, attn_simt.cu.)
 __device__ __forceinline__ int quant_code_fast(float x, float scale, float inv, int bits) {
   if (!(scale > 0.f)) return 0;
   const float lo = bits == 8 ? -128.f : -8.f, hi = bits == 8 ? 127.f : 7.f;
