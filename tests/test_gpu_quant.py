@@ -52,6 +52,23 @@ def test_quantize_bit_exact(ctx, dtype, bits, rows, cols, br, bc):
     assert np.array_equal(np.asarray(codes).ravel().view(np.uint8), np.asarray(rc).ravel().view(np.uint8))
 
 
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+@pytest.mark.parametrize("bits", [8, 4])
+@pytest.mark.parametrize("rows", [256, 300, 4608])
+def test_quantize_single_trip_variant_bit_exact(ctx, dtype, bits, rows, monkeypatch):
+    """the opt-in register-resident block quantiser (MFA_QUANT_SINGLE_TRIP=1, token blocks of 64 x 128) is bit-exact too"""
+    import umfa
+    rng = np.random.default_rng(rows + bits)
+    x = (rng.standard_normal((rows, 128)) * 3).astype(np.float32)
+    arr, vals = _src(x, dtype)
+    monkeypatch.setenv("MFA_QUANT_SINGLE_TRIP", "1")
+    codes, scales = umfa.quantize(ctx, arr, bits=bits, block_rows=64, block_cols=0, src_precision=dtype)
+    monkeypatch.delenv("MFA_QUANT_SINGLE_TRIP")
+    rc, rs = O.quantize(vals, bits=bits, block_rows=64, block_cols=None)
+    assert np.array_equal(scales.view(np.uint32), rs.view(np.uint32))
+    assert np.array_equal(np.asarray(codes).ravel().view(np.uint8), np.asarray(rc).ravel().view(np.uint8))
+
+
 def test_quantize_kat_and_floor(ctx):
     import umfa
     x = np.array([[-10.0, -5.0, 0.0, 5.0, 10.0, 0.0, 0.0, 0.0]], np.float32)
@@ -114,6 +131,37 @@ def test_prequantised_forward_entry_point(ctx):
                                    kv_precision="int8", q_scale=float(qs[0]), k_scale=float(ks[0]), v_scale=float(vs[0]))
     ref, _ = O.attention_forward(*(O.dequantize(c, s, S, D)[None, None] for c, s in ((qc, qs), (kc, ks), (vc, vs))))
     assert np.abs(out - ref[0, 0]).max() < 2e-5
+
+
+@pytest.mark.parametrize("n", [2, 8, 16, 32, 64, 128, 256, 512, 1024])
+def test_hadamard_every_block_size(ctx, n, monkeypatch):
+    """in-place FWHT with the 1/sqrt(n) scaling against the explicit Hadamard matrix: blocks of 32 .. 1024 run on the warp kernel
+    (registers + shuffles), smaller ones on the shared-memory kernel; both routes agree; H H = I"""
+    import umfa
+    from umfa._ffi import _lib
+    rng = np.random.default_rng(n)
+    nb = 3001 if n <= 128 else 301
+    x = rng.standard_normal((nb, n)).astype(np.float32)
+    Hm = np.array([[1.0]])
+    while Hm.shape[0] < n:
+        Hm = np.block([[Hm, Hm], [Hm, -Hm]])
+    ref = (x.astype(np.float64) @ Hm.T / np.sqrt(n)).astype(np.float32)
+    def rotate(a):
+        b = umfa.MFABuffer(ctx, a)
+        rc = _lib.mfa_hadamard_rotate(b.handle, n, nb)
+        b.close()
+        assert rc == 0
+
+    y = x.copy()
+    rotate(y)
+    np.testing.assert_allclose(y, ref, rtol=2e-5, atol=2e-5)
+    z = x.copy()
+    monkeypatch.setenv("MFA_HADAMARD_SMEM", "1")
+    rotate(z)
+    monkeypatch.delenv("MFA_HADAMARD_SMEM")
+    np.testing.assert_allclose(z, y, rtol=1e-5, atol=1e-5)
+    rotate(y)
+    np.testing.assert_allclose(y, x, rtol=2e-5, atol=2e-5)
 
 
 def test_hadamard_and_merge(ctx):

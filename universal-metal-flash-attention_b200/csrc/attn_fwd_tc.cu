@@ -1180,13 +1180,19 @@ struct MaskTileParams {
   int* counts;
 };
 
-// one CTA per (KV tile, query block, mask batch x head): flag = the tile lies in the causal / window range of the block and
-// holds at least one visible element.  Warp = 32 rows, lane = column (4 coalesced loads per row), all loads independent.
-__global__ void __launch_bounds__(256) mask_flags_kernel(const MaskTileParams q, uint8_t* __restrict__ flags) {
-  const int j = blockIdx.x, qb = blockIdx.y, mbh = blockIdx.z;
+// per (KV tile, query block, mask batch x head): flag = the tile lies in the causal / window range of the block and holds at
+// least one visible element (1), or is visible everywhere with a no-op mask (2).  Lane = column (4 coalesced loads per row).
+// One WARP per tile, 8 tiles (neighbouring KV tiles of one query block) per CTA, no block-level synchronisation: with a CTA per tile
+// the pre-pass of a dense [1, H, S, S] mask (15552 tiles at the FLUX shape, each decided by its first rows) was bound by the CTA launch
+// rate -- 25 us with 256-thread CTAs, still 20-24 us with 64-thread ones (profiles/r02bi_launches_mask.csv).
+constexpr int kFlagThreads = 256;
+__global__ void __launch_bounds__(kFlagThreads) mask_flags_kernel(const MaskTileParams q, uint8_t* __restrict__ flags) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (kFlagThreads / 32) + warp, qb = blockIdx.y, mbh = blockIdx.z;
+  if (j >= q.nkt) return;
   const int mb = mbh / q.MH, mh = mbh % q.MH;
   const int r0 = qb * 256, rows = min(256, q.Sq - r0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int RPW = 4;                                   // rows of the first round
   int klo, khi;
   visible_key_range(q.causal, q.window, q.Skv, r0, min(r0 + 256, q.Sq), klo, khi);
   const int j_lo = klo >> 7, j_hi = khi > klo ? (khi + 127) >> 7 : j_lo;
@@ -1194,29 +1200,50 @@ __global__ void __launch_bounds__(256) mask_flags_kernel(const MaskTileParams q,
   if (j >= j_lo && j < j_hi) {
     const int c0 = j * 128, ncol = min(128, q.Skv - c0);
     const int nrows = q.sq ? rows : 1;                     // a mask broadcast over the rows: one row decides
-    // a warp stops as soon as its rows prove the tile "partial" (something visible and something that is not a no-op):
-    // a dense bias costs one row per warp, only uniform-looking tiles are read in full
-    for (int rr = warp; rr < nrows; rr += 8) {
-      const long long off = (long long)mb * q.sb + (long long)mh * q.sh + (long long)(r0 + rr) * q.sq + c0;
+    // the warp stops as soon as its rows prove the tile "partial" (something visible and something that is not a no-op): a dense
+    // bias is decided by the first round of 4 rows; tiles that look uniform are then read in rounds of 16 rows (64 loads in flight
+    // per lane: a uniform tile costs 1 + 16 memory latencies)
+    // two passes over raw[][]: first nothing but the loads (volatile asm: they stay back to back, all in flight together), then the
+    // conversions -- fused into one loop the compiler pairs every load with its conversion and the round trips serialise (64 per
+    // round: the two-phase version measured 70 us on a packing mask before this, profiles/r02bh_launches_mask.csv)
+    const int esz_sel = q.kind == kMaskBool ? 0 : q.scalar == kMaskF32 ? 2 : 1;
+    auto round = [&](int rb, auto nr_tag) {
+      constexpr int NR = decltype(nr_tag)::value;
+      uint32_t raw[NR][4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c = lane + 32 * k;
-        if (c < ncol) {
+      for (int i = 0; i < NR; ++i) {
+        const int rr = min(rb + i, nrows - 1);             // past the end: the last row again
+        const long long off = (long long)mb * q.sb + (long long)mh * q.sh + (long long)(r0 + rr) * q.sq + c0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const long long e = off + min(lane + 32 * k, ncol - 1);      // past the end: the last key again
+          if (esz_sel == 0) raw[i][k] = ldg_pred_u8(reinterpret_cast<const uint8_t*>(q.mask) + e, true, 0u);
+          else if (esz_sel == 2) raw[i][k] = ldg_pred_b32(reinterpret_cast<const float*>(q.mask) + e, true, 0u);
+          else raw[i][k] = ldg_pred_u16(reinterpret_cast<const uint16_t*>(q.mask) + e, true, 0u);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
           float val;
-          if (q.kind == kMaskBool) val = reinterpret_cast<const uint8_t*>(q.mask)[off + c] != 0 ? 0.f : -CUDART_INF_F;
-          else if (q.scalar == kMaskF32) val = reinterpret_cast<const float*>(q.mask)[off + c];
-          else if (q.scalar == kMaskBF16) val = __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(q.mask)[off + c] << 16);
-          else val = __half2float(reinterpret_cast<const __half*>(q.mask)[off + c]);
+          if (esz_sel == 0) val = raw[i][k] != 0u ? 0.f : -CUDART_INF_F;
+          else if (esz_sel == 2) val = __uint_as_float(raw[i][k]);
+          else if (q.scalar == kMaskBF16) val = __uint_as_float(raw[i][k] << 16);
+          else val = __half2float(__ushort_as_half((unsigned short)raw[i][k]));
           any |= val > -CUDART_INF_F;
           all &= val == 0.f;
         }
       }
-      if (__any_sync(0xffffffffu, any) && !__all_sync(0xffffffffu, all)) break;
-    }
+      return __any_sync(0xffffffffu, any) && !__all_sync(0xffffffffu, all);
+    };
+    bool decided = round(0, std::integral_constant<int, RPW>{});
+    constexpr int RPW2 = 16;
+    for (int rb = RPW; rb < nrows && !decided; rb += RPW2) decided = round(rb, std::integral_constant<int, RPW2>{});
   }
-  any = __syncthreads_or(any);
-  all = __syncthreads_and(all);
-  if (threadIdx.x == 0) flags[((size_t)mbh * q.nqb + qb) * q.nkt + j] = any ? (all ? 2 : 1) : 0;
+  any = __any_sync(0xffffffffu, any);
+  all = __all_sync(0xffffffffu, all);
+  if (lane == 0) flags[((size_t)mbh * q.nqb + qb) * q.nkt + j] = any ? (all ? 2 : 1) : 0;
 }
 
 // one thread per list: compacts the flagged tile indices in ascending order; kTileNoMask marks tiles on which the mask is a
@@ -1498,7 +1525,7 @@ cudaError_t launch_mask_flags(const AttnParams& p, uint8_t* flags, cudaStream_t 
   q.sb = p.mask_sb; q.sh = p.mask_sh; q.sq = p.mask_sq;
   q.Sq = p.Sq; q.Skv = p.Skv; q.causal = p.causal; q.window = p.window; q.nqb = m.nqb; q.nkt = m.nkt; q.MH = m.MH;
   q.counts = nullptr; q.tiles = nullptr;
-  mask_flags_kernel<<<dim3((unsigned)m.nkt, (unsigned)m.nqb, (unsigned)(m.MB * m.MH)), 256, 0, st>>>(q, flags);
+  mask_flags_kernel<<<dim3((unsigned)((m.nkt + 7) / 8), (unsigned)m.nqb, (unsigned)(m.MB * m.MH)), kFlagThreads, 0, st>>>(q, flags);
   ++g_launch_count;
   return cudaGetLastError();
 }
@@ -1516,7 +1543,7 @@ cudaError_t fwd_tc_build_mask_tiles(FwdTcParams& prm, const AttnParams& p, cudaS
   q.counts = p.mask_tile_scratch;
   q.tiles = p.mask_tile_scratch + m.lists;
   uint8_t* flags = reinterpret_cast<uint8_t*>(q.tiles + m.lists * m.nkt);
-  mask_flags_kernel<<<dim3((unsigned)m.nkt, (unsigned)m.nqb, (unsigned)(m.MB * m.MH)), 256, 0, st>>>(q, flags);
+  mask_flags_kernel<<<dim3((unsigned)((m.nkt + 7) / 8), (unsigned)m.nqb, (unsigned)(m.MB * m.MH)), kFlagThreads, 0, st>>>(q, flags);
   mask_compact_kernel<<<(unsigned)((m.lists + 127) / 128), 128, 0, st>>>(flags, q.tiles, q.counts, (int)m.lists, m.nkt);
   g_launch_count += 2;
   prm.mtiles = q.tiles; prm.mcounts = q.counts; prm.m_nkt = m.nkt;

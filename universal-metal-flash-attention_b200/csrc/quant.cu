@@ -13,6 +13,8 @@
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "common.h"
 
 namespace mfa {
@@ -142,6 +144,75 @@ __global__ void __launch_bounds__(256) quant_span_kernel(const T* __restrict__ s
 #pragma unroll
       for (int i = 0; i < 8; ++i) out |= (uint32_t)((q[i] + 8) & 0xF) << (4 * i);
       *reinterpret_cast<uint32_t*>(codes + (e >> 1)) = out;
+    }
+  }
+}
+
+// ---- single trip for 16-bit sources and blocks of up to 8192 elements (the 64-token x 128-dim blocks of the attention path): a CTA
+// per block, every thread ISSUES its (up to four) 16-byte loads before the first use and keeps the raw words in registers for the
+// apply step.  The two-trip kernel above walks its span in a loop whose abs-max consumes each load right away -- four serialised
+// memory latencies per thread in the first trip and four more L2 latencies in the second: 21.5 us per 28 MB FLUX tensor, 0.30 of
+// the copy rate, with only ~1.5 waves of CTAs (profiles/r02bg_helpers.csv).  Same code rule (quant_code_fast): bit-exact.
+// MEASURED: no faster -- 21.8 us against 21.5 us (profiles/r02bh_helpers_single.csv / _two.csv), so the latencies were not the
+// limit; what is left is the ~16 instructions per element of convert / scale / round / tie check / pack (8 M warp instructions per
+// tensor).  Kept as an opt-in (MFA_QUANT_SINGLE_TRIP=1) with its parity tests; the two-trip kernel stays the default.
+template <typename T, int BITS>
+__global__ void __launch_bounds__(256) quant_span_reg_kernel(const T* __restrict__ src, uint8_t* __restrict__ codes,
+                                                             float* __restrict__ scales, uint64_t rows, uint64_t cols,
+                                                             uint32_t block_rows, uint64_t group_rows, uint32_t nb_per_group,
+                                                             float floor_v) {
+  static_assert(sizeof(T) == 2, "16-bit sources");
+  __shared__ float red[8];
+  const uint64_t blk = blockIdx.x;
+  const uint64_t g = blk / nb_per_group, lb = blk % nb_per_group;
+  const uint64_t r0 = g * group_rows + lb * block_rows;
+  uint64_t r1 = r0 + block_rows;
+  if (r1 > (g + 1) * group_rows) r1 = (g + 1) * group_rows;
+  if (r1 > rows) r1 = rows;
+  const uint64_t e0 = r0 * cols;
+  const uint32_t n = (uint32_t)((r1 - r0) * cols);              // <= 8192, a multiple of 8 (launcher)
+  const T* base = src + e0;
+  uint4 raw[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t idx = (uint32_t)(k * 256 + threadIdx.x) * 8;
+    raw[k] = idx < n ? *reinterpret_cast<const uint4*>(base + idx) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float amax = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const T* e = reinterpret_cast<const T*>(&raw[k]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(to_f32<T>(e[i])));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  amax = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) amax = fmaxf(amax, red[i]);
+  const float sc = make_scale(amax, BITS, floor_v);
+  const float inv = inv_scale(sc);
+  if (threadIdx.x == 0) scales[blk] = sc;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t idx = (uint32_t)(k * 256 + threadIdx.x) * 8;
+    if (idx >= n) continue;
+    const T* e = reinterpret_cast<const T*>(&raw[k]);
+    int q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = quant_code_fast(to_f32<T>(e[i]), sc, inv, BITS);
+    if (BITS == 8) {
+      uint2 out;
+      out.x = pack4_bytes(q[0], q[1], q[2], q[3]);
+      out.y = pack4_bytes(q[4], q[5], q[6], q[7]);
+      *reinterpret_cast<uint2*>(codes + e0 + idx) = out;
+    } else {
+      uint32_t out = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out |= (uint32_t)((q[i] + 8) & 0xF) << (4 * i);
+      *reinterpret_cast<uint32_t*>(codes + ((e0 + idx) >> 1)) = out;
     }
   }
 }
@@ -434,6 +505,11 @@ cudaError_t quantize_typed(const T* src, uint8_t* codes, float* scales, uint64_t
       unsigned grid = (unsigned)((nblocks + 7) / 8);
       if (bits == 8) quant_span_kernel<T, 8, true><<<grid, 256, 0, st>>>(src, codes, scales, rows, cols, br, group_rows, nb_per_group, nblocks, floor_v);
       else quant_span_kernel<T, 4, true><<<grid, 256, 0, st>>>(src, codes, scales, rows, cols, br, group_rows, nb_per_group, nblocks, floor_v);
+    } else if (sizeof(T) == 2 && span <= 8192 && nblocks <= 0x7fffffffull && getenv("MFA_QUANT_SINGLE_TRIP")) {
+      if constexpr (sizeof(T) == 2) {
+        if (bits == 8) quant_span_reg_kernel<T, 8><<<(unsigned)nblocks, 256, 0, st>>>(src, codes, scales, rows, cols, br, group_rows, nb_per_group, floor_v);
+        else quant_span_reg_kernel<T, 4><<<(unsigned)nblocks, 256, 0, st>>>(src, codes, scales, rows, cols, br, group_rows, nb_per_group, floor_v);
+      }
     } else {
       unsigned grid = (unsigned)nblocks;
       if (bits == 8) quant_span_kernel<T, 8, false><<<grid, 256, 0, st>>>(src, codes, scales, rows, cols, br, group_rows, nb_per_group, nblocks, floor_v);
@@ -545,9 +621,81 @@ cudaError_t launch_merge_partials(float* o_acc, float* l_acc, const float* o_par
   return cudaGetLastError();
 }
 
+// Blocks of n = 32 E values, E = 1 .. 32: one warp per block, lane L holds elements [E L, E L + E) in registers (vector loads:
+// a warp request covers the whole block, fully coalesced), the butterflies with span h < E stay inside the lane, those with
+// h >= E exchange with lane L ^ (h / E) by shuffle -- no shared memory, no barriers; HBM-bound (4 B in + 4 B out per element).
+// The shared-memory kernel above (one CTA per block, a barrier per stage) moved a 512-byte head_dim-128 block per CTA.
+template <int E>
+__global__ void __launch_bounds__(256) hadamard_warp_kernel(float* __restrict__ data, uint32_t num_blocks) {
+  const uint32_t lane = threadIdx.x & 31;
+  const float norm = rsqrtf((float)(32 * E));
+  for (uint64_t blk = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); blk < num_blocks; blk += (uint64_t)gridDim.x * 8) {
+    float* p = data + blk * (32 * E) + lane * E;
+    float x[E];
+    if constexpr (E >= 4) {
+#pragma unroll
+      for (int i = 0; i < E / 4; ++i) {
+        const float4 v = reinterpret_cast<const float4*>(p)[i];
+        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+      }
+    } else if constexpr (E == 2) {
+      const float2 v = *reinterpret_cast<const float2*>(p);
+      x[0] = v.x; x[1] = v.y;
+    } else {
+      x[0] = p[0];
+    }
+#pragma unroll
+    for (int h = 1; h < E; h <<= 1) {
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        if ((i & h) == 0) {
+          const float a = x[i], b = x[i + h];
+          x[i] = a + b; x[i + h] = a - b;
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+      const bool upper = (lane & m) != 0;
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const float v = __shfl_xor_sync(0xffffffffu, x[i], m);
+        x[i] = upper ? v - x[i] : x[i] + v;
+      }
+    }
+    if constexpr (E >= 4) {
+#pragma unroll
+      for (int i = 0; i < E / 4; ++i)
+        reinterpret_cast<float4*>(p)[i] = make_float4(x[4 * i] * norm, x[4 * i + 1] * norm, x[4 * i + 2] * norm, x[4 * i + 3] * norm);
+    } else if constexpr (E == 2) {
+      *reinterpret_cast<float2*>(p) = make_float2(x[0] * norm, x[1] * norm);
+    } else {
+      p[0] = x[0] * norm;
+    }
+  }
+}
+
+template <int E>
+void launch_hadamard_warp(float* data, uint32_t num_blocks, cudaStream_t st) {
+  const unsigned want = (num_blocks + 7) / 8, cap = 148u * 8 * 4;
+  hadamard_warp_kernel<E><<<want < cap ? want : cap, 256, 0, st>>>(data, num_blocks);
+}
+
 cudaError_t launch_hadamard(float* data, uint32_t block_size, uint32_t num_blocks, cudaStream_t st) {
   if (block_size == 0 || block_size > 1024 || (block_size & (block_size - 1))) return cudaErrorInvalidValue;
   if (num_blocks == 0) return cudaSuccess;
+  if (block_size >= 32 && (reinterpret_cast<uintptr_t>(data) & 15) == 0 && !getenv("MFA_HADAMARD_SMEM")) {
+    switch (block_size / 32) {
+      case 1: launch_hadamard_warp<1>(data, num_blocks, st); break;
+      case 2: launch_hadamard_warp<2>(data, num_blocks, st); break;
+      case 4: launch_hadamard_warp<4>(data, num_blocks, st); break;
+      case 8: launch_hadamard_warp<8>(data, num_blocks, st); break;
+      case 16: launch_hadamard_warp<16>(data, num_blocks, st); break;
+      default: launch_hadamard_warp<32>(data, num_blocks, st); break;
+    }
+    ++g_launch_count;
+    return cudaGetLastError();
+  }
   unsigned threads = block_size / 2 < 32 ? 32 : block_size / 2;
   unsigned grid = num_blocks < 148u * 16 ? num_blocks : 148u * 16;
   hadamard_kernel<<<grid, threads, block_size * sizeof(float), st>>>(data, block_size, num_blocks);
