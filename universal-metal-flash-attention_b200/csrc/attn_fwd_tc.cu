@@ -1182,17 +1182,22 @@ struct MaskTileParams {
 
 // per (KV tile, query block, mask batch x head): flag = the tile lies in the causal / window range of the block and holds at
 // least one visible element (1), or is visible everywhere with a no-op mask (2).  Lane = column (4 coalesced loads per row).
-// One WARP per tile, 8 tiles (neighbouring KV tiles of one query block) per CTA, no block-level synchronisation: with a CTA per tile
-// the pre-pass of a dense [1, H, S, S] mask (15552 tiles at the FLUX shape, each decided by its first rows) was bound by the CTA launch
-// rate -- 25 us with 256-thread CTAs, still 20-24 us with 64-thread ones (profiles/r02bi_launches_mask.csv).
-constexpr int kFlagThreads = 256;
-__global__ void __launch_bounds__(kFlagThreads) mask_flags_kernel(const MaskTileParams q, uint8_t* __restrict__ flags) {
+// Two shapes of the same kernel, chosen by the tile count (launch_flags):
+//   WARP_TILE = false: a CTA of 64 threads per tile, its two warps share the rows -- few tiles (a [1, 1, S, S] mask at the FLUX shape has
+//     648): the latency chain of a tile that must be read in full (uniform tiles of a packing mask) is what counts, 29.5 us there
+//     against 45.7 us with one warp per tile;
+//   WARP_TILE = true: one warp per tile, 8 neighbouring KV tiles per CTA, no block-level synchronisation -- many tiles (dense
+//     [1, H, S, S]: 15552, each decided by its first rows): the CTA launch rate bounds the pass, 25 us with a 256-thread CTA per tile,
+//     20-24 us with 64-thread CTAs, 14-17 us with a warp per tile (profiles/r02bi_launches_mask.csv, r02bj_launches_mask.csv).
+template <bool WARP_TILE>
+__global__ void __launch_bounds__(WARP_TILE ? 256 : 64) mask_flags_kernel(const MaskTileParams q, uint8_t* __restrict__ flags) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * (kFlagThreads / 32) + warp, qb = blockIdx.y, mbh = blockIdx.z;
-  if (j >= q.nkt) return;
+  const int j = WARP_TILE ? blockIdx.x * 8 + warp : blockIdx.x, qb = blockIdx.y, mbh = blockIdx.z;
+  if (j >= q.nkt) return;                                  // (WARP_TILE only: whole warps, no barrier follows)
   const int mb = mbh / q.MH, mh = mbh % q.MH;
   const int r0 = qb * 256, rows = min(256, q.Sq - r0);
-  constexpr int RPW = 4;                                   // rows of the first round
+  constexpr int NW = WARP_TILE ? 1 : 2, RPW = 4;           // warps sharing a tile, rows per warp in the first round
+  const int wt = WARP_TILE ? 0 : warp;                     // this warp's index among them
   int klo, khi;
   visible_key_range(q.causal, q.window, q.Skv, r0, min(r0 + 256, q.Sq), klo, khi);
   const int j_lo = klo >> 7, j_hi = khi > klo ? (khi + 127) >> 7 : j_lo;
@@ -1200,9 +1205,9 @@ __global__ void __launch_bounds__(kFlagThreads) mask_flags_kernel(const MaskTile
   if (j >= j_lo && j < j_hi) {
     const int c0 = j * 128, ncol = min(128, q.Skv - c0);
     const int nrows = q.sq ? rows : 1;                     // a mask broadcast over the rows: one row decides
-    // the warp stops as soon as its rows prove the tile "partial" (something visible and something that is not a no-op): a dense
-    // bias is decided by the first round of 4 rows; tiles that look uniform are then read in rounds of 16 rows (64 loads in flight
-    // per lane: a uniform tile costs 1 + 16 memory latencies)
+    // a warp stops as soon as its rows prove the tile "partial" (something visible and something that is not a no-op): a dense
+    // bias is decided by the first round of 4 rows per warp; tiles that look uniform are then read in rounds of 16 rows per warp
+    // (64 loads in flight per lane)
     // two passes over raw[][]: first nothing but the loads (volatile asm: they stay back to back, all in flight together), then the
     // conversions -- fused into one loop the compiler pairs every load with its conversion and the round trips serialise (64 per
     // round: the two-phase version measured 70 us on a packing mask before this, profiles/r02bh_launches_mask.csv)
@@ -1237,13 +1242,30 @@ __global__ void __launch_bounds__(kFlagThreads) mask_flags_kernel(const MaskTile
       }
       return __any_sync(0xffffffffu, any) && !__all_sync(0xffffffffu, all);
     };
-    bool decided = round(0, std::integral_constant<int, RPW>{});
+    bool decided = false;
+    if (wt * RPW < nrows) decided = round(wt * RPW, std::integral_constant<int, RPW>{});
     constexpr int RPW2 = 16;
-    for (int rb = RPW; rb < nrows && !decided; rb += RPW2) decided = round(rb, std::integral_constant<int, RPW2>{});
+    for (int rb = NW * RPW + wt * RPW2; rb < nrows && !decided; rb += NW * RPW2) decided = round(rb, std::integral_constant<int, RPW2>{});
   }
-  any = __any_sync(0xffffffffu, any);
-  all = __all_sync(0xffffffffu, all);
-  if (lane == 0) flags[((size_t)mbh * q.nqb + qb) * q.nkt + j] = any ? (all ? 2 : 1) : 0;
+  if constexpr (WARP_TILE) {
+    any = __any_sync(0xffffffffu, any);
+    all = __all_sync(0xffffffffu, all);
+    if (lane == 0) flags[((size_t)mbh * q.nqb + qb) * q.nkt + j] = any ? (all ? 2 : 1) : 0;
+  } else {
+    any = __syncthreads_or(any);
+    all = __syncthreads_and(all);
+    if (threadIdx.x == 0) flags[((size_t)mbh * q.nqb + qb) * q.nkt + j] = any ? (all ? 2 : 1) : 0;
+  }
+}
+
+// grid shape by tile count (see the kernel)
+template <typename M>
+void launch_flags(const MaskTileParams& q, const M& m, uint8_t* flags, cudaStream_t st) {
+  const long long tiles = (long long)m.nkt * m.nqb * m.MB * m.MH;
+  if (tiles >= 4096 && !getenv("MFA_MASK_FLAGS_CTA_TILE"))
+    mask_flags_kernel<true><<<dim3((unsigned)((m.nkt + 7) / 8), (unsigned)m.nqb, (unsigned)(m.MB * m.MH)), 256, 0, st>>>(q, flags);
+  else
+    mask_flags_kernel<false><<<dim3((unsigned)m.nkt, (unsigned)m.nqb, (unsigned)(m.MB * m.MH)), 64, 0, st>>>(q, flags);
 }
 
 // one thread per list: compacts the flagged tile indices in ascending order; kTileNoMask marks tiles on which the mask is a
@@ -1525,7 +1547,7 @@ cudaError_t launch_mask_flags(const AttnParams& p, uint8_t* flags, cudaStream_t 
   q.sb = p.mask_sb; q.sh = p.mask_sh; q.sq = p.mask_sq;
   q.Sq = p.Sq; q.Skv = p.Skv; q.causal = p.causal; q.window = p.window; q.nqb = m.nqb; q.nkt = m.nkt; q.MH = m.MH;
   q.counts = nullptr; q.tiles = nullptr;
-  mask_flags_kernel<<<dim3((unsigned)((m.nkt + 7) / 8), (unsigned)m.nqb, (unsigned)(m.MB * m.MH)), kFlagThreads, 0, st>>>(q, flags);
+  launch_flags(q, m, flags, st);
   ++g_launch_count;
   return cudaGetLastError();
 }
@@ -1543,7 +1565,7 @@ cudaError_t fwd_tc_build_mask_tiles(FwdTcParams& prm, const AttnParams& p, cudaS
   q.counts = p.mask_tile_scratch;
   q.tiles = p.mask_tile_scratch + m.lists;
   uint8_t* flags = reinterpret_cast<uint8_t*>(q.tiles + m.lists * m.nkt);
-  mask_flags_kernel<<<dim3((unsigned)((m.nkt + 7) / 8), (unsigned)m.nqb, (unsigned)(m.MB * m.MH)), kFlagThreads, 0, st>>>(q, flags);
+  launch_flags(q, m, flags, st);
   mask_compact_kernel<<<(unsigned)((m.lists + 127) / 128), 128, 0, st>>>(flags, q.tiles, q.counts, (int)m.lists, m.nkt);
   g_launch_count += 2;
   prm.mtiles = q.tiles; prm.mcounts = q.counts; prm.m_nkt = m.nkt;
