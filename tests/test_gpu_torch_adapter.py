@@ -142,6 +142,36 @@ def test_autograd_matches_math(torch_mod, adapter, dtype, causal):
         assert relmax(a, b) < tol
 
 
+@pytest.mark.parametrize("mask_kind", ["bf16_additive", "bool"])
+def test_autograd_with_dense_mask_takes_the_staged_kernels(torch_mod, adapter, mask_kind):
+    """F.scaled_dot_product_attention with a dense bf16 bias / bool mask in the tensors' own dtype: the mask is handed over in
+    place and both directions run on the kernels that stage mask tiles in shared memory by TMA; O and the gradients against
+    the written-out fp32 math"""
+    torch = torch_mod
+    p, ext = adapter
+    g = torch.Generator(device="cuda").manual_seed(21)
+    B, H, Sq, Skv, D = 1, 3, 384, 512, 128
+    q = torch.randn(B, H, Sq, D, device="cuda", generator=g).to(torch.bfloat16).requires_grad_(True)
+    k, v = (torch.randn(B, H, Skv, D, device="cuda", generator=g).to(torch.bfloat16).requires_grad_(True) for _ in range(2))
+    go = torch.randn(B, H, Sq, D, device="cuda", generator=g).to(torch.bfloat16)
+    if mask_kind == "bool":
+        mask = torch.rand(1, H, Sq, Skv, device="cuda", generator=g) > 0.4
+        mask[..., 0] = True
+    else:
+        mask = (1.5 * torch.randn(1, H, Sq, Skv, device="cuda", generator=g)).to(torch.bfloat16)
+    with p.use_metal_sdpa():
+        out = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=mask)
+    assert ext._context(q.device).last_kernel == "fwd_tc_bf16_d128_tma_mask"
+    out.backward(go)
+    assert ext._context(q.device).last_kernel == "bwd_tc_bf16_d128_tma_mask"
+    qr, kr, vr = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    ref = ref_sdpa(torch, qr, kr, vr, mask=mask)
+    ref.backward(go.float())
+    assert relmax(out, ref) < 1e-2
+    for a, b in ((q.grad, qr.grad), (k.grad, kr.grad), (v.grad, vr.grad)):
+        assert relmax(a, b) < 2e-2
+
+
 @pytest.mark.parametrize("prec,mode,min_cos", [(3, 0, 0.99), (3, 2, 0.99), (4, 2, 0.93)])
 def test_quantised_autograd(torch_mod, adapter, prec, mode, min_cos):
     """Bounds: cosine >= 0.99 (int8) / 0.93 (int4 at this small size) on O vs fp32 math, and the reference's own gate

@@ -1190,7 +1190,7 @@ struct MaskTileParams {
 //     [1, H, S, S]: 15552, each decided by its first rows): the CTA launch rate bounds the pass, 25 us with a 256-thread CTA per tile,
 //     20-24 us with 64-thread CTAs, 14-17 us with a warp per tile (profiles/r02bi_launches_mask.csv, r02bj_launches_mask.csv).
 template <bool WARP_TILE>
-__global__ void __launch_bounds__(WARP_TILE ? 256 : 64) mask_flags_kernel(const MaskTileParams q, uint8_t* __restrict__ flags) {
+__global__ void __launch_bounds__(WARP_TILE ? 256 : 64, WARP_TILE ? 4 : 16) mask_flags_kernel(const MaskTileParams q, uint8_t* __restrict__ flags) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = WARP_TILE ? blockIdx.x * 8 + warp : blockIdx.x, qb = blockIdx.y, mbh = blockIdx.z;
   if (j >= q.nkt) return;                                  // (WARP_TILE only: whole warps, no barrier follows)
@@ -1242,10 +1242,67 @@ __global__ void __launch_bounds__(WARP_TILE ? 256 : 64) mask_flags_kernel(const 
       }
       return __any_sync(0xffffffffu, any) && !__all_sync(0xffffffffu, all);
     };
-    bool decided = false;
-    if (wt * RPW < nrows) decided = round(wt * RPW, std::integral_constant<int, RPW>{});
-    constexpr int RPW2 = 16;
-    for (int rb = NW * RPW + wt * RPW2; rb < nrows && !decided; rb += NW * RPW2) decided = round(rb, std::integral_constant<int, RPW2>{});
+    // full tiles whose rows are aligned for it take one vector load per row and lane (4 keys: 4 / 8 / 16 bytes) instead of four
+    // element loads, and the row offset is one multiply-add on a hoisted base: the pre-pass of a dense [1, H, S, S] mask spent more
+    // instructions on addresses than on loads
+    const long long base_off = (long long)mb * q.sb + (long long)mh * q.sh + (long long)r0 * q.sq + c0;
+    const int esz = esz_sel == 0 ? 1 : esz_sel == 2 ? 4 : 2;
+    const uintptr_t base_addr = reinterpret_cast<uintptr_t>(q.mask) + (uintptr_t)(base_off * esz);
+    const bool vec_ok = ncol == 128 && (base_addr & (uintptr_t)(4 * esz - 1)) == 0 && ((q.sq * esz) & (4 * esz - 1)) == 0;
+    auto round_vec = [&](int rb, auto nr_tag, auto esz_tag) {
+      constexpr int NR = decltype(nr_tag)::value, ESZ = decltype(esz_tag)::value, W = ESZ;      // words per lane and row: 1 / 2 / 4
+      uint32_t raw[NR][W];
+      const char* lane_ptr = reinterpret_cast<const char*>(base_addr) + lane * 4 * ESZ;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const char* ptr = lane_ptr + (long long)min(rb + i, nrows - 1) * q.sq * ESZ;          // past the end: the last row again
+        if constexpr (ESZ == 1) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(raw[i][0]) : "l"(ptr));
+        else if constexpr (ESZ == 2) asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(raw[i][0]), "=r"(raw[i][1]) : "l"(ptr));
+        else asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw[i][0]), "=r"(raw[i][1]), "=r"(raw[i][2]), "=r"(raw[i][3]) : "l"(ptr));
+      }
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        if constexpr (ESZ == 1) {                          // four bool bytes: any byte set / no zero byte
+          const uint32_t w = raw[i][0];
+          any |= w != 0u;
+          all &= ((w - 0x01010101u) & ~w & 0x80808080u) == 0u;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float val;
+            if constexpr (ESZ == 4) val = __uint_as_float(raw[i][k]);
+            else {
+              const uint32_t h16 = (raw[i][k >> 1] >> (16 * (k & 1))) & 0xffffu;
+              val = q.scalar == kMaskBF16 ? __uint_as_float(h16 << 16) : __half2float(__ushort_as_half((unsigned short)h16));
+            }
+            any |= val > -CUDART_INF_F;
+            all &= val == 0.f;
+          }
+        }
+      }
+      return __any_sync(0xffffffffu, any) && !__all_sync(0xffffffffu, all);
+    };
+    // rounds: first RPW rows per warp, then RPW2 rows per warp and round until the tile is decided or read
+    auto walk = [&](auto first, auto later, int rpw2) {
+      bool decided = false;
+      if (wt * RPW < nrows) decided = first(wt * RPW);
+      for (int rb = NW * RPW + wt * rpw2; rb < nrows && !decided; rb += NW * rpw2) decided = later(rb);
+    };
+    // (32 raw words per lane in the later rounds of every variant: the pass wants many resident warps)
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    using I4 = std::integral_constant<int, 4>;
+    using I8 = std::integral_constant<int, 8>;
+    using I16 = std::integral_constant<int, 16>;
+    using I32 = std::integral_constant<int, 32>;
+    if (vec_ok && esz_sel == 0)
+      walk([&](int rb) { return round_vec(rb, I4{}, I1{}); }, [&](int rb) { return round_vec(rb, I32{}, I1{}); }, 32);
+    else if (vec_ok && esz_sel == 1)
+      walk([&](int rb) { return round_vec(rb, I4{}, I2{}); }, [&](int rb) { return round_vec(rb, I16{}, I2{}); }, 16);
+    else if (vec_ok)
+      walk([&](int rb) { return round_vec(rb, I4{}, I4{}); }, [&](int rb) { return round_vec(rb, I8{}, I4{}); }, 8);
+    else
+      walk([&](int rb) { return round(rb, I4{}); }, [&](int rb) { return round(rb, I8{}); }, 8);
   }
   if constexpr (WARP_TILE) {
     any = __any_sync(0xffffffffu, any);
