@@ -55,23 +55,40 @@ __device__ __forceinline__ float make_scale(float amax, int bits, float floor_v)
 // per-element convert / round / clamp / pack arithmetic, not memory.  A register-resident single-trip block variant was tried
 // and was slower than the two-trip one: 24.4 vs 21 us.  A four-rows-per-warp D-term kernel first measured slower as well, 36.6 vs
 // 24 us -- its 64-bit row / head divisions were the cost; with those moved into the grid shape it runs in 15.5 us, attn_simt.cu.)
-__device__ __forceinline__ int quant_code_fast(float x, float scale, float inv, int bits) {
-  if (!(scale > 0.f)) return 0;
+__device__ __forceinline__ int quant_code_exact(float x, float scale, int bits) {
   const float lo = bits == 8 ? -128.f : -8.f, hi = bits == 8 ? 127.f : 7.f;
-  const float t = x * inv;
-  // beyond [lo - 1/4, hi + 1/4] everything clamps alike; inside, adding 1.5 * 2^23 rounds t to the nearest integer (ties to even)
-  // in the mantissa -- one FADD instead of trunc / copysign / add / trunc, and the integer falls out of the bit pattern
-  const float tc = fminf(fmaxf(t, lo - 0.25f), hi + 0.25f);
-  const float y = tc + 12582912.f;
-  const float d = tc - (y - 12582912.f);                       // distance to that integer, in [-1/2, 1/2]
-  int q = __float_as_int(y) - 0x4B400000;
-  // near a tie (where half-away-from-zero and the inexact product could disagree with the exact quotient) or for a
-  // non-finite / out-of-range t: the exact rule
-  if (fabsf(d) > 0.5f - 1e-4f || !(fabsf(t) < 1024.f)) {
-    const float r = fminf(fmaxf(roundf(__fdiv_rn(x, scale)), lo), hi);
-    q = (int)r;
+  return (int)fminf(fmaxf(roundf(__fdiv_rn(x, scale)), lo), hi);
+}
+// Eight codes at once.  The scale of a block is never below amax / 127 (amax / 7), so |t| <= 127 (7) up to rounding and the
+// nearest integer needs no clamp: adding 1.5 * 2^23 rounds t to it in the mantissa (ties to even) -- one FADD instead of trunc /
+// copysign / add / trunc, and the integer falls out of the bit pattern.  Elements within 1e-4 of a tie (where half-away-from-zero
+// and the inexact product could disagree with the exact quotient), NaN / infinite t (d is NaN then) and any t outside the range
+// the argument above promises take the exact rule; the eight tests are merged into ONE branch (a branch per element cost more
+// than the arithmetic it guarded: ~16 instructions per element before this, profiles/r02bh_helpers_two.csv).
+__device__ __forceinline__ void quant_codes8(const float* x, float scale, float inv, int bits, int* q) {
+  if (!(scale > 0.f)) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = 0;
+    return;
   }
-  return q;
+  bool rare = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float t = x[i] * inv;
+    const float y = t + 12582912.f;
+    const float d = t - (y - 12582912.f);                      // distance to that integer, in [-1/2, 1/2]
+    q[i] = __float_as_int(y) - 0x4B400000;
+    rare |= !(fabsf(d) <= 0.5f - 1e-4f) || !(fabsf(t) <= 130.f);
+  }
+  if (rare) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = x[i] * inv;
+      const float y = t + 12582912.f;
+      const float d = t - (y - 12582912.f);
+      if (!(fabsf(d) <= 0.5f - 1e-4f) || !(fabsf(t) <= 130.f)) q[i] = quant_code_exact(x[i], scale, bits);
+    }
+  }
 }
 // low bytes of four ints -> one word (three byte permutes instead of four masks, three shifts and three ors)
 __device__ __forceinline__ uint32_t pack4_bytes(int a, int b, int c, int d) {
@@ -133,7 +150,7 @@ __global__ void __launch_bounds__(256) quant_span_kernel(const T* __restrict__ s
     Vec8<T>::load(src + e, x);
     int q[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = quant_code_fast(x[i], sc, inv, BITS);
+    quant_codes8(x, sc, inv, BITS, q);
     if (BITS == 8) {
       uint2 out;
       out.x = pack4_bytes(q[0], q[1], q[2], q[3]);
@@ -152,7 +169,7 @@ __global__ void __launch_bounds__(256) quant_span_kernel(const T* __restrict__ s
 // per block, every thread ISSUES its (up to four) 16-byte loads before the first use and keeps the raw words in registers for the
 // apply step.  The two-trip kernel above walks its span in a loop whose abs-max consumes each load right away -- four serialised
 // memory latencies per thread in the first trip and four more L2 latencies in the second: 21.5 us per 28 MB FLUX tensor, 0.30 of
-// the copy rate, with only ~1.5 waves of CTAs (profiles/r02bg_helpers.csv).  Same code rule (quant_code_fast): bit-exact.
+// the copy rate, with only ~1.5 waves of CTAs (profiles/r02bg_helpers.csv).  Same code rule (quant_codes8): bit-exact.
 // MEASURED: no faster -- 21.8 us against 21.5 us (profiles/r02bh_helpers_single.csv / _two.csv), so the latencies were not the
 // limit; what is left is the ~16 instructions per element of convert / scale / round / tie check / pack (8 M warp instructions per
 // tensor).  Kept as an opt-in (MFA_QUANT_SINGLE_TRIP=1) with its parity tests; the two-trip kernel stays the default.
@@ -201,8 +218,10 @@ __global__ void __launch_bounds__(256) quant_span_reg_kernel(const T* __restrict
     if (idx >= n) continue;
     const T* e = reinterpret_cast<const T*>(&raw[k]);
     int q[8];
+    float x[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = quant_code_fast(to_f32<T>(e[i]), sc, inv, BITS);
+    for (int i = 0; i < 8; ++i) x[i] = to_f32<T>(e[i]);
+    quant_codes8(x, sc, inv, BITS, q);
     if (BITS == 8) {
       uint2 out;
       out.x = pack4_bytes(q[0], q[1], q[2], q[3]);
@@ -251,7 +270,7 @@ __global__ void __launch_bounds__(256) quant_flat_kernel(const T* __restrict__ s
     Vec8<T>::load(src + i * 8, x);
     int q[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) q[k] = quant_code_fast(x[k], sc, inv, BITS);
+    quant_codes8(x, sc, inv, BITS, q);
     if (BITS == 8) {
       uint2 out;
       out.x = pack4_bytes(q[0], q[1], q[2], q[3]);
