@@ -95,6 +95,34 @@ def test_tc_flux_shape_one_head_vs_oracle(ctx):
     run_case(ctx, 1, 2, 4608, 4608, 128, "bf16", seed=5)
 
 
+@pytest.mark.parametrize("kind", ["add_bf16_per_head", "bool_packing"])
+def test_tc_flux_shape_staged_masks_vs_oracle(ctx, kind):
+    """BASELINE.json configs[1] geometry (N = 4608, D = 128, bf16) under a dense bf16 bias [1, H, N, N] and under a sequence-packing
+    bool mask [N, N] (36 KV steps per item through the TMA-staged mask tiles, hidden tiles skipped): forward (and, for the bias, backward) of two heads against the oracle"""
+    import umfa
+    B, H, S, D = 1, 2, 4608, 128
+    rng = np.random.default_rng(55)
+    q, k, v, g = (rng.standard_normal((B, H, S, D)).astype(np.float32) for _ in range(4))
+    (qa, qv), (ka, kv), (va, vv), (ga, gv) = (to_dtype(x, "bf16") for x in (q, k, v, g))
+    kw = {}
+    if kind == "bool_packing":
+        m = om = _packing_mask(S, 8)
+    else:
+        om, m = O.round_bf16((1.5 * rng.standard_normal((1, H, S, S))).astype(np.float32))
+        kw["mask_precision"] = "bf16"
+    out, lse = umfa.flash_attention_forward(ctx, qa, ka, va, input_precision="bf16", output_precision="fp32", layout="bhsd",
+                                            attn_mask=m, return_lse=True, **kw)
+    assert ctx.last_kernel == "fwd_tc_bf16_d128_tma_mask", ctx.last_kernel
+    ref, lref = O.attention_forward(qv, kv, vv, mask=om)
+    assert rel_max(out, ref) < 2e-2 and np.abs(lse - lref).max() < 2e-2
+    if kind == "bool_packing":
+        return                                 # (the fp64 oracle's backward at this size costs ~10 s: one mask kind is enough)
+    dq, dk, dv, _ = umfa.flash_attention_backward(ctx, ga, qa, ka, va, ref, lref, input_precision="bf16", attn_mask=m, **kw)
+    assert ctx.last_kernel == "bwd_tc_bf16_d128_tma_mask", ctx.last_kernel
+    rq, rk, rv, _ = O.attention_backward(qv, kv, vv, gv, mask=om)
+    assert max(rel_max(dq, rq), rel_max(dk, rk), rel_max(dv, rv)) < 2e-2
+
+
 def test_tc_matches_simt_bitwise_stats_close(ctx, monkeypatch):
     """Same inputs through the SIMT path (MFA_DISABLE_TC) and the tensor-core path agree within bf16 tolerance."""
     import umfa
