@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) quant_span_kernel(const T* __restrict__ s
                                                          uint32_t block_rows, uint64_t group_rows, uint32_t nb_per_group,
                                                          uint64_t nblocks, float floor_v) {
   __shared__ float red[8];
-  const int nworker = WARP ? 32 : 256;
+  const int nworker = WARP ? 32 : (int)blockDim.x;           // CTA variant: 256 or 128 threads (launcher)
   const int wid = WARP ? (threadIdx.x >> 5) : 0;
   const int lane = WARP ? (threadIdx.x & 31) : threadIdx.x;
   const uint64_t blk = WARP ? (uint64_t)blockIdx.x * 8 + wid : blockIdx.x;
@@ -138,8 +138,7 @@ __global__ void __launch_bounds__(256) quant_span_kernel(const T* __restrict__ s
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
     __syncthreads();
     amax = red[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) amax = fmaxf(amax, red[i]);
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) amax = fmaxf(amax, red[i]);
   }
   const float sc = make_scale(amax, BITS, floor_v);
   const float inv = inv_scale(sc);
@@ -531,8 +530,15 @@ cudaError_t quantize_typed(const T* src, uint8_t* codes, float* scales, uint64_t
       }
     } else {
       unsigned grid = (unsigned)nblocks;
-      if (bits == 8) quant_span_kernel<T, 8, false><<<grid, 256, 0, st>>>(src, codes, scales, rows, cols, br, group_rows, nb_per_group, nblocks, floor_v);
-      else quant_span_kernel<T, 4, false><<<grid, 256, 0, st>>>(src, codes, scales, rows, cols, br, group_rows, nb_per_group, nblocks, floor_v);
+      // CTA size: with 256 threads ~6 CTAs fit an SM (888 on the chip), so the 1728 blocks of a FLUX tensor run as two waves;
+      // 128-thread CTAs (13 per SM) hold them all at once -- and measure SLOWER, 20.3 against 18.2 us under ncu
+      // (profiles/r02bo_helpers_{128,256}.csv): the wave count is not what bounds this pass either.  MFA_QUANT_SPAN_THREADS=128 keeps
+      // the experiment reachable.
+      static int forced = -1;
+      if (forced < 0) { const char* e = getenv("MFA_QUANT_SPAN_THREADS"); forced = e ? atoi(e) : 0; }
+      const unsigned threads = forced == 128 ? 128u : 256u;
+      if (bits == 8) quant_span_kernel<T, 8, false><<<grid, threads, 0, st>>>(src, codes, scales, rows, cols, br, group_rows, nb_per_group, nblocks, floor_v);
+      else quant_span_kernel<T, 4, false><<<grid, threads, 0, st>>>(src, codes, scales, rows, cols, br, group_rows, nb_per_group, nblocks, floor_v);
     }
     ++g_launch_count;
     g_last_kernel = "quant_span";
