@@ -135,17 +135,26 @@ __global__ void __launch_bounds__(256) quant_span_kernel(const T* __restrict__ s
   const int lane = WARP ? (threadIdx.x & 31) : threadIdx.x;
   const uint64_t blk = WARP ? (uint64_t)blockIdx.x * 8 + wid : blockIdx.x;
   if (blk >= nblocks) return;
-  const uint64_t g = blk / nb_per_group, lb = blk % nb_per_group;
+  // (the block index fits 32 bits whenever the grid does: 32-bit division; inside the block everything is a 32-bit offset from the
+  // block's own base pointers -- the span is at most 65536 elements -- instead of 64-bit element indices into the tensor.  The ncu
+  // capture of this pass showed it instruction-bound, profiles/r02bp_ncu_quant_span.txt; the int8 call as a whole did not move with
+  // this change, 0.309 vs 0.308 ms, profiles/r02br_bench_quant.json, so the index arithmetic was not the larger part of it)
+  uint64_t g, lb;
+  if (blk <= 0xffffffffull) { const uint32_t b32 = (uint32_t)blk; g = b32 / nb_per_group; lb = b32 % nb_per_group; }
+  else { g = blk / nb_per_group; lb = blk % nb_per_group; }
   const uint64_t r0 = g * group_rows + lb * block_rows;
   uint64_t r1 = r0 + block_rows;
   if (r1 > (g + 1) * group_rows) r1 = (g + 1) * group_rows;
   if (r1 > rows) r1 = rows;
-  const uint64_t e0 = r0 * cols, e1 = r1 * cols;
+  const uint64_t e0 = r0 * cols;
+  const uint32_t n = (uint32_t)((r1 - r0) * cols), step = (uint32_t)nworker * 8;
+  const T* bsrc = src + e0;
+  uint8_t* bcodes = codes + (BITS == 8 ? e0 : (e0 >> 1));
 
   float amax = 0.f;
-  for (uint64_t e = e0 + (uint64_t)lane * 8; e < e1; e += (uint64_t)nworker * 8) {
+  for (uint32_t e = (uint32_t)lane * 8; e < n; e += step) {
     float x[8];
-    Vec8<T>::load(src + e, x);
+    Vec8<T>::load(bsrc + e, x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(x[i]));
   }
@@ -161,22 +170,21 @@ __global__ void __launch_bounds__(256) quant_span_kernel(const T* __restrict__ s
   const float inv = inv_scale(sc);
   if (lane == 0) scales[blk] = sc;
 
-  for (uint64_t e = e0 + (uint64_t)lane * 8; e < e1; e += (uint64_t)nworker * 8) {
+  for (uint32_t e = (uint32_t)lane * 8; e < n; e += step) {
     float x[8];
-    Vec8<T>::load(src + e, x);
+    Vec8<T>::load(bsrc + e, x);
     int q[8];
-#pragma unroll
     quant_codes8(x, sc, inv, BITS, q);
     if (BITS == 8) {
       uint2 out;
       out.x = pack4_bytes(q[0], q[1], q[2], q[3]);
       out.y = pack4_bytes(q[4], q[5], q[6], q[7]);
-      *reinterpret_cast<uint2*>(codes + e) = out;
+      *reinterpret_cast<uint2*>(bcodes + e) = out;
     } else {
       uint32_t out = 0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) out |= (uint32_t)((q[i] + 8) & 0xF) << (4 * i);
-      *reinterpret_cast<uint32_t*>(codes + (e >> 1)) = out;
+      *reinterpret_cast<uint32_t*>(bcodes + (e >> 1)) = out;
     }
   }
 }
@@ -285,7 +293,6 @@ __global__ void __launch_bounds__(256) quant_flat_kernel(const T* __restrict__ s
     float x[8];
     Vec8<T>::load(src + i * 8, x);
     int q[8];
-#pragma unroll
     quant_codes8(x, sc, inv, BITS, q);
     if (BITS == 8) {
       uint2 out;
