@@ -243,3 +243,27 @@ def test_headline_forward_kernels_do_not_spill():
             seen += 1
             assert stack == 0, (m.group(1), stack)
     assert seen >= 8
+
+
+def test_staged_mask_kernels_exist_and_do_not_spill():
+    """The instantiations that stage external-mask tiles in shared memory (MASKED = 2: forward bf16 / fp16 at both head-dim
+    widths, both backward kernels) are in the library and keep their working set in registers."""
+    import re
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    lib_dir = os.path.join(ROOT, "universal-metal-flash-attention_b200", "lib")
+    if not os.path.exists(cuobjdump) or not os.path.exists(os.path.join(lib_dir, "attn_fwd_tc.o")):
+        pytest.skip("cuobjdump or the object files are not available")
+    fwd = subprocess.run([cuobjdump, "-res-usage", os.path.join(lib_dir, "attn_fwd_tc.o")], capture_output=True, text=True).stdout
+    seen = set()
+    for m in re.finditer(r"Function \S*fwd_tc_kernelILi(\d+)ELi([01])ELi(\d+)ELb0ELi2E\S*:\s*\n\s*REG:(\d+) STACK:(\d+)", fwd):
+        assert int(m.group(5)) == 0, m.group(0)
+        seen.add((int(m.group(1)), int(m.group(2))))
+    assert seen == {(64, 0), (64, 1), (128, 0), (128, 1)}
+    bwd = subprocess.run([cuobjdump, "-res-usage", os.path.join(lib_dir, "attn_bwd_tc.o")], capture_output=True, text=True).stdout
+    seen = set()
+    for m in re.finditer(r"Function \S*bwd_(dkv|dq)_tc_kernelILi(\d+)ELb([01])ELi2E\S*:\s*\n\s*REG:(\d+) STACK:(\d+)", bwd):
+        assert int(m.group(5)) == 0, m.group(0)
+        seen.add((m.group(1), int(m.group(2)), int(m.group(3))))
+    assert len(seen) == 8, seen
